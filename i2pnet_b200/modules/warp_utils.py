@@ -1,0 +1,33 @@
+"""Quaternion helpers (mirror of src/modules/warp_utils.py: inv_q :10, mul_q :25, warp_quat_xyz
+:78).  Device-agnostic: the reference hard-codes `.cuda()` on its constant tensors (:5,:18-19),
+which pins everything to the current device."""
+import torch
+
+
+def inv_q(q):
+    """q (B,1,4) or (B,4) -> conj(q) / (|q|^2 + 1e-10), (B,4)"""
+    q = q.reshape(q.shape[0], 4)
+    q_2 = torch.sum(q * q, dim=-1, keepdim=True) + 1e-10
+    return torch.cat([q[:, :1], -q[:, 1:]], dim=-1) / q_2
+
+
+def mul_q(q_a, q_b):
+    """Hamilton product with broadcasting over the point axis: (B,1|N,4) x (B,1|N,4) -> (B,N,4)"""
+    if q_a.ndim == 2:
+        q_a = q_a.unsqueeze(1)
+    if q_b.ndim == 2:
+        q_b = q_b.unsqueeze(1)
+    a0, a1, a2, a3 = q_a.unbind(-1)
+    b0, b1, b2, b3 = q_b.unbind(-1)
+    return torch.stack([a0 * b0 - a1 * b1 - a2 * b2 - a3 * b3,
+                        a0 * b1 + a1 * b0 + a2 * b3 - a3 * b2,
+                        a0 * b2 - a1 * b3 + a2 * b0 + a3 * b1,
+                        a0 * b3 + a1 * b2 - a2 * b1 + a3 * b0], dim=-1)
+
+
+def warp_quat_xyz(lidar_xyz, Hi_quat, H_trans):
+    """p' = q [0,p] q^-1 + [0,t] for lidar_xyz (B,N,3), Hi_quat (B,4), H_trans (B,4) -> (B,N,3)"""
+    B, N, _ = lidar_xyz.shape
+    homo = torch.cat([lidar_xyz.new_zeros(B, N, 1), lidar_xyz], -1)
+    homo = mul_q(mul_q(Hi_quat, homo), inv_q(Hi_quat)) + H_trans.reshape(B, 1, 4)
+    return homo[:, :, 1:4]

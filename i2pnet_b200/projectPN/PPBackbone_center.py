@@ -1,0 +1,364 @@
+"""Projection-aware building blocks of the large-range model (mirror of the reference's
+src/projectPN/PPBackbone_center.py: Conv2d :10, ProjectPointNet :54, ProjSetUpconvModule :208,
+CostVolume :305, PoseHead :503, FlowPredictor :566).
+
+Constructor arguments, forward signatures, return tuples and parameter names (hence
+state_dict keys: `mlp_convs.0.conv.weight`, `...bn_linear.bias`, `hidden_layer.
+composed_module.0.weight`, ...) are the reference's, so checkpoints and the unchanged model
+assembly interchange.  The data flow underneath is re-designed:
+
+* tensors stay channels-last (B, N, K, C) end to end: the shared MLP is a row-major GEMM
+  + batch-statistics normalisation on that layout, not the reference's permute -> NCHW 1x1
+  conv -> BatchNorm2d -> permute sandwich (:35-46);
+* neighbourhoods come from the warp-per-centre select kernel as one int32 flat index (no
+  int64 (b,h,w) triples, no zero-filled `valid_idx` buffers) and are fetched with the
+  vectorised row gather, whose backward is a vector red.add scatter;
+* centres of a regular stride grid are a strided view, not a gather;
+* the cost volume never materialises the reference's `repeat`ed (B,N,K,C) operands.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..modules.basicConv import Conv1d
+from .utils import (FLAG_COPY, FLAG_SHIFT, StrideGrid, check_valid, gather_rows, gather_torch, knn_point,
+                    select_flat)
+
+
+class Conv2d(nn.Module):
+    """1x1 conv (+ batch-statistics BN) (+ ReLU / LeakyReLU(0.1)) over the last axis of a
+    channels-last (b, n, s, c) tensor.  `conv` / `bn_linear` hold the parameters under the
+    reference's names; with use_bn_input the norm always uses the statistics of the current
+    batch, in eval() too (track_running_stats=False, PPBackbone_center.py:30)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=None, bn=False, activation_fn=True,
+                 leaky_relu=True, use_bn_input=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride = kernel_size, stride if stride is not None else [1, 1]
+        self.bn, self.activation_fn, self.use_bn_input, self.leaky_relu = bn, activation_fn, use_bn_input, leaky_relu
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, self.stride)
+        if bn:
+            self.bn_linear = nn.BatchNorm2d(out_channels, track_running_stats=not use_bn_input)
+        if activation_fn:
+            self.relu = nn.ReLU(inplace=True) if not leaky_relu else nn.LeakyReLU(0.1, inplace=True)
+
+    def forward(self, x):
+        lead = x.shape[:-1]
+        y = F.linear(x.reshape(-1, self.in_channels), self.conv.weight.view(self.out_channels, self.in_channels),
+                     self.conv.bias)
+        if self.bn:
+            y = _batch_norm_rows(y, self.bn_linear)
+        if self.activation_fn:
+            y = self.relu(y)
+        return y.view(*lead, self.out_channels)
+
+    def set_bn(self):
+        if self.bn:
+            self.bn_linear.track_running_stats = not self.use_bn_input
+            self.bn_linear.training = True
+
+
+def _batch_norm_rows(y, m):
+    """BatchNorm over the rows of y (rows, C) with the parameters / buffers of the BatchNorm2d `m`.
+    Batch statistics (biased variance, as nn.BatchNorm2d normalises) unless m tracks running
+    statistics and is in eval mode.  Statistics come from torch.var_mean (a stable pairwise /
+    Welford reduction on both devices); F.batch_norm's 2-D CPU path accumulates in f32 and is
+    off by 1e-3 on 2e5 rows."""
+    if m.training or not m.track_running_stats:
+        var, mean = torch.var_mean(y, dim=0, unbiased=False)
+        if m.track_running_stats and m.training:
+            with torch.no_grad():
+                mom = m.momentum if m.momentum is not None else 0.1
+                n = y.shape[0]
+                m.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+                m.running_var.mul_(1 - mom).add_(var * (n / max(n - 1, 1)), alpha=mom)
+                m.num_batches_tracked += 1
+    else:
+        mean, var = m.running_mean, m.running_var
+    scale = torch.rsqrt(var + m.eps)
+    if m.weight is not None:
+        return (y - mean) * (scale * m.weight) + m.bias
+    return (y - mean) * scale
+
+
+def _centres(sample_idx, B, out_h, out_w, stride_H, stride_W, device):
+    return sample_idx if sample_idx is not None else StrideGrid(B, out_h, out_w, stride_H, stride_W, device)
+
+
+def _take_centres(image, sample_idx, B, H, W):
+    if isinstance(sample_idx, StrideGrid):
+        return sample_idx.take(image).contiguous()
+    return gather_torch(image, *sample_idx, B, H, W)
+
+
+def _centre_index(sample_idx, B, out_h, out_w):
+    """What the select kernel needs: the grid itself, or (B,N,2) int32 for an explicit triple."""
+    if isinstance(sample_idx, StrideGrid):
+        return sample_idx
+    _, h, w = sample_idx
+    return torch.stack([h, w], dim=-1).reshape(B, out_h * out_w, 2).to(torch.int32)
+
+
+class ProjectPointNet(nn.Module):
+    """Set abstraction on the range image: stride-grid centres, K nearest inside a window,
+    shared MLP, max over K."""
+
+    def __init__(self, H, W, out_h, out_w, stride_H, stride_W, kernel_size, nsample, distance, in_channel, mlp,
+                 use_trans=False, use_bn_p=True, use_bn_input=True):
+        super().__init__()
+        self.H, self.W, self.out_h, self.out_w = H, W, out_h, out_w
+        self.stride_H, self.stride_W = stride_H, stride_W
+        self.kernel_size, self.distance, self.nsample, self.usetrans = kernel_size, distance, nsample, use_trans
+        self.mlp_convs = nn.ModuleList()
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(Conv2d(last_channel, out_channel, kernel_size=(1, 1), bn=use_bn_p,
+                                         leaky_relu=False, use_bn_input=use_bn_input))
+            last_channel = out_channel
+
+    def _group(self, xyz_proj_raw, xyz_proj, sample_idx, raw_feat_point):
+        B = xyz_proj.shape[0]
+        n = self.out_h * self.out_w
+        sample_idx = _centres(sample_idx, B, self.out_h, self.out_w, self.stride_H, self.stride_W, xyz_proj.device)
+        new_xyz_proj = _take_centres(xyz_proj, sample_idx, B, self.H, self.W)
+        new_xyz_proj_raw = _take_centres(xyz_proj_raw, sample_idx, B, self.H, self.W)
+        xyz_pr = xyz_proj if self.usetrans else xyz_proj_raw
+        flat, _ = select_flat(xyz_pr, xyz_pr, _centre_index(sample_idx, B, self.out_h, self.out_w),
+                              self.kernel_size, self.nsample, FLAG_SHIFT | FLAG_COPY, self.distance)
+        src, ctr = (xyz_proj_raw, new_xyz_proj_raw) if raw_feat_point else (xyz_proj, new_xyz_proj)
+        grouped_xyz = gather_rows(src, flat)                        # B,N,K,3
+        grouped_xyz_norm = grouped_xyz - ctr.reshape(B, n, 1, 3)
+        return sample_idx, new_xyz_proj_raw, new_xyz_proj, flat, grouped_xyz, grouped_xyz_norm
+
+    def _mlp_max(self, new_points, B):
+        for conv in self.mlp_convs:
+            new_points = conv(new_points)
+        return torch.max(new_points, dim=2)[0].view(B, self.out_h, self.out_w, -1)
+
+    def forward(self, xyz_proj_raw, xyz_proj, feature_proj, sample_idx=None, cfg=None, raw_feat_point=False):
+        """xyz_proj_raw / xyz_proj (B,H,W,3), feature_proj (B,H,W,C) ->
+        (new_xyz_proj_raw, new_xyz_proj (B,h,w,3), new_points (B,h,w,mlp[-1]), grouped_xyz, sample_idx)"""
+        B = xyz_proj.shape[0]
+        sample_idx, new_raw, new_xyz, flat, grouped_xyz, norm = self._group(xyz_proj_raw, xyz_proj, sample_idx,
+                                                                            raw_feat_point)
+        grouped_points = gather_rows(feature_proj, flat)            # B,N,K,C
+        new_points = self._mlp_max(torch.cat([norm, grouped_points], -1), B)
+        return new_raw, new_xyz, new_points, grouped_xyz, sample_idx
+
+    def forward_center(self, xyz_proj_raw, xyz_proj, feature_proj, sample_idx=None, cfg=None, using_intens=False,
+                       raw_feat_point=False):
+        """First level: the feature is geometric only -- (offset, centre, neighbour, |offset|) = 10
+        channels (+ feature_proj when using_intens).  The reference also gathers feature_proj when
+        it is not used (:157); this does not."""
+        B = xyz_proj.shape[0]
+        sample_idx, new_raw, new_xyz, flat, grouped_xyz, norm = self._group(xyz_proj_raw, xyz_proj, sample_idx,
+                                                                            raw_feat_point)
+        centre = new_xyz.reshape(B, self.out_h * self.out_w, 1, 3).expand(-1, -1, norm.shape[2], -1)
+        dist = torch.norm(norm, p=2, dim=3, keepdim=True)
+        parts = [norm, centre, grouped_xyz, dist]
+        if using_intens:
+            parts.append(gather_rows(feature_proj, flat))
+        new_points = self._mlp_max(torch.cat(parts, -1), B)
+        return new_raw, new_xyz, new_points, grouped_xyz, sample_idx
+
+    def set_bn(self):
+        for conv in self.mlp_convs:
+            conv.set_bn()
+
+
+class ProjSetUpconvModule(nn.Module):
+    """Feature propagation from a coarse level (xyz2, feat2) to a finer one (xyz1, feat1)."""
+
+    def __init__(self, H, W, out_h, out_w, stride_H, stride_W, kernel_size, nsample, distance, in_channels, mlp,
+                 mlp2, use_trans=False, use_bn_p=True, use_bn_input=True):
+        super().__init__()
+        self.nsample, self.mlp, self.mlp2 = nsample, mlp, mlp2
+        self.H, self.W, self.out_h, self.out_w = H, W, out_h, out_w
+        self.stride_H, self.stride_W = stride_H, stride_W
+        self.kernel_size, self.distance, self.use_trans = kernel_size, distance, use_trans
+        self.last_channel = in_channels[-1] + 3
+        self.mlp_conv = nn.ModuleList()
+        self.mlp2_conv = nn.ModuleList()
+        if mlp is not None:
+            for c in mlp:
+                self.mlp_conv.append(Conv2d(self.last_channel, c, [1, 1], stride=[1, 1], bn=use_bn_p,
+                                            use_bn_input=use_bn_input))
+                self.last_channel = c
+        self.last_channel = (mlp[-1] if len(mlp) > 0 else self.last_channel) + in_channels[0]
+        if mlp2 is not None:
+            for c in mlp2:
+                self.mlp2_conv.append(Conv2d(self.last_channel, c, [1, 1], stride=[1, 1], bn=use_bn_p,
+                                             use_bn_input=use_bn_input))
+                self.last_channel = c
+
+    def forward(self, xyz1_raw, xyz2_raw, xyz1, xyz2, idx_n2, feat1, feat2, cfg=None, raw_feat_point=False):
+        """xyz1* (B,out_h,out_w,3), xyz2* (B,H,W,3), idx_n2 (B,out_h*out_w,2) int32 (or a StrideGrid),
+        feat1 (B,out_h,out_w,c1), feat2 (B,H,W,c2) -> (B, out_h*out_w, mlp2[-1])"""
+        B = xyz1.shape[0]
+        n = self.out_h * self.out_w
+        xyz1_pr, xyz2_pr = (xyz1, xyz2) if self.use_trans else (xyz1_raw, xyz2_raw)
+        flat, _ = select_flat(xyz1_pr, xyz2_pr, idx_n2, self.kernel_size, self.nsample, FLAG_SHIFT | FLAG_COPY,
+                              self.distance, self.stride_H, self.stride_W)
+        src2, src1 = (xyz2_raw, xyz1_raw) if raw_feat_point else (xyz2, xyz1)
+        xyz_diff = gather_rows(src2, flat) - src1.reshape(B, n, 1, 3)
+        upfeats = torch.cat([gather_rows(feat2, flat), xyz_diff], dim=3)   # B,N,K,C+3
+        if self.mlp is not None:
+            for conv in self.mlp_conv:
+                upfeats = conv(upfeats)
+        feat1_new = torch.max(upfeats, dim=2)[0].view(B, self.out_h, self.out_w, -1)
+        if feat1 is not None:
+            feat1_new = torch.cat([feat1_new, feat1], dim=3)
+        if self.mlp2 is not None:
+            for conv in self.mlp2_conv:
+                feat1_new = conv(feat1_new)
+        return feat1_new.reshape(B, n, -1)
+
+    def set_bn(self):
+        for conv in list(self.mlp_conv) + list(self.mlp2_conv):
+            conv.set_bn()
+
+
+def _standardise(x):
+    """(x - mean) / max(std, 1e-12) over the channel axis, unbiased std (:384-389)."""
+    return (x - x.mean(-1, keepdim=True)) / torch.clip(x.std(-1, keepdim=True), min=1e-12)
+
+
+class CostVolume(nn.Module):
+    """2D-3D cost volume: every LiDAR point attends over image pixels (all of them, or its
+    nsample_q nearest on the normalised plane), then over its nsample 3-D neighbours."""
+
+    def __init__(self, H, W, kernel_size, distance, nsample, nsample_q, rgb_in_channels, lidar_in_channels, mlp1,
+                 mlp2, backward_validation=False, use_trans=False, use_bn_p=True, use_bn_input=True):
+        super().__init__()
+        self.H, self.W, self.nsample, self.nsample_q, self.distance = H, W, nsample, nsample_q, distance
+        self.mlp1, self.mlp2, self.kernel_size = mlp1, mlp2, kernel_size
+        self.backward_validation, self.use_trans = backward_validation, use_trans
+        kw = dict(stride=[1, 1], bn=use_bn_p, use_bn_input=use_bn_input)
+        self.in_channels = rgb_in_channels + (lidar_in_channels if backward_validation else 0) + 6
+        self.mlp1_convs, self.mlp2_convs, self.mlp2_convs_2 = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        for c in mlp1:
+            self.mlp1_convs.append(Conv2d(self.in_channels, c, [1, 1], **kw))
+            self.in_channels = c
+        self.pi_encoding = Conv2d(6, mlp1[-1], [1, 1], **kw)
+        self.in_channels = 2 * mlp1[-1]
+        for c in mlp2:
+            self.mlp2_convs.append(Conv2d(self.in_channels, c, [1, 1], **kw))
+            self.in_channels = c
+        self.pc_encoding = Conv2d(10, mlp1[-1], [1, 1], **kw)
+        self.in_channels = 2 * mlp1[-1] + lidar_in_channels
+        for c in mlp2:
+            self.mlp2_convs_2.append(Conv2d(self.in_channels, c, [1, 1], **kw))
+            self.in_channels = c
+
+    def forward(self, xyz_proj_raw, warped_xyz, warped_points, idx_n2, f2_xyz, f2_points, lidar_z, cfg=None):
+        """warped_xyz (B,HW,3) on the normalised plane, warped_points (B,HW,C), idx_n2 (B,HW,2),
+        f2_xyz (B,N2,3), f2_points (B,N2,C), lidar_z (B,HW,1) -> (B,H,W,mlp2[-1])"""
+        B, N, C = warped_points.shape
+        if self.nsample_q > 0:
+            idx = knn_point(self.nsample_q, f2_xyz.contiguous(), warped_xyz.contiguous()).to(torch.int32)
+            qi_xyz = gather_rows(f2_xyz, idx)                       # B,N,K,3
+            qi_points = gather_rows(f2_points, idx)                 # B,N,K,C
+        else:
+            qi_xyz = f2_xyz.unsqueeze(1).expand(-1, N, -1, -1)      # B,N,N2,3
+            qi_points = f2_points.unsqueeze(1)                      # B,1,N2,C (broadcast over points)
+        K = qi_xyz.shape[2]
+        warped_xyz = warped_xyz.mul(lidar_z)                        # restore depth (:379)
+        pi_xyz_diff_concat = torch.cat([warped_xyz[:, :, None, :].expand(-1, -1, K, -1), qi_xyz], dim=3)
+
+        pi_n = _standardise(warped_points)[:, :, None, :]           # B,N,1,C
+        qi_n = _standardise(qi_points)                              # B,(1|N),K,C
+        corr = pi_n * qi_n                                          # B,N,K,C
+        parts = [pi_xyz_diff_concat, corr]
+        if self.backward_validation:
+            valid = check_valid(warped_xyz).unsqueeze(-1)           # B,N,1,1
+            masked = corr * valid + -1e10 * (1 - valid)
+            parts.append(torch.max(masked, 1, keepdim=True)[0].expand(-1, N, -1, -1))
+        pi_feat1_new = torch.cat(parts, dim=3)
+        for conv in self.mlp1_convs:
+            pi_feat1_new = conv(pi_feat1_new)
+        pi_concat = torch.cat([self.pi_encoding(pi_xyz_diff_concat), pi_feat1_new], dim=3)
+        for conv in self.mlp2_convs:
+            pi_concat = conv(pi_concat)
+        pi_feat1_new = torch.sum(F.softmax(pi_concat, dim=2) * pi_feat1_new, dim=2)   # B,N,mlp1[-1]
+
+        # second stage: re-weight over the nsample 3-D neighbours of every point
+        warped_xyz_bhw = warped_xyz.view(B, self.H, self.W, 3)
+        xyz_pr = warped_xyz_bhw if self.use_trans else xyz_proj_raw
+        flat, valid_mask = select_flat(xyz_pr, xyz_pr, idx_n2, self.kernel_size, self.nsample, FLAG_SHIFT,
+                                       self.distance)
+        pc_xyz_grouped = gather_rows(warped_xyz_bhw, flat)           # B,N,K,3
+        pc_points_grouped = gather_rows(pi_feat1_new, flat)          # B,N,K,mlp1[-1]
+        pc_xyz_new = warped_xyz[:, :, None, :].expand(-1, -1, self.nsample, -1)
+        pc_points_new = warped_points[:, :, None, :].expand(-1, -1, self.nsample, -1)
+        pc_xyz_diff = pc_xyz_grouped - pc_xyz_new
+        pc_euc_diff = torch.sqrt(torch.sum(pc_xyz_diff * pc_xyz_diff, dim=3, keepdim=True) + 1e-20)
+        pc_xyz_encoding = self.pc_encoding(torch.cat([pc_xyz_new, pc_xyz_grouped, pc_xyz_diff, pc_euc_diff], dim=3))
+        pc_concat = torch.cat([pc_xyz_encoding, pc_points_new, pc_points_grouped], dim=-1)
+        for conv in self.mlp2_convs_2:
+            pc_concat = conv(pc_concat)
+        pc_concat = pc_concat * valid_mask + -1e10 * (1 - valid_mask)
+        pc_feat1_new = torch.sum(F.softmax(pc_concat, dim=2) * pc_points_grouped, dim=2)
+        return pc_feat1_new.view(B, self.H, self.W, -1)
+
+    def set_bn(self):
+        for conv in list(self.mlp2_convs) + list(self.mlp1_convs) + list(self.mlp2_convs_2):
+            conv.set_bn()
+        self.pc_encoding.set_bn()
+        self.pi_encoding.set_bn()
+
+
+class PoseHead(nn.Module):
+    """Mask-weighted pooling over points -> hidden -> (unit quaternion, translation)."""
+
+    def __init__(self, in_channels, mlp1, mlp2, hidden, q_dim, t_dim, dropout_rate=0.5, split_dp=False,
+                 pos_embed=False, sigmoid=False, maxhead=False):
+        super().__init__()
+        self.sigmoid, self.maxhead, self.pos_embed = sigmoid, maxhead, pos_embed
+        in_channel, _ = in_channels
+        self.DP1 = nn.Identity() if split_dp else nn.Dropout(dropout_rate)
+        self.DP2 = nn.Dropout(dropout_rate) if split_dp else nn.Identity()
+        self.hidden_layer = Conv1d(in_channel, hidden, use_activation=False)
+        self.quat_head = Conv1d(hidden, q_dim, use_activation=False)
+        self.trans_head = Conv1d(hidden, t_dim, use_activation=False)
+
+    def forward(self, prediction, mask, xyz, feature, projection_mask):
+        """prediction, mask (B,N,C) -> q (B,4), t (B,3), mask_p (B,N,C)"""
+        if not self.sigmoid:
+            if projection_mask is not None:
+                projection_mask = torch.argmax(projection_mask.detach(), dim=-1, keepdim=True).float()
+                mask = mask * projection_mask + -1e10 * (1. - projection_mask)
+        else:
+            prediction = prediction * projection_mask
+        if self.maxhead:
+            mask = torch.max(mask, dim=-1, keepdim=True)[0]
+        mask_p = F.softmax(mask, dim=1)
+        pooled = torch.sum(prediction * mask_p, dim=1, keepdim=True)      # B,1,C
+        hidden = self.DP1(self.hidden_layer(pooled))
+        q = self.quat_head(self.DP2(hidden)).squeeze(1)
+        t = self.trans_head(self.DP2(hidden)).squeeze(1)
+        q = q / (torch.sqrt(torch.sum(q * q, dim=-1, keepdim=True) + 1e-10) + 1e-10)
+        return q, t, mask_p
+
+
+class FlowPredictor(nn.Module):
+    """Per-point MLP over the concatenation [points_f1, cost_volume, upsampled_feat]."""
+
+    def __init__(self, in_channels, mlp, is_training, bn_decay, bn=True, use_bn_input=True):
+        super().__init__()
+        self.in_channels, self.mlp, self.is_training, self.bn_decay, self.bn = in_channels, mlp, is_training, bn_decay, bn
+        self.mlp_conv = nn.ModuleList()
+        for c in mlp:
+            self.mlp_conv.append(Conv2d(self.in_channels, c, [1, 1], stride=[1, 1], bn=bn, use_bn_input=use_bn_input))
+            self.in_channels = c
+
+    def forward(self, points_f1, upsampled_feat, cost_volume):
+        parts = [points_f1, cost_volume] + ([upsampled_feat] if upsampled_feat is not None else [])
+        x = torch.cat(parts, -1).unsqueeze(2)
+        for conv in self.mlp_conv:
+            x = conv(x)
+        return x.squeeze(2)
+
+    def set_bn(self):
+        for conv in self.mlp_conv:
+            conv.set_bn()

@@ -1,0 +1,137 @@
+/*
+ * i2p_b200.h -- C ABI of libi2p_b200.so: the I2PNet hot-path operators as hand-written
+ * sm_100a CUDA kernels.
+ *
+ * Conventions (they mirror the reference's pybind layer):
+ *   - every pointer is a DEVICE pointer into memory the caller owns; outputs are written
+ *     in place and the library keeps no reference to them;
+ *   - tensors are dense, row-major ("contiguous"), float = IEEE f32, indices int32 unless
+ *     the reference's binding uses int64 (the fused select outputs, kNN);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream), never synchronises, never allocates, and is therefore
+ *     capturable into a CUDA graph;
+ *   - return value: 0 on success, I2P_ERR_* otherwise.  Nothing calls exit(); the
+ *     reference's launchers do (e.g. pointnet2/src/group_points_gpu.cu:81-85).
+ *   - `citations` are relative to the reference repository IRMVLab/I2PNet.
+ */
+#ifndef I2P_B200_H
+#define I2P_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I2P_OK 0
+#define I2P_ERR_INVALID_ARGUMENT 1 /* shape / size outside what the operator defines      */
+#define I2P_ERR_UNSUPPORTED 2      /* defined by the reference but beyond this build       */
+#define I2P_ERR_CUDA 3             /* a CUDA runtime error; see i2p_last_error()           */
+
+#define I2P_FLAG_COPY 1  /* fused_conv_select_k.py:6 */
+#define I2P_FLAG_SHIFT 2 /* fused_conv_select_k.py:7 */
+
+/* Human-readable description of the last error raised on the calling thread. */
+const char *i2p_last_error(void);
+/* ABI version of this header (bumped when a signature changes). */
+int i2p_abi_version(void);
+/* Number of kernel launches issued through this library since load (all threads). */
+uint64_t i2p_launch_count(void);
+
+/* ---- PointNet++ operators: replace pointnet2/src/pointnet2_api.cpp:10-24 ------------- */
+
+/* furthest_point_sampling_wrapper  (pointnet2/src/sampling.cpp:40-51, sampling_gpu.cu:93-253)
+ * dataset (B,N,3); temp (B,N) scratch pre-filled by the caller with 1e10 (on return it
+ * holds each point's squared distance to the sampled set, as the reference leaves it);
+ * idxs (B,M).  Starts at index 0; ties resolve exactly as the reference's tree reduction. */
+int i2p_furthest_point_sampling(int b, int n, int m, const float *dataset, float *temp, int32_t *idxs,
+                                void *stream);
+
+/* gather_points_wrapper / _grad_wrapper  (sampling.cpp:11-37, sampling_gpu.cu:8-79)
+ * points (B,C,N), idx (B,M) -> out (B,C,M);  grad_out (B,C,M) -> grad_points (B,C,N) += */
+int i2p_gather_points(int b, int c, int n, int npoints, const float *points, const int32_t *idx, float *out,
+                      void *stream);
+int i2p_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int32_t *idx,
+                           float *grad_points, void *stream);
+
+/* ball_query_wrapper  (ball_query.cpp:14-31, ball_query_gpu.cu:9-66)
+ * new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample), pre-zeroed by the caller. */
+int i2p_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
+                   int32_t *idx, void *stream);
+
+/* group_points_wrapper / _grad_wrapper  (group_points.cpp:10-44, group_points_gpu.cu:8-86)
+ * points (B,C,N), idx (B,npoints,nsample) -> out (B,C,npoints,nsample); grad: += */
+int i2p_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int32_t *idx,
+                     float *out, void *stream);
+int i2p_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                          const int32_t *idx, float *grad_points, void *stream);
+
+/* three_nn_wrapper  (interpolate.cpp:14-27, interpolate_gpu.cu:9-73)
+ * unknown (B,N,3), known (B,M,3) -> dist2 (B,N,3) SQUARED distances, idx (B,N,3) */
+int i2p_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx,
+                 void *stream);
+
+/* three_interpolate_wrapper / _grad_wrapper  (interpolate.cpp:30-60, interpolate_gpu.cu:77-160)
+ * points (B,C,M), idx/weight (B,N,3) -> out (B,C,N);  grad_out (B,C,N) -> grad_points (B,C,M) += */
+int i2p_three_interpolate(int b, int c, int m, int n, const float *points, const int32_t *idx,
+                          const float *weight, float *out, void *stream);
+int i2p_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int32_t *idx,
+                               const float *weight, float *grad_points, void *stream);
+
+/* knn_wrapper -- called by pointnet2/pointnet2_utils.py:32 but never bound by the reference.
+ * unknown (B,N,3), known (B,M,3) -> dist2 (B,N,k) squared distances ascending, idx (B,N,k). */
+int i2p_knn(int b, int n, int m, int k, const float *unknown, const float *known, float *dist2, int32_t *idx,
+            void *stream);
+
+/* ---- projection-aware operators: replace src/projectPN ------------------------------ */
+
+/* fused_conv_select_k  (fused_conv_select/fused_conv_g.cpp:15-67, fused_conv_go.cu:11-264)
+ * xyz1 (B,H,W,3), xyz2 (B,small_h,small_w,3), idx_n2 (B,npoints,2) centre (h,w) in xyz1,
+ * random_hw (kH*kW) window visiting order -> selected_{b,h,w}_idx (B,npoints,K) int64 and
+ * selected_mask (B,npoints,K) f32, all pre-zeroed by the caller and only partially written,
+ * exactly as the reference does.  The reference's valid_idx / valid_in_dis_idx arguments are
+ * never written by it (fused_conv_go.cu:150,167) and are therefore not part of this ABI. */
+int i2p_fused_conv_select_k(int batch, int H, int W, int npoints, int kH, int kW, int K, int flag,
+                            float distance, int stride_h, int stride_w, const float *xyz1, const float *xyz2,
+                            const int32_t *idx_n2, const int32_t *random_hw, int64_t *selected_b_idx,
+                            int64_t *selected_h_idx, int64_t *selected_w_idx, float *selected_mask,
+                            int small_h, int small_w, void *stream);
+
+/* Same selection, compact output for the fused consumers below: flat = h*small_w + w as int32
+ * (B,npoints,K) and mask (B,npoints,K); both FULLY written (0 where the reference leaves its
+ * pre-zeroed buffers untouched).  Centres are the regular grid (h*stride_ch, w*stride_cw),
+ * out_h x out_w of them, as built by get_stride_idx_cuda (src/projectPN/utils.py:28-33) when
+ * idx_n2 == NULL. */
+int i2p_select_k_flat(int batch, int H, int W, int npoints, int kH, int kW, int K, int flag, float distance,
+                      int stride_h, int stride_w, const float *xyz1, const float *xyz2, const int32_t *idx_n2,
+                      int out_w, int stride_ch, int stride_cw, int32_t *flat_idx, float *mask, int small_h,
+                      int small_w, void *stream);
+
+/* gather_torch  (src/projectPN/utils.py:36-60): feature (B,HW,C) channels-last, flat index
+ * (B,M) int32 -> out (B,M,C).  Backward: grad_feature (B,HW,C) += scatter of grad_out. */
+int i2p_gather_rows(int b, int hw, int c, int m, const float *feature, const int32_t *flat_idx, float *out,
+                    void *stream);
+int i2p_gather_rows_grad(int b, int hw, int c, int m, const float *grad_out, const int32_t *flat_idx,
+                         float *grad_feature, void *stream);
+
+/* knn_point  (src/projectPN/utils.py:344-380; twins src/modules/point_utils.py:114-177,
+ * pointnet_util.py:14-57): the nsample nearest of xyz (B,N,3) for each new_xyz (B,S,3) under
+ * dist = -2 q.x + |q|^2 + |x|^2 (f32), returned sorted by (dist, index) as int64 (B,S,nsample).
+ * The reference's order is unspecified (topk sorted=False).  dist_out may be NULL. */
+int i2p_knn_point(int b, int n, int s, int nsample, const float *xyz, const float *new_xyz, int64_t *group_idx,
+                  float *dist_out, void *stream);
+
+/* project_seq with rank=False  (src/projectPN/utils.py:111-187): spherical range-image
+ * scatter.  xyz (B,N,3) -> cell (row,col) by the reference's truncating formulas; each of the
+ * nfeat feature arrays feat[j] (B,N,fdim[j]) and xyz itself are written to (B,H,W,.) images,
+ * zero where no point lands.  Duplicate cells: the highest point index wins (the reference's
+ * index_put_ is last-writer-wins on CPU and unordered on CUDA).  owner (B,H,W) int32 scratch.
+ * feats / outs: DEVICE-resident float pointers passed by value in host arrays. */
+int i2p_project_seq(int b, int n, int H, int W, float fup_deg, float fdown_deg, const float *xyz, int nfeat,
+                    const float *const *feats, const int *fdims, float *xyz_proj, float *const *feat_projs,
+                    int32_t *owner, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2P_B200_H */

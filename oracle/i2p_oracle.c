@@ -19,6 +19,7 @@
  * section 2.2).  This file spells that with fmaf() and must be compiled with
  * -ffp-contract=off so that gcc adds no contraction of its own.
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -336,5 +337,41 @@ void orc_gather_rows_grad(int b, int hw, int c, int m, const float *grad_out, co
             float *g = grad_feat + ((size_t)bi * hw + idx[(size_t)bi * m + p]) * c;
             const float *go = grad_out + ((size_t)bi * m + p) * c;
             for (int ci = 0; ci < c; ++ci) g[ci] += go[ci];
+        }
+}
+
+/* ------------------------------------------------------------------------- */
+/* project_seq with rank=False: src/projectPN/utils.py:111-187.
+ * f32 arithmetic as torch evaluates it on CUDA: scalars are computed in double by the Python
+ * code (:125-139) and cast to f32 where they meet f32 tensors; a division by a Python scalar
+ * is a multiplication by its f32 reciprocal (ATen BinaryDivTrueKernel.cu, cpu-scalar fast
+ * path).  Duplicate cells: the highest point index wins (index_put_ on CPU is sequential,
+ * last writer wins; on CUDA the winner is unordered -- parity inputs avoid duplicates).
+ * xyz (B,N,3); feats[j] (B,N,fdim[j]) -> xyz_proj (B,H,W,3), feat_proj[j] (B,H,W,fdim[j]).    */
+/* ------------------------------------------------------------------------- */
+static long long clampll(long long v, long long lo, long long hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+void orc_project_seq(int b, int n, int H, int W, float fup_deg, float fdown_deg, const float *xyz, int nfeat,
+                     const float *const *feats, const int *fdims, float *xyz_proj, float *const *feat_projs) {
+    const double deg2rad = M_PI / 180.0;
+    const double az = 360.0 / W * deg2rad;
+    const double down = (double)fdown_deg * deg2rad, up = (double)fup_deg * deg2rad;
+    const double vres = (up - down) / (H - 1);
+    const double voff = -down / vres;
+    const float pi = (float)M_PI, inv_az = 1.0f / (float)az, inv_vres = 1.0f / (float)vres, voff_f = (float)voff;
+    memset(xyz_proj, 0, sizeof(float) * (size_t)b * H * W * 3);
+    for (int j = 0; j < nfeat; ++j) memset(feat_projs[j], 0, sizeof(float) * (size_t)b * H * W * fdims[j]);
+    for (int bi = 0; bi < b; ++bi)
+        for (int i = 0; i < n; ++i) {                     /* ascending i: the last writer wins */
+            const float *p = xyz + ((size_t)bi * n + i) * 3;
+            const float r = sqrtf(fmaf(p[2], p[2], fmaf(p[1], p[1], p[0] * p[0])));       /* :144 */
+            const long long col = (long long)((pi - atan2f(p[1], p[0])) * inv_az);        /* :147 */
+            const float beta = asinf(p[2] / r);                                           /* :150 */
+            const long long row = (long long)H - (long long)(beta * inv_vres + voff_f);   /* :152 */
+            const size_t cell = ((size_t)bi * H + (size_t)clampll(row, 0, H - 1)) * W + (size_t)clampll(col, 0, W - 1);
+            memcpy(xyz_proj + cell * 3, p, sizeof(float) * 3);
+            for (int j = 0; j < nfeat; ++j)
+                memcpy(feat_projs[j] + cell * fdims[j], feats[j] + ((size_t)bi * n + i) * fdims[j],
+                       sizeof(float) * fdims[j]);
         }
 }

@@ -210,3 +210,22 @@ def gather_rows_grad(grad_out, idx, HW):
     g = np.zeros((B, HW, C), dtype=np.float32)
     lib().orc_gather_rows_grad(B, HW, C, M, _fp(grad_out), _ip(idx), _fp(g))
     return g
+
+
+def project_seq(xyz, feats, H, W, fup=2.0, fdown=-24.8):
+    """xyz (B,N,3), feats list of (B,N,D) -> xyz_proj (B,H,W,3), [feat_proj (B,H,W,D)]; rank=False."""
+    xyz = _f32(xyz)
+    feats = [_f32(f) for f in feats]
+    B, N, _ = xyz.shape
+    nf = len(feats)
+    xyz_proj = np.empty((B, H, W, 3), dtype=np.float32)
+    outs = [np.empty((B, H, W, f.shape[-1]), dtype=np.float32) for f in feats]
+    L = lib()
+    fp = (_f * max(nf, 1))(*[_fp(f) for f in feats])
+    op = (_f * max(nf, 1))(*[_fp(o) for o in outs])
+    dims = (ctypes.c_int * max(nf, 1))(*[f.shape[-1] for f in feats])
+    L.orc_project_seq.argtypes = [_int] * 4 + [_flt, _flt, _f, _int, ctypes.c_void_p, ctypes.c_void_p, _f,
+                                              ctypes.c_void_p]
+    L.orc_project_seq(B, N, H, W, float(fup), float(fdown), _fp(xyz), nf, ctypes.cast(fp, ctypes.c_void_p),
+                      ctypes.cast(dims, ctypes.c_void_p), _fp(xyz_proj), ctypes.cast(op, ctypes.c_void_p))
+    return xyz_proj, outs

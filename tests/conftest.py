@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture
+def oracle_backend(monkeypatch):
+    """Host-logic tests only: stand the C oracle in for the CUDA kernels behind i2pnet_b200._cabi
+    so that the nn.Module / autograd plumbing can be checked on a machine without a GPU.  The
+    product never does this -- without libi2p_b200.so and a CUDA tensor it raises."""
+    from tests import cpu_backend
+    cpu_backend.patch(monkeypatch)
+    yield

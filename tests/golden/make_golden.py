@@ -1,0 +1,116 @@
+"""Generate the golden vectors of tests/golden/ by running the REAL reference.
+
+Runs in the build container only (needs /root/reference; no GPU).  The reference's Python is
+imported unchanged; its two CUDA extension modules are replaced by CPU stand-ins backed by the
+C oracle (oracle/ref_shims.py), everything else -- project_seq, gather_torch, knn_point,
+CostVolume, ProjectPointNet, RegNet_v2, Get_loss -- is the reference's own code executing on
+CPU tensors.  The resulting fixtures pin (a) oracle/model_cpu.py and (b) the CUDA path of
+i2pnet_b200 against the reference's module-level behaviour.
+
+    python tests/golden/make_golden.py          # writes tests/golden/*.npz
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims  # noqa: E402
+
+ref_shims.install("/root/reference")
+
+from i2pnet_b200.synthetic import make_pairs  # noqa: E402  (input generator only; no operators)
+
+
+def _save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+                                 for k, v in arrays.items()})
+    print("wrote %s (%.2f MB)" % (path, os.path.getsize(path) / 1e6))
+
+
+def golden_ops():
+    """Op-level vectors from the reference's own Python helpers (src/projectPN/utils.py)."""
+    from src.projectPN import utils as U
+    g = torch.Generator().manual_seed(1)
+    d = make_pairs(2, n_points=4096, seed=3)
+    xyz_proj, (f1, f2) = U.project_seq(d["raw_point_xyz"], [d["lidar_feats"], d["lidar"]], 64, 1800, False, 2.0, -24.8)
+    nz = xyz_proj.abs().sum(-1) > 0
+    # project_seq: store sparsely (cell index + value) to keep the fixture small
+    _save("ref_project_seq.npz", raw=d["raw_point_xyz"], feats=d["lidar_feats"], cam=d["lidar"],
+          cells=nz.nonzero(), xyz=xyz_proj[nz], f1=f1[nz], f2=f2[nz])
+
+    # get_neighbor_copy / get_neighbor_att + gather_torch on a small range image
+    B, H, W = 2, 16, 225
+    img = torch.zeros(B, H, W, 3)
+    keep = torch.rand(B, H, W, generator=g) < 0.6
+    img[keep] = (torch.rand(int(keep.sum()), 3, generator=g) - 0.5) * 20
+    idx_n2 = U.get_stride_idx_cuda(B, 8, 113, 2, 2, "cpu")
+    feat = torch.randn(B, H, W, 5, generator=g)
+    res = {}
+    for name, fn in (("copy", U.get_neighbor_copy), ("att", U.get_neighbor_att)):
+        b, h, w, m = fn(img, img, idx_n2, [5, 9], 8, distance=6.0)
+        res["%s_h" % name], res["%s_w" % name], res["%s_mask" % name] = h, w, m
+        res["%s_gather" % name] = U.gather_torch(feat, b, h, w, B, H, W)
+    # up-conv form: xyz1 at 4x57, xyz2 at 4x29, stride (1,2)
+    x1 = img[:, :4, :57].contiguous()
+    x2 = x1[:, :, ::2].contiguous()
+    b, h, w, m = U.get_neighbor_copy(x1, x2, U.get_idx_cuda(B, 4, 57, "cpu"), [5, 9], 8, 1, 2, distance=9.0)
+    res.update(up_h=h, up_w=w, up_mask=m)
+    q = torch.randn(B, 50, 3, generator=g)
+    s = torch.randn(B, 300, 3, generator=g)
+    res["knn_idx_sorted"] = torch.sort(U.knn_point(16, s, q), dim=-1)[0]
+    _save("ref_select_gather.npz", img=img, idx_n2=idx_n2, feat=feat, knn_q=q, knn_s=s, **res)
+
+
+def golden_model():
+    """Whole-model forward + loss + backward of the reference RegNet_v2 (KITTI shape, B=2)."""
+    import compute_loss
+    from src.config_proj_lidarcenter import I2PNetConfig as cfg
+    from src.modellearn_proj_center import RegNet_v2
+    cfg.efgh = False
+    torch.manual_seed(0)
+    model = RegNet_v2(cfg=cfg)
+    model.train()
+    for head in (model.l4_head, model.l3_head):   # training-mode BN everywhere, dropout silenced
+        head.DP1.p = 0.0
+    # non-trivial BN affine parameters so that their gradients are exercised
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "bn" in n or (".1." in n and "RGB" in n) or ".5." in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+
+    d = make_pairs(2, n_points=20480, seed=11, occupy_centres=(4, 8))
+    inter = {}
+    for name in ("LiDAR_lv2", "LiDAR_lv3", "cost_volume1", "layer_idx", "set_upconv0_upsample", "cost_volume2"):
+        def hook(mod, args, out, name=name):
+            t = out[2] if isinstance(out, tuple) else out
+            inter["inter_" + name] = t.detach().clone()
+        getattr(model, name).register_forward_hook(hook)
+    out3, out4, _, _, sx, sq = model(d["rgb"], d["lidar"], d["raw_point_xyz"], None, d["intrinsic"], None, None,
+                                     None, d["lidar_feats"], cfg)
+    loss, lq, lx = compute_loss.Get_loss(out3, out4, d["q_gt"], d["t_gt"], sx, sq, cfg)
+    loss.backward()
+    grads = {n: p.grad for n, p in model.named_parameters()}
+    names = sorted(grads)
+    keep = ["sq", "sx", "l3_head.quat_head.composed_module.0.weight", "cost_volume1.mlp1_convs.0.conv.weight",
+            "LiDAR_lv1.mlp_convs.0.conv.weight", "RGB_net1.0.weight", "cost_volume2.pc_encoding.bn_linear.weight"]
+    inter["inter_LiDAR_lv2"] = inter["inter_LiDAR_lv2"][:, ::2, ::7]   # subsample the big one
+    _save("ref_model_kitti_b2.npz",
+          rgb_u8=d["rgb"].to(torch.uint8), lidar=d["lidar"], raw_point_xyz=d["raw_point_xyz"],
+          lidar_feats=d["lidar_feats"], intrinsic=d["intrinsic"], q_gt=d["q_gt"], t_gt=d["t_gt"],
+          out3=out3, out4=out4, loss=loss, grad_names=np.array(names),
+          grad_norms=np.array([float(grads[n].norm()) for n in names]),
+          **{"grad__" + n: grads[n] for n in keep}, **{"state__" + k: v for k, v in state.items()}, **inter)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    golden_ops()
+    golden_model()

@@ -1,0 +1,95 @@
+"""Host-side logic of the product modules (state_dict layout, data flow, autograd wiring),
+checked WITHOUT a GPU against the golden vectors recorded from the real reference model
+(tests/golden/make_golden.py).  The CUDA kernels are replaced by the C oracle through the
+`oracle_backend` fixture; the same comparison with the real kernels is tests/test_model_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLDEN
+
+REL = 1e-4  # north_star: fp32 features and regressed pose within 1e-4 relative
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def load_golden_model():
+    g = np.load(os.path.join(GOLDEN, "ref_model_kitti_b2.npz"))
+    state = {k[len("state__"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state__")}
+    return g, state
+
+
+def build_model(state, device="cpu"):
+    from i2pnet_b200.modellearn_proj_center import RegNet_v2
+    model = RegNet_v2()
+    missing = model.load_state_dict(state, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model.train()
+    for head in (model.l4_head, model.l3_head):
+        head.DP1.p = 0.0
+    return model.to(device)
+
+
+def run_model(model, g, device="cpu"):
+    from i2pnet_b200.compute_loss import Get_loss
+    from i2pnet_b200.config_proj_lidarcenter import I2PNetConfig as cfg
+    t = lambda k: torch.from_numpy(g[k]).to(device)
+    rgb = torch.from_numpy(g["rgb_u8"]).float().to(device)
+    inter = {}
+    for name in ("LiDAR_lv2", "LiDAR_lv3", "cost_volume1", "layer_idx", "set_upconv0_upsample", "cost_volume2"):
+        def hook(mod, args, out, name=name):
+            inter[name] = (out[2] if isinstance(out, tuple) else out).detach()
+        getattr(model, name).register_forward_hook(hook)
+    out3, out4, _, _, sx, sq = model(rgb, t("lidar"), t("raw_point_xyz"), None, t("intrinsic"), None, None, None,
+                                     t("lidar_feats"), cfg)
+    loss, _, _ = Get_loss(out3, out4, t("q_gt"), t("t_gt"), sx, sq, cfg)
+    loss.backward()
+    return out3, out4, loss, inter
+
+
+def check_against_golden(model, g, out3, out4, loss, inter, tol=REL):
+    inter["LiDAR_lv2"] = inter["LiDAR_lv2"][:, ::2, ::7]
+    for name, val in inter.items():
+        ref = g["inter_" + name]
+        assert _rel(val.cpu().reshape(ref.shape), ref) < tol, name
+    assert _rel(out4.detach().cpu(), g["out4"]) < tol
+    assert _rel(out3.detach().cpu(), g["out3"]) < tol
+    assert abs(float(loss) - float(g["loss"])) < tol * abs(float(g["loss"]))
+    grads = {n: p.grad for n, p in model.named_parameters()}
+    names = [str(n) for n in g["grad_names"]]
+    assert sorted(grads) == names
+    for n, ref_norm in zip(names, g["grad_norms"]):
+        mine = float(grads[n].norm())
+        assert abs(mine - ref_norm) <= 2e-3 * max(ref_norm, 1e-6) + 1e-7, (n, mine, ref_norm)
+    for k in g.files:
+        if k.startswith("grad__"):
+            assert _rel(grads[k[len("grad__"):]].cpu(), g[k]) < 2e-3, k
+
+
+def test_state_dict_matches_reference_layout():
+    g, state = load_golden_model()
+    from i2pnet_b200.modellearn_proj_center import RegNet_v2
+    mine = RegNet_v2().state_dict()
+    assert list(mine.keys()) == list(state.keys())           # same names, same registration order
+    assert all(mine[k].shape == state[k].shape for k in mine)
+    assert sum(p.numel() for p in RegNet_v2().parameters()) == 844896
+
+
+def test_model_host_logic_matches_reference(oracle_backend):
+    g, state = load_golden_model()
+    model = build_model(state)
+    out3, out4, loss, inter = run_model(model, g)
+    check_against_golden(model, g, out3, out4, loss, inter)
+
+
+def test_product_refuses_cpu_tensors():
+    """No fallback: the real binding raises on a CPU tensor instead of computing anything."""
+    from i2pnet_b200 import _cabi
+    from i2pnet_b200.projectPN.utils import gather_rows
+    with pytest.raises(_cabi.I2PError):
+        gather_rows(torch.zeros(1, 4, 4), torch.zeros(1, 2, dtype=torch.int32))
