@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""Benchmark of the I2PNet hot path: image + point-cloud pairs/s of one full RegNet_v2 training
+step (forward + loss + backward + grad all-reduce + clip + Adam) on KITTI-shaped synthetic pairs
+(160x512 RGB + 20480 points, batch 8 per GPU; BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # ours, one JSON line
+    python bench.py --impl reference [--steps K] [--warmup W]        # the reference path on host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N     # one rank per GPU, weak scaling
+
+Keys follow the driver's contract: `value` = whole-job pairs/s with inputs resident in HBM,
+`e2e` = the same through TrainStep.step_from_host (pinned host batch -> device -> step -> loss on
+host), `roofline` = the dominant own kernel against the measured HBM peak, `cpu_baseline` = the
+CPU oracle port (oracle/model_cpu.py) on a bounded sample.  The oracle is executed only in the
+cpu_baseline leg and the --impl reference arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "kitti_160x512_rgb+20480pts_batch8_per_gpu_fwd+bwd+adam"
+N_POINTS, IMAGE_HW, BATCH = 20480, (160, 512), 8
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_steps(steps, warmup, batch, threads=None, seed=0):
+    """The reference path on host cores: oracle/model_cpu.py forward + loss + backward + Adam on
+    `batch` pairs per step.  -> (seconds per step list, cores)"""
+    import torch
+    from i2pnet_b200.synthetic import make_pairs
+    from oracle import model_cpu
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    sd = {k: v.requires_grad_(True) for k, v in model_cpu.random_state(seed).items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=1e-3, weight_decay=1e-4)
+    times = []
+    for i in range(warmup + steps):
+        d = make_pairs(batch, N_POINTS, IMAGE_HW, seed=1000 + i)
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out3, out4 = model_cpu.forward(sd, d["rgb"], d["lidar"], d["raw_point_xyz"], d["intrinsic"], d["lidar_feats"])
+        loss = model_cpu.loss_fn(out3, out4, d["q_gt"], d["t_gt"], sd["sx"], sd["sq"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(sd.values()), 10.0)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = BATCH   # ~3 s per step on 8 cores: the full per-GPU batch fits the time budget
+    times, cores = cpu_reference_steps(args.steps, args.warmup, batch)
+    total = sum(times)
+    value = batch * len(times) / total
+    sample = "%d steps of batch %d (of the batch-%d workload) on %d host threads, oracle/model_cpu.py" % (
+        len(times), batch, BATCH, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "points": N_POINTS, "image": list(IMAGE_HW), "sample_batch": batch},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def time_select_kernel(device, peak):
+    """The dominant own kernel in isolation: projection-window select at the SA1 shape, batch 8,
+    CUDA events on the launching stream, L2 flushed between launches."""
+    import torch
+    from i2pnet_b200.projectPN.utils import FLAG_COPY, FLAG_SHIFT, StrideGrid, project_seq, select_flat
+    from i2pnet_b200.synthetic import make_pairs
+    d = make_pairs(BATCH, N_POINTS, IMAGE_HW, seed=7)
+    _, (cam,) = project_seq(d["raw_point_xyz"].to(device), [d["lidar"].to(device)], 64, 1800, False)
+    grid = StrideGrid(BATCH, 16, 225, 4, 8, device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    evs = []
+    for i in range(25):
+        flush.fill_(i & 0xff)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        select_flat(cam, cam, grid, [9, 15], 32, FLAG_SHIFT | FLAG_COPY, 0.75)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize(device)
+    ms = statistics.median(a.elapsed_time(b) for a, b in evs[5:])
+    n, K = 3600, 32
+    alg = BATCH * (12 * 64 * 1800 + 8 * n * K)   # xyz2 once + int32 index + f32 mask (compact form)
+    achieved = alg / (ms * 1e-3) / 1e9
+    return {"kernel": "select_k_kernel<5,flat> @SA1 (64x1800, 3600 centres, 9x15, K=32, batch 8)", "bound": "hbm",
+            "achieved": achieved, "peak": peak[0], "peak_source": peak[1], "unit": "GB/s", "frac": achieved / peak[0],
+            "traffic": None, "algorithmic_bytes": alg, "us_per_launch": ms * 1e3}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from i2pnet_b200 import _cabi
+    from i2pnet_b200.engine import INPUT_KEYS, TrainStep
+    from i2pnet_b200.synthetic import make_pairs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; i2pnet_b200 has no CPU path (use --impl reference)")
+    _cabi.lib()  # fail loudly here if the sm_100a library is missing
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    torch.backends.cuda.matmul.allow_tf32 = False   # f32 parity configuration (north_star: 1e-4 relative)
+    torch.backends.cudnn.allow_tf32 = False
+
+    eng = TrainStep(BATCH, N_POINTS, IMAGE_HW, device=device, seed=0, use_graph=not args.no_graph)
+    nb = 4  # distinct batches, cycled
+    host = [make_pairs(BATCH, N_POINTS, IMAGE_HW, seed=100 * rank + i) for i in range(nb)]
+    host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    dev_batches = [{k: v.to(device) for k, v in b.items()} for b in host]
+    eng.load(dev_batches[0])
+    eng.warmup_and_capture(eager_steps=3)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(n_steps, from_host):
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for i in range(n_steps):
+            flush.fill_(i & 0xff)
+            if from_host:
+                eng.step_from_host(host[i % nb])
+            else:
+                eng.load(dev_batches[i % nb])
+                eng.step()
+        stop.record()
+        barrier()
+        ms = torch.tensor([start.elapsed_time(stop)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    timed(max(args.warmup, 3), False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(args.steps, False)
+    clocks = sampler.stop() if rank == 0 else None
+    timed(3, True)
+    ms_e2e = timed(args.steps, True)
+    loss = float(eng.loss.item())
+
+    if rank == 0:
+        peak = _peaks()
+        roof = time_select_kernel(device, peak)
+        value = world * BATCH * args.steps / (ms * 1e-3)
+        e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
+        h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in INPUT_KEYS)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            t, cores = cpu_reference_steps(3, 1, BATCH)
+            cpu = {"value": BATCH * len(t) / sum(t), "unit": "pairs/s", "cores": cores, "kind": "port",
+                   "sample": "3 steps of batch %d (the same workload) after 1 warm-up, oracle/model_cpu.py "
+                             "fwd+bwd+clip+Adam" % BATCH}
+        print(json.dumps({
+            "metric": "pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points": N_POINTS, "image": list(IMAGE_HW), "per_gpu_batch": BATCH,
+                       "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
+                       "l2": "256 MB flush write between steps", "tf32": False, "final_loss": loss},
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(eng.launches_per_step) * args.steps,
+            "gpu_launches_per_step": int(eng.launches_per_step),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="eager step instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,15 @@ def run_model(model, g, device="cpu"):
     return out3, out4, loss, inter
 
 
+def _bias_cancelled_by_bn(name):
+    """A conv bias feeding a batch-statistics BatchNorm has an exactly zero gradient; what both
+    implementations produce there is rounding noise (1e-10..1e-5) and is not compared."""
+    if name.endswith(".conv.bias"):
+        return True
+    parts = name.split(".")
+    return parts[0].startswith("RGB_net") and parts[-1] == "bias" and int(parts[1]) % 4 == 0
+
+
 def check_against_golden(model, g, out3, out4, loss, inter, tol=REL):
     inter["LiDAR_lv2"] = inter["LiDAR_lv2"][:, ::2, ::7]
     for name, val in inter.items():
@@ -64,6 +73,9 @@ def check_against_golden(model, g, out3, out4, loss, inter, tol=REL):
     names = [str(n) for n in g["grad_names"]]
     assert sorted(grads) == names
     for n, ref_norm in zip(names, g["grad_norms"]):
+        if _bias_cancelled_by_bn(n):
+            assert float(grads[n].norm()) < 1e-3
+            continue
         mine = float(grads[n].norm())
         assert abs(mine - ref_norm) <= 2e-3 * max(ref_norm, 1e-6) + 1e-7, (n, mine, ref_norm)
     for k in g.files:
