@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(G_THREADS) scatter_cn_kernel(int c, int n, int
 }
 
 // out[b,c,j] = w0*p[i0] + w1*p[i1] + w2*p[i2], contracted as nvcc -O2 contracts the reference
-// expression (interpolate_gpu.cu:96): fma(w2,p2, fma(w1,p1, w0*p0))
+// expression (interpolate_gpu.cu:96), SASS FMUL w1*p1; FFMA w0*p0+t; FFMA w2*p2+t:
+// fma(w2,p2, fma(w0,p0, w1*p1))
 __global__ void __launch_bounds__(G_THREADS) interp_kernel(int c, int m, int n, const float *__restrict__ points,
                                                            const int32_t *__restrict__ idx,
                                                            const float *__restrict__ weight,
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(G_THREADS) interp_kernel(int c, int m, int n, 
         if (u < cc) {
             const float *p = points + ((size_t)b * c + c0 + u) * m;
             out[((size_t)b * c + c0 + u) * n + j] =
-                __fmaf_rn(w2, __ldg(p + i2), __fmaf_rn(w1, __ldg(p + i1), __fmul_rn(w0, __ldg(p + i0))));
+                __fmaf_rn(w2, __ldg(p + i2), __fmaf_rn(w0, __ldg(p + i0), __fmul_rn(w1, __ldg(p + i1))));
         }
 }
 

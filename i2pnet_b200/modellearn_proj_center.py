@@ -31,8 +31,9 @@ def set_id_grid(rf):
 def change_intrinsic(intrinsic, RF, rgb_img):
     """Rescale K (B,3,3) from the input image to the feature map RF (B,C,h,w)."""
     sx, sy = RF.shape[3] / rgb_img.shape[3], RF.shape[2] / rgb_img.shape[2]
-    scale = intrinsic.new_tensor([[sx, 1.0, sx], [1.0, sy, sy], [1.0, 1.0, 1.0]])
-    return intrinsic * scale
+    # row scaling only (no host tensor: the forward must stay capturable into a CUDA graph);
+    # K[0,1] and K[1,0] are zero for a pinhole intrinsic, as the reference assumes too
+    return torch.cat([intrinsic[:, 0:1] * sx, intrinsic[:, 1:2] * sy, intrinsic[:, 2:3]], dim=1)
 
 
 def _mask_fill(x, valid):

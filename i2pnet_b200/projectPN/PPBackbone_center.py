@@ -59,7 +59,7 @@ class Conv2d(nn.Module):
             self.bn_linear.training = True
 
 
-def _batch_norm_rows(y, m):
+def _batch_norm_rows_stable(y, m):
     """BatchNorm over the rows of y (rows, C) with the parameters / buffers of the BatchNorm2d `m`.
     Batch statistics (biased variance, as nn.BatchNorm2d normalises) unless m tracks running
     statistics and is in eval mode.  Statistics come from torch.var_mean (a stable pairwise /
@@ -80,6 +80,17 @@ def _batch_norm_rows(y, m):
     if m.weight is not None:
         return (y - mean) * (scale * m.weight) + m.bias
     return (y - mean) * scale
+
+
+def _batch_norm_rows(y, m):
+    """The product path: ATen's fused channels-last batch-norm kernels (Welford statistics, one
+    normalise pass, fused backward).  _batch_norm_rows_stable is the same function spelled with
+    torch.var_mean; the CPU host-logic tests substitute it because ATen's 2-D CPU kernel
+    accumulates in f32."""
+    use_batch = m.training or not m.track_running_stats
+    return F.batch_norm(y, m.running_mean if m.track_running_stats else None,
+                        m.running_var if m.track_running_stats else None, m.weight, m.bias, use_batch,
+                        m.momentum if m.momentum is not None else 0.1, m.eps)
 
 
 def _centres(sample_idx, B, out_h, out_w, stride_H, stride_W, device):

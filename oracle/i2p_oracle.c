@@ -182,7 +182,8 @@ void orc_three_nn(int b, int n, int m, const float *unknown, const float *known,
 
 /* ------------------------------------------------------------------------- */
 /* K8/K9 three_interpolate (+grad): interpolate_gpu.cu:77-142                  */
-/* nvcc contracts w0*p0 + w1*p1 + w2*p2 to fma(w2,p2, fma(w1,p1, w0*p0))       */
+/* nvcc contracts w0*p0 + w1*p1 + w2*p2 like the distance sites: FMUL w1*p1;    */
+/* FFMA w0*p0+t; FFMA w2*p2+t (SASS of oracle/_ref/pointnet2_cuda.so)            */
 /* ------------------------------------------------------------------------- */
 void orc_three_interpolate(int b, int c, int m, int n, const float *points, const int32_t *idx, const float *weight, float *out) {
     for (int bi = 0; bi < b; ++bi)
@@ -191,7 +192,7 @@ void orc_three_interpolate(int b, int c, int m, int n, const float *points, cons
             for (int p = 0; p < n; ++p) {
                 const float *w = weight + ((size_t)bi * n + p) * 3;
                 const int32_t *id = idx + ((size_t)bi * n + p) * 3;
-                out[((size_t)bi * c + ci) * n + p] = fmaf(w[2], pt[id[2]], fmaf(w[1], pt[id[1]], w[0] * pt[id[0]]));
+                out[((size_t)bi * c + ci) * n + p] = fmaf(w[2], pt[id[2]], fmaf(w[0], pt[id[0]], w[1] * pt[id[1]]));
             }
         }
 }

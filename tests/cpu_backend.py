@@ -69,3 +69,5 @@ def patch(monkeypatch):
     for name in ("select_k_flat", "fused_conv_select_k", "gather_rows", "gather_rows_grad", "knn_point",
                  "project_seq", "group_points", "group_points_grad"):
         monkeypatch.setattr(_cabi, name, globals()[name])
+    from i2pnet_b200.projectPN import PPBackbone_center as P
+    monkeypatch.setattr(P, "_batch_norm_rows", P._batch_norm_rows_stable)   # see its docstring

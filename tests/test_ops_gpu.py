@@ -156,10 +156,10 @@ def test_full_size_properties(dev):
     assert (idx[:, 0] == 0).all()
     assert all(len(set(r.tolist())) == 4096 for r in idx.cpu())       # distinct points never repeat
     sel = torch.gather(xyz, 1, idx[:, :, None].expand(-1, -1, 3))
-    d_sel = torch.cdist(sel[:, :512], sel[:, :512]) + torch.eye(512, device=dev) * 1e9
+    d_sel = (sel[:, :512, None] - sel[:, None, :512]).norm(dim=-1) + torch.eye(512, device=dev) * 1e9
     # FPS is greedy max-min: the i-th pick's distance to the earlier picks is non-increasing in i
     dmin = torch.stack([d_sel[:, i, :i].min(-1)[0] for i in range(1, 512)], 1)
-    assert (dmin[:, 1:] <= dmin[:, :-1] + 1e-4).all()
+    assert (dmin[:, 1:] <= dmin[:, :-1] + 1e-3).all()
     # ball query at sweep size: every returned index is inside the radius (or a padded copy of the first)
     q = sel[:, :2048].contiguous()
     bq = pu.ball_query(1.0, 32, xyz, q).long()

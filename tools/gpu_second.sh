@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python tools/debug_model_grads.py > gpurun_out/debug_grads.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/pytest_gpu_all.log 2>&1
+timeout 900 python bench.py --steps 20 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/bench_eager.log 2>&1
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_graph.log 2>&1
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_step.csv python tools/profile_step.py step > gpurun_out/ncu_step.log 2>&1
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:select_k_kernel -c 2 \
+    -f -o gpurun_out/prof_select python tools/profile_step.py fwd > gpurun_out/ncu_select.log 2>&1
+tail -n 3 gpurun_out/debug_grads.log gpurun_out/pytest_gpu_all.log gpurun_out/bench_eager.log gpurun_out/bench_graph.log
