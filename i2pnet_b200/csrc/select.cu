@@ -5,16 +5,19 @@
 // per-thread arrays in local memory, an O(K * kH*kW) scalar selection sort.
 // This design: one WARP per centre, grid over all B*npoints centres.  The kH*kW window
 // slots live in registers, slot t in lane t%32 register t/32 (<= 5 registers for the
-// reference's 150-slot limit).  Each of the K selection steps is two redux.sync
-// reductions (minimum distance, then lowest slot holding it) and three shuffles that
-// replay the reference's swap, so the emitted order -- including its behaviour on exact
-// distance ties, which depends on the swap history -- is bit-identical.  Results are staged
-// in shared memory and written with coalesced stores.
+// reference's 150-slot limit); window loads are issued before the centre is inspected so the
+// two memory latencies overlap.  Valid slots are compacted (ballot + popc) into a per-warp
+// shared list and every candidate computes its output position as its RANK in that list --
+// independent compares, no serial chain.  Only when two valid distances are bit-equal does
+// the emitted order depend on the reference's swap history; that (rare) case replays its
+// selection sort step by step with two redux.sync reductions and three shuffles per step.
+// Either way the result is bit-identical to the reference.  Results are staged in shared
+// memory and written with coalesced stores.
 #include "common.cuh"
 
 namespace i2p {
 
-constexpr int SEL_WARPS = 8;      // warps (centres) per block
+constexpr int SEL_WARPS = 4;      // warps (centres) per block
 constexpr int SEL_MAX_SLOTS = 160;  // 5 registers x 32 lanes >= the reference's 150
 constexpr int SEL_MAX_K = 150;      // fused_conv_go.cu:52-53 arrays are [150]
 
@@ -48,7 +51,9 @@ __device__ __forceinline__ int pick(const int (&a)[R], int r) {
 
 template <int R, bool FLAT>
 __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectArgs a) {
-    __shared__ int s_hw[SEL_WARPS][SEL_MAX_K];  // packed (h << 16 | w), -1 = slot not written
+    __shared__ int s_hw[SEL_WARPS][SEL_MAX_K];               // packed (h << 16 | w), -1 = slot not written
+    __shared__ unsigned s_d[SEL_WARPS][SEL_MAX_SLOTS];       // compacted valid candidates: distance bits
+    __shared__ int s_c[SEL_WARPS][SEL_MAX_SLOTS + 1];        // ... their (h << 16 | w); [last] = the nearest
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -72,83 +77,128 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectAr
 
     const float *pc = a.xyz1 + (((size_t)b * a.H + sH) * a.W + sW) * 3;
     const float xc = __ldg(pc), yc = __ldg(pc + 1), zc = __ldg(pc + 2);
+
+    // Window slots: issued before the centre is inspected, so that the two global-memory
+    // latencies overlap instead of chaining.
+    const int half_H = a.kH / 2, half_W = a.kW / 2;
+    const int base_h = sH / a.stride_h - half_H, base_w = sW / a.stride_w - half_W;  // :89-92
+    const float *x2 = a.xyz2 + (size_t)b * a.small_h * a.small_w * 3;
+    float qx[R], qy[R], qz[R];
+    int hw[R];
+    bool inside[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int t = r * 32 + lane;
+        inside[r] = false;
+        hw[r] = 0;
+        qx[r] = qy[r] = qz[r] = 0.f;
+        if (t < total) {
+            const int khw = a.random_hw != nullptr ? __ldg(a.random_hw + t) : t;  // utils.py:84 arange
+            int kh = base_h + khw / a.kW;
+            int kw = base_w + khw % a.kW;
+            bool ok = (kh >= 0) && (kh < a.small_h);
+            if (a.flag & I2P_FLAG_SHIFT) {  // :96-113 the range image is circular in width
+                if (kw < 0) kw += a.small_w;
+                if (kw >= a.small_w) kw -= a.small_w;
+            }
+            // (a window wider than the image can still fall outside after one wrap; the reference
+            // would read out of bounds there, this kernel drops the slot)
+            ok = ok && (kw >= 0) && (kw < a.small_w);
+            if (ok) {
+                const float *q = x2 + ((size_t)kh * a.small_w + kw) * 3;
+                qx[r] = __ldg(q); qy[r] = __ldg(q + 1); qz[r] = __ldg(q + 2);
+                hw[r] = (kh << 16) | kw;
+                inside[r] = true;
+            }
+        }
+    }
+
     const float dist_c = fmaxf(sqlen(xc, yc, zc), 1e-10f);  // :72
     const bool centre_valid = !(dist_c <= 1e-10f);           // :74-78 empty centre -> nothing written
 
     if (centre_valid) {
         const float dist_square = __fmul_rn(a.distance, a.distance);  // :26
-        const int half_H = a.kH / 2, half_W = a.kW / 2;
-        const int base_h = sH / a.stride_h - half_H, base_w = sW / a.stride_w - half_W;  // :89-92
-        const float *x2 = a.xyz2 + (size_t)b * a.small_h * a.small_w * 3;
-
         float dist[R];
-        int hw[R];
+        int nvalid = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int t = r * 32 + lane;
-            dist[r] = 1e10f;
-            hw[r] = 0;
-            if (t < total) {
-                const int khw = a.random_hw != nullptr ? __ldg(a.random_hw + t) : t;  // utils.py:84 arange
-                int kh = base_h + khw / a.kW;
-                int kw = base_w + khw % a.kW;
-                bool ok = (kh >= 0) && (kh < a.small_h);
-                if (a.flag & I2P_FLAG_SHIFT) {  // :96-113 the range image is circular in width
-                    if (kw < 0) kw += a.small_w;
-                    if (kw >= a.small_w) kw -= a.small_w;
-                    // a window wider than the image can still fall outside after one wrap; the
-                    // reference would read out of bounds there, this kernel drops the slot
-                    ok = ok && (kw >= 0) && (kw < a.small_w);
-                } else {
-                    ok = ok && (kw >= 0) && (kw < a.small_w);
-                }
-                if (ok) {
-                    const float *q = x2 + ((size_t)kh * a.small_w + kw) * 3;
-                    const float xq = __ldg(q), yq = __ldg(q + 1), zq = __ldg(q + 2);
-                    const float dq0 = sqlen(xq, yq, zq);  // :140 empty cell
-                    const float dq = fmaxf(sqlen(__fsub_rn(xc, xq), __fsub_rn(yc, yq), __fsub_rn(zc, zq)), 1e-10f);
-                    if (!(dq0 <= 1e-10f) && !(dq > dist_square)) {  // :146, :156
-                        dist[r] = dq;
-                        hw[r] = (kh << 16) | kw;
-                    }
-                }
+            const float dq0 = sqlen(qx[r], qy[r], qz[r]);  // :140 empty cell
+            const float dq = fmaxf(sqlen(__fsub_rn(xc, qx[r]), __fsub_rn(yc, qy[r]), __fsub_rn(zc, qz[r])), 1e-10f);
+            const bool ok = inside[r] && !(dq0 <= 1e-10f) && !(dq > dist_square);  // :146, :156
+            dist[r] = ok ? dq : 1e10f;
+            hw[r] = ok ? hw[r] : 0;
+            // compact the valid slots, in slot order, into this warp's shared list
+            const unsigned vmask = __ballot_sync(FULL, ok);
+            if (ok) {
+                const int pos = nvalid + __popc(vmask & ((1u << lane) - 1u));
+                s_d[warp][pos] = __float_as_uint(dq);
+                s_c[warp][pos] = hw[r];
             }
+            nvalid += __popc(vmask);
         }
         __syncwarp();
 
-        // K steps of the reference's selection sort (:183-208), one warp-wide step each.
-        const int steps = K < total ? K : total;
-        for (int s = 0; s < steps; ++s) {
-            unsigned best_d = 0xffffffffu, best_t = 0xffffffffu;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const unsigned t = r * 32 + lane;
-                const unsigned bits = __float_as_uint(dist[r]);  // all distances are positive floats
-                if (t >= (unsigned)s && t < (unsigned)total && bits < best_d) {
-                    best_d = bits;
-                    best_t = t;
-                }
+        // Fast path: with pairwise-distinct distances the reference's selection sort emits the
+        // valid slots in ascending distance, so each candidate's output position is its RANK --
+        // nvalid independent compares per candidate, no serial dependency chain.
+        bool tie = false;
+        for (int c = lane; c < nvalid; c += 32) {
+            const unsigned mine = s_d[warp][c];
+            int rank = 0;
+            for (int j = 0; j < nvalid; ++j) {
+                const unsigned other = s_d[warp][j];
+                rank += other < mine;
+                tie |= (other == mine) && (j != c);
             }
-            const unsigned m = __reduce_min_sync(FULL, best_d);
-            const unsigned mi = __reduce_min_sync(FULL, best_d == m ? best_t : 0xffffffffu);
-            const int hw_m = __shfl_sync(FULL, pick<R>(hw, mi >> 5), mi & 31);
-            const int hw_s = __shfl_sync(FULL, pick<R>(hw, s >> 5), s & 31);
-            const float d_s = __shfl_sync(FULL, pick<R>(dist, s >> 5), s & 31);
-            if (mi != (unsigned)s && lane == (int)(mi & 31)) {  // the swap: slot mi takes slot s's entry
+            if (rank < K) s_hw[warp][rank] = s_c[warp][c];
+            if (rank == 0) s_c[warp][SEL_MAX_SLOTS] = s_c[warp][c];  // the nearest, for FLAG_COPY
+        }
+        tie = __any_sync(FULL, tie);
+        __syncwarp();
+        if (!tie) {
+            if (a.flag & I2P_FLAG_COPY) {  // :211-222 pad with the nearest; hw = 0 when nothing is valid
+                const int first = nvalid > 0 ? s_c[warp][SEL_MAX_SLOTS] : 0;
+                for (int k = lane; k < K; k += 32)
+                    if (k >= nvalid) s_hw[warp][k] = first;
+            }
+        } else {
+            // Exact distances tie: the reference's emitted order then depends on its swap
+            // history.  Replay the K steps of its selection sort (:183-208), one warp-wide step each.
+            for (int k = lane; k < K; k += 32) s_hw[warp][k] = -1;
+            __syncwarp();
+            const int steps = K < total ? K : total;
+            for (int s = 0; s < steps; ++s) {
+                unsigned best_d = 0xffffffffu, best_t = 0xffffffffu;
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (r == (int)(mi >> 5)) {
-                        dist[r] = d_s;
-                        hw[r] = hw_s;
+                for (int r = 0; r < R; ++r) {
+                    const unsigned t = r * 32 + lane;
+                    const unsigned bits = __float_as_uint(dist[r]);  // all distances are positive floats
+                    if (t >= (unsigned)s && t < (unsigned)total && bits < best_d) {
+                        best_d = bits;
+                        best_t = t;
                     }
+                }
+                const unsigned m = __reduce_min_sync(FULL, best_d);
+                const unsigned mi = __reduce_min_sync(FULL, best_d == m ? best_t : 0xffffffffu);
+                const int hw_m = __shfl_sync(FULL, pick<R>(hw, mi >> 5), mi & 31);
+                const int hw_s = __shfl_sync(FULL, pick<R>(hw, s >> 5), s & 31);
+                const float d_s = __shfl_sync(FULL, pick<R>(dist, s >> 5), s & 31);
+                if (mi != (unsigned)s && lane == (int)(mi & 31)) {  // the swap: slot mi takes slot s's entry
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r == (int)(mi >> 5)) {
+                            dist[r] = d_s;
+                            hw[r] = hw_s;
+                        }
+                }
+                const bool valid = __uint_as_float(m) < 1e10f;
+                if (s == 0 && (a.flag & I2P_FLAG_COPY)) {  // :211-222, unconditional on validity
+                    for (int k = lane; k < K; k += 32) s_hw[warp][k] = hw_m;
+                    __syncwarp();
+                }
+                if (valid && lane == 0) s_hw[warp][s] = hw_m;  // :225-233
+                if (!valid) break;  // every remaining slot is 1e10: nothing more is written
             }
-            const bool valid = __uint_as_float(m) < 1e10f;
-            if (s == 0 && (a.flag & I2P_FLAG_COPY)) {  // :211-222, unconditional on validity
-                for (int k = lane; k < K; k += 32) s_hw[warp][k] = hw_m;
-                __syncwarp();
-            }
-            if (valid && lane == 0) s_hw[warp][s] = hw_m;  // :225-233
-            if (!valid) break;  // every remaining slot is 1e10: nothing more is written
         }
     }
     __syncwarp();

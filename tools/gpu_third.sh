@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider -s > gpurun_out/pytest_gpu_all.log 2>&1
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_graph.log 2>&1
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:select_k_kernel -c 2 \
+    -f -o gpurun_out/prof_select python tools/profile_step.py fwd > gpurun_out/ncu_select.log 2>&1
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.log 2>&1
+grep -E "passed|failed|FAILED|largest" gpurun_out/pytest_gpu_all.log | tail -n 12; tail -n 2 gpurun_out/bench_graph.log gpurun_out/bench_reference.log
