@@ -27,6 +27,7 @@ _lib = None
 _vp = ctypes.c_void_p
 _int = ctypes.c_int
 _flt = ctypes.c_float
+_ll = ctypes.c_longlong
 
 _SIGNATURES = {
     "i2p_furthest_point_sampling": [_int, _int, _int, _vp, _vp, _vp, _vp],
@@ -45,12 +46,19 @@ _SIGNATURES = {
     "i2p_gather_rows_grad": [_int] * 4 + [_vp] * 4,
     "i2p_knn_point": [_int] * 4 + [_vp] * 5,
     "i2p_project_seq": [_int] * 4 + [_flt, _flt, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
+    "i2p_pw_linear_fwd": [_int] * 3 + [_vp] * 3 + [_flt] + [_vp] * 5,
+    "i2p_bn_finalize": [_int, _int, _vp, _vp, _vp, _flt, _vp, _vp, _vp, _vp, _vp],
+    "i2p_bn_act": [_ll, _int, _vp, _vp, _vp, _flt, _vp, _vp],
+    "i2p_bn_act_maxk": [_ll, _int, _int, _vp, _vp, _vp, _flt, _vp, _vp, _vp],
+    "i2p_bn_bwd_reduce": [_ll, _int, _vp, _vp, _vp, _int] + [_vp] * 5 + [_flt, _vp, _vp],
+    "i2p_pw_linear_bwd_dx": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 3 + [_vp] * 5 + [_flt, _vp, _vp],
+    "i2p_pw_linear_bwd_dw": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 4 + [_flt, _vp, _vp],
 }
 
 
 def exported_symbols():
     """Every entry point include/i2p_b200.h declares."""
-    return sorted(list(_SIGNATURES) + ["i2p_last_error", "i2p_abi_version", "i2p_launch_count"])
+    return sorted(list(_SIGNATURES) + ["i2p_last_error", "i2p_abi_version", "i2p_launch_count", "i2p_pw_num_tiles"])
 
 
 def lib():
@@ -68,6 +76,8 @@ def lib():
         L.i2p_last_error.restype = ctypes.c_char_p
         L.i2p_abi_version.restype = _int
         L.i2p_launch_count.restype = ctypes.c_uint64
+        L.i2p_pw_num_tiles.argtypes = [_int]
+        L.i2p_pw_num_tiles.restype = _int
         _lib = L
     return _lib
 

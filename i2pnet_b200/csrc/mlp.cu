@@ -1,0 +1,655 @@
+// Shared per-point MLP: y = BN_batchstats(x W^T + b) -> activation, chained, forward and backward.
+//
+// Reference formulation (src/projectPN/PPBackbone_center.py:10-46, used ~35 times per forward):
+// permute to NCHW, cuDNN/cuBLAS 1x1 conv, BatchNorm2d over the batch statistics, in-place
+// (Leaky)ReLU, permute back -- each a separate pass over a (B, N, K, C) tensor, and as many again
+// in autograd's backward (plus a bias-gradient reduction that is identically zero under BN).
+//
+// This design keeps only the RAW pre-normalisation outputs y_l in HBM and folds everything else
+// into the GEMM kernels:
+//   forward, one launch per layer:  y_l = act(y_{l-1} * scale + shift) W_l^T + b_l, where the
+//       previous layer's normalise + activation is applied while the A tile is staged into shared
+//       memory; the epilogue emits per-tile (mean, M2) of y_l, merged exactly (Chan) by a
+//       finalize kernel into mean / rstd / scale / shift -- no E[y^2]-E[y]^2 cancellation;
+//   consumer:  act(y_L * scale + shift), optionally max-reduced over the K neighbours with the
+//       arg-max kept for the backward pass;
+//   backward, two launches per layer: dW_l (split over row chunks) and dX_l, both rebuilding
+//       dY_l = gamma rstd (dz - S1/n - yhat S2/n) on the fly from (g_l, y_l); the dX epilogue already
+//       accumulates the S1, S2 sums the NEXT (earlier) layer's batch-norm backward needs.
+// All arithmetic is f32 FMA (the parity configuration: 1e-4 relative rules out TF32); tiles are
+// 128 x {16,32,64} x 16 with 8 x {1,2,4} register blocking.
+#include "common.cuh"
+
+namespace i2p {
+
+constexpr int MLP_THREADS = 256;
+constexpr int MLP_BM = 128;  // rows per tile
+constexpr int MLP_BK = 16;
+constexpr int MLP_MAXC = 512;  // widest layer supported by the per-channel shared tables
+
+__device__ __forceinline__ float act_fwd(float z, float slope) { return z > 0.f ? z : z * slope; }
+__device__ __forceinline__ float act_grad(float z, float slope) { return z > 0.f ? 1.f : slope; }
+
+// -------------------------------------------------------------------------------------------
+// forward GEMM with fused input transform and tile statistics
+// -------------------------------------------------------------------------------------------
+struct FwdArgs {
+    int rows, cin, cout;
+    const float *x, *in_scale, *in_shift;  // in_scale == nullptr: x is used as is
+    float in_slope;
+    const float *w, *bias;
+    float *y, *tile_stats;  // tile_stats (ntiles, cout, 2) or nullptr
+};
+
+template <int BN>
+__global__ void __launch_bounds__(MLP_THREADS) pw_linear_fwd_kernel(const FwdArgs a) {
+    constexpr int TN = BN / 16, TM = 8, LDA = MLP_BM + 4, LDB = BN + 4;
+    __shared__ __align__(16) float As[MLP_BK][LDA];
+    __shared__ __align__(16) float Bs[MLP_BK][LDB];
+    __shared__ float red[16][BN];
+    __shared__ float colmean[BN];
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int r0 = blockIdx.x * MLP_BM, n0 = blockIdx.y * BN;
+    const int lk = tid & 15, lm = tid >> 4;  // loader coordinates: 16 consecutive k per row
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float pa[MLP_BM / 16], pb[BN / 16];
+    auto fetch = [&](int k0) {
+        const int k = k0 + lk;
+        const bool kin = k < a.cin;
+        float sc = 1.f, sh = 0.f;
+        if (a.in_scale != nullptr && kin) { sc = __ldg(a.in_scale + k); sh = __ldg(a.in_shift + k); }
+#pragma unroll
+        for (int i = 0; i < MLP_BM / 16; ++i) {
+            const int r = r0 + lm + 16 * i;
+            float v = 0.f;
+            if (kin && r < a.rows) {
+                v = __ldg(a.x + (size_t)r * a.cin + k);
+                if (a.in_scale != nullptr) v = act_fwd(__fmaf_rn(v, sc, sh), a.in_slope);
+            }
+            pa[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+            const int n = n0 + lm + 16 * i;
+            pb[i] = (kin && n < a.cout) ? __ldg(a.w + (size_t)n * a.cin + k) : 0.f;
+        }
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int i = 0; i < MLP_BM / 16; ++i) As[lk][lm + 16 * i] = pa[i];
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) Bs[lk][lm + 16 * i] = pb[i];
+    };
+
+    fetch(0);
+    for (int k0 = 0; k0 < a.cin; k0 += MLP_BK) {
+        __syncthreads();
+        stage();
+        __syncthreads();
+        if (k0 + MLP_BK < a.cin) fetch(k0 + MLP_BK);  // next tile's global loads fly during the FMAs
+#pragma unroll
+        for (int k = 0; k < MLP_BK; ++k) {
+            float av[TM], bv[TN];
+            *reinterpret_cast<float4 *>(&av[0]) = *reinterpret_cast<const float4 *>(&As[k][ty * TM]);
+            *reinterpret_cast<float4 *>(&av[4]) = *reinterpret_cast<const float4 *>(&As[k][ty * TM + 4]);
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bv[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = __fmaf_rn(av[i], bv[j], acc[i][j]);
+        }
+    }
+
+    // epilogue: bias, store, tile statistics
+    const int vr = min(MLP_BM, a.rows - r0);  // valid rows in this tile
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int n = n0 + tx * TN + j;
+        const float b = (n < a.cout && a.bias != nullptr) ? __ldg(a.bias + n) : 0.f;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) acc[i][j] += b;
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int r = r0 + ty * TM + i;
+        if (r < a.rows) {
+            float *dst = a.y + (size_t)r * a.cout + n0 + tx * TN;
+            if (TN == 4 && n0 + tx * TN + 3 < a.cout && (a.cout & 3) == 0) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+                    if (n0 + tx * TN + j < a.cout) dst[j] = acc[i][j];
+            }
+        }
+    }
+    if (a.tile_stats == nullptr) return;
+    // two-pass within the tile: column mean, then sum of squared deviations
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) s += (ty * TM + i < vr) ? acc[i][j] : 0.f;
+        red[ty][tx * TN + j] = s;
+    }
+    __syncthreads();
+    if (tid < BN) {
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) s += red[t][tid];
+        colmean[tid] = s / (float)vr;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const float mu = colmean[tx * TN + j];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const float d = acc[i][j] - mu;
+            s += (ty * TM + i < vr) ? d * d : 0.f;
+        }
+        red[ty][tx * TN + j] = s;
+    }
+    __syncthreads();
+    if (tid < BN && n0 + tid < a.cout) {
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) s += red[t][tid];
+        float *ts = a.tile_stats + ((size_t)blockIdx.x * a.cout + n0 + tid) * 2;
+        ts[0] = colmean[tid];
+        ts[1] = s;
+    }
+}
+
+// One warp per channel merges the per-tile (count, mean, M2) triples in f64 (Chan et al.).
+__global__ void __launch_bounds__(128) bn_finalize_kernel(int rows, int cout, int ntiles, const float *tile_stats,
+                                                          const float *gamma, const float *beta, float eps,
+                                                          float *mean, float *rstd, float *scale, float *shift) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= cout) return;
+    double n = 0.0, mu = 0.0, m2 = 0.0;
+    for (int t = lane; t < ntiles; t += 32) {
+        const double nt = (double)min(MLP_BM, rows - t * MLP_BM);
+        const double mt = tile_stats[((size_t)t * cout + c) * 2], st = tile_stats[((size_t)t * cout + c) * 2 + 1];
+        const double tot = n + nt, d = mt - mu;
+        mu += d * nt / tot;
+        m2 += st + d * d * n * nt / tot;
+        n = tot;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double n2 = __shfl_down_sync(FULL, n, off), mu2 = __shfl_down_sync(FULL, mu, off),
+                     s2 = __shfl_down_sync(FULL, m2, off);
+        const double tot = n + n2;
+        if (n2 > 0.0) {
+            const double d = mu2 - mu;
+            mu += d * n2 / tot;
+            m2 += s2 + d * d * n * n2 / tot;
+            n = tot;
+        }
+    }
+    if (lane == 0) {
+        const double var = m2 / n;  // biased, as BatchNorm normalises
+        const float r = (float)(1.0 / sqrt(var + (double)eps));
+        const float g = gamma != nullptr ? gamma[c] : 1.f, b = beta != nullptr ? beta[c] : 0.f;
+        mean[c] = (float)mu;
+        rstd[c] = r;
+        scale[c] = g * r;
+        shift[c] = b - (float)mu * g * r;
+    }
+}
+
+// out = act(y * scale + shift)
+__global__ void __launch_bounds__(256) bn_act_kernel(long long total4, int c4, const float4 *y, const float4 *scale,
+                                                     const float4 *shift, float slope, float4 *out) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total4; e += (long long)gridDim.x * 256) {
+        const int c = (int)(e % c4);
+        const float4 v = __ldg(y + e), sc = __ldg(scale + c), sh = __ldg(shift + c);
+        out[e] = make_float4(act_fwd(__fmaf_rn(v.x, sc.x, sh.x), slope), act_fwd(__fmaf_rn(v.y, sc.y, sh.y), slope),
+                             act_fwd(__fmaf_rn(v.z, sc.z, sh.z), slope), act_fwd(__fmaf_rn(v.w, sc.w, sh.w), slope));
+    }
+}
+
+// out[g,c] = max_k act(y[g,k,c] * scale + shift); arg[g,c] = first k attaining it
+__global__ void __launch_bounds__(256) bn_act_maxk_kernel(long long total, int k, int c, const float *y,
+                                                          const float *scale, const float *shift, float slope,
+                                                          float *out, int32_t *arg) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long g = e / c;
+        const int ch = (int)(e - g * c);
+        const float sc = __ldg(scale + ch), sh = __ldg(shift + ch);
+        const float *p = y + (size_t)g * k * c + ch;
+        float best = -INFINITY;
+        int bi = 0;
+        for (int j = 0; j < k; ++j) {
+            const float v = act_fwd(__fmaf_rn(__ldg(p + (size_t)j * c), sc, sh), slope);
+            if (v > best) { best = v; bi = j; }
+        }
+        out[e] = best;
+        arg[e] = bi;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// backward
+// -------------------------------------------------------------------------------------------
+// Where the gradient w.r.t. a layer's ACTIVATED output comes from: a dense (rows, c) tensor, or the
+// (groups, c) gradient of a max-over-k output routed through its arg-max.
+struct GradSrc {
+    const float *dense;  // (rows, c) or nullptr
+    const float *dout;   // (groups, c)
+    const int32_t *arg;  // (groups, c)
+    int k;
+    __device__ __forceinline__ float at(long long r, int ch, int c) const {
+        if (dense != nullptr) return __ldg(dense + (size_t)r * c + ch);
+        const long long g = r / k;
+        const int kk = (int)(r - g * k);
+        return __ldg(arg + (size_t)g * c + ch) == kk ? __ldg(dout + (size_t)g * c + ch) : 0.f;
+    }
+};
+
+struct BnRef {  // a layer's raw output and its batch-norm constants
+    const float *y, *mean, *rstd, *scale, *shift;
+    float slope;
+};
+
+// s12[0][c] = sum_r dz, s12[1][c] = sum_r dz * yhat   (dz = g * act'(z)); f64 accumulators, pre-zeroed
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(long long rows, int c, GradSrc gs, BnRef bn,
+                                                            int rows_per_block, double *s12) {
+    __shared__ float r1[256], r2[256];
+    const int cw = c < 64 ? c : 64;  // columns per block (c is a multiple of 16)
+    const int lanes = 256 / cw;
+    const int col = threadIdx.x % cw, rl = threadIdx.x / cw;
+    const int ch = blockIdx.y * cw + col;
+    const long long rb = (long long)blockIdx.x * rows_per_block;
+    const long long re = min(rows, rb + rows_per_block);
+    float s1 = 0.f, s2 = 0.f;
+    if (ch < c && rl < lanes) {
+        const float mu = bn.mean[ch], rs = bn.rstd[ch], sc = bn.scale[ch], sh = bn.shift[ch];
+        if (gs.dense != nullptr) {
+            for (long long r = rb + rl; r < re; r += lanes) {
+                const float yv = __ldg(bn.y + (size_t)r * c + ch);
+                const float dz = __ldg(gs.dense + (size_t)r * c + ch) * act_grad(__fmaf_rn(yv, sc, sh), bn.slope);
+                s1 += dz;
+                s2 += dz * ((yv - mu) * rs);
+            }
+        } else {  // only the arg-max element of each group carries gradient
+            const long long gb = rb / gs.k, ge = (re + gs.k - 1) / gs.k;
+            for (long long g = gb + rl; g < ge; g += lanes) {
+                const long long r = g * gs.k + __ldg(gs.arg + (size_t)g * c + ch);
+                if (r < rb || r >= re) continue;
+                const float yv = __ldg(bn.y + (size_t)r * c + ch);
+                const float dz = __ldg(gs.dout + (size_t)g * c + ch) * act_grad(__fmaf_rn(yv, sc, sh), bn.slope);
+                s1 += dz;
+                s2 += dz * ((yv - mu) * rs);
+            }
+        }
+    }
+    r1[threadIdx.x] = s1;
+    r2[threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.x < cw && ch < c) {
+        float t1 = 0.f, t2 = 0.f;
+        for (int l = 0; l < lanes; ++l) { t1 += r1[l * cw + threadIdx.x]; t2 += r2[l * cw + threadIdx.x]; }
+        atomicAdd(s12 + ch, (double)t1);
+        atomicAdd(s12 + c + ch, (double)t2);
+    }
+}
+
+// Per-channel constants that turn (g, y) into dY, staged once per block.
+struct DyTables {
+    float scale[MLP_MAXC], shift[MLP_MAXC], mean[MLP_MAXC], rstd[MLP_MAXC], s1n[MLP_MAXC], s2n[MLP_MAXC];
+};
+
+__device__ __forceinline__ void load_dy_tables(DyTables &t, const BnRef &bn, const double *s12, int c, long long rows) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        t.scale[i] = bn.scale[i]; t.shift[i] = bn.shift[i]; t.mean[i] = bn.mean[i]; t.rstd[i] = bn.rstd[i];
+        t.s1n[i] = (float)(s12[i] / (double)rows);
+        t.s2n[i] = (float)(s12[c + i] / (double)rows);
+    }
+}
+
+__device__ __forceinline__ float make_dy(const DyTables &t, float g, float yv, int ch, float slope) {
+    const float dz = g * act_grad(__fmaf_rn(yv, t.scale[ch], t.shift[ch]), slope);
+    const float yhat = (yv - t.mean[ch]) * t.rstd[ch];
+    return t.scale[ch] * (dz - t.s1n[ch] - yhat * t.s2n[ch]);
+}
+
+struct DxArgs {
+    int rows, cin, cout;
+    GradSrc gs;     // gradient w.r.t. this layer's activated output (rows, cout)
+    BnRef bn;       // this layer
+    const double *s12;
+    const float *w;  // (cout, cin)
+    float *dx;       // (rows, cin): gradient w.r.t. this layer's input (the previous activation)
+    BnRef prev;      // previous layer (prev.y == nullptr: the input is not a BN output)
+    double *prev_s12;
+};
+
+// dx[r,i] = sum_o dY[r,o] W[o,i]; epilogue accumulates the previous layer's S1/S2.
+template <int BN>
+__global__ void __launch_bounds__(MLP_THREADS) pw_linear_bwd_dx_kernel(const DxArgs a) {
+    constexpr int TN = BN / 16, TM = 8, LDA = MLP_BM + 4, LDB = BN + 4;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    DyTables &tab = *reinterpret_cast<DyTables *>(dyn_smem);
+    __shared__ __align__(16) float As[MLP_BK][LDA];
+    __shared__ __align__(16) float Bs[MLP_BK][LDB];
+    __shared__ float red1[16][BN], red2[16][BN];
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int r0 = blockIdx.x * MLP_BM, n0 = blockIdx.y * BN;
+    const int lk = tid & 15, lm = tid >> 4;     // A loader: 16 consecutive k (= cout) per row
+    const int bn_ = tid % BN, bk = tid / BN;    // B loader: consecutive n (= cin), 256/BN k per pass
+    constexpr int BPASS = MLP_BK * BN / MLP_THREADS > 0 ? MLP_BK * BN / MLP_THREADS : 1;
+    load_dy_tables(tab, a.bn, a.s12, a.cout, a.rows);
+    __syncthreads();
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float pa[MLP_BM / 16], pb[BPASS];
+    auto fetch = [&](int k0) {
+        const int k = k0 + lk;
+#pragma unroll
+        for (int i = 0; i < MLP_BM / 16; ++i) {
+            const int r = r0 + lm + 16 * i;
+            float v = 0.f;
+            if (k < a.cout && r < a.rows)
+                v = make_dy(tab, a.gs.at(r, k, a.cout), __ldg(a.bn.y + (size_t)r * a.cout + k), k, a.bn.slope);
+            pa[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < BPASS; ++i) {
+            const int kk = k0 + bk + i * (MLP_THREADS / BN), n = n0 + bn_;
+            pb[i] = (bk + i * (MLP_THREADS / BN) < MLP_BK && kk < a.cout && n < a.cin) ? __ldg(a.w + (size_t)kk * a.cin + n) : 0.f;
+        }
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int i = 0; i < MLP_BM / 16; ++i) As[lk][lm + 16 * i] = pa[i];
+#pragma unroll
+        for (int i = 0; i < BPASS; ++i)
+            if (bk + i * (MLP_THREADS / BN) < MLP_BK) Bs[bk + i * (MLP_THREADS / BN)][bn_] = pb[i];
+    };
+
+    fetch(0);
+    for (int k0 = 0; k0 < a.cout; k0 += MLP_BK) {
+        __syncthreads();
+        stage();
+        __syncthreads();
+        if (k0 + MLP_BK < a.cout) fetch(k0 + MLP_BK);
+#pragma unroll
+        for (int k = 0; k < MLP_BK; ++k) {
+            float av[TM], bv[TN];
+            *reinterpret_cast<float4 *>(&av[0]) = *reinterpret_cast<const float4 *>(&As[k][ty * TM]);
+            *reinterpret_cast<float4 *>(&av[4]) = *reinterpret_cast<const float4 *>(&As[k][ty * TM + 4]);
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bv[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = __fmaf_rn(av[i], bv[j], acc[i][j]);
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int r = r0 + ty * TM + i;
+        if (r < a.rows)
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+                if (n0 + tx * TN + j < a.cin) a.dx[(size_t)r * a.cin + n0 + tx * TN + j] = acc[i][j];
+    }
+    if (a.prev.y == nullptr) return;
+    // the previous layer's batch-norm backward sums, from the tile still in registers
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int ch = n0 + tx * TN + j;
+        float s1 = 0.f, s2 = 0.f;
+        if (ch < a.cin) {
+            const float mu = a.prev.mean[ch], rs = a.prev.rstd[ch], sc = a.prev.scale[ch], sh = a.prev.shift[ch];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                const int r = r0 + ty * TM + i;
+                if (r < a.rows) {
+                    const float yv = __ldg(a.prev.y + (size_t)r * a.cin + ch);
+                    const float dz = acc[i][j] * act_grad(__fmaf_rn(yv, sc, sh), a.prev.slope);
+                    s1 += dz;
+                    s2 += dz * ((yv - mu) * rs);
+                }
+            }
+        }
+        red1[ty][tx * TN + j] = s1;
+        red2[ty][tx * TN + j] = s2;
+    }
+    __syncthreads();
+    if (tid < BN && n0 + tid < a.cin) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { t1 += red1[t][tid]; t2 += red2[t][tid]; }
+        atomicAdd(a.prev_s12 + n0 + tid, (double)t1);
+        atomicAdd(a.prev_s12 + a.cin + n0 + tid, (double)t2);
+    }
+}
+
+struct DwArgs {
+    int rows, cin, cout, rows_per_block;
+    GradSrc gs;
+    BnRef bn;
+    const double *s12;
+    const float *x;  // (rows, cin): raw input, or the previous layer's raw output when prev.scale != nullptr
+    BnRef prev;
+    float *dw;       // (cout, cin), pre-zeroed, accumulated with atomics
+};
+
+// dW[o,i] += sum_{r in chunk} dY[r,o] * A_prev[r,i]     64 x 64 output tile, 4 x 4 per thread
+__global__ void __launch_bounds__(MLP_THREADS) pw_linear_bwd_dw_kernel(const DwArgs a) {
+    constexpr int BMo = 64, BNi = 64, LD = 64 + 4;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    DyTables &tab = *reinterpret_cast<DyTables *>(dyn_smem);
+    __shared__ __align__(16) float As[MLP_BK][LD];  // [row r][o]
+    __shared__ __align__(16) float Bs[MLP_BK][LD];  // [row r][i]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BMo, n0 = blockIdx.z * BNi;
+    const long long rb = (long long)blockIdx.x * a.rows_per_block;
+    const long long re = min((long long)a.rows, rb + a.rows_per_block);
+    const int lc = tid & 63, lr = tid >> 6;  // loader: 64 consecutive channels, 4 rows per pass
+    load_dy_tables(tab, a.bn, a.s12, a.cout, a.rows);
+    __syncthreads();
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float pa[4], pb[4];
+    auto fetch = [&](long long rr0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long r = rr0 + lr + 4 * i;
+            const int o = m0 + lc, ci = n0 + lc;
+            float va = 0.f, vb = 0.f;
+            if (r < re) {
+                if (o < a.cout)
+                    va = make_dy(tab, a.gs.at(r, o, a.cout), __ldg(a.bn.y + (size_t)r * a.cout + o), o, a.bn.slope);
+                if (ci < a.cin) {
+                    vb = __ldg(a.x + (size_t)r * a.cin + ci);
+                    if (a.prev.scale != nullptr)
+                        vb = act_fwd(__fmaf_rn(vb, __ldg(a.prev.scale + ci), __ldg(a.prev.shift + ci)), a.prev.slope);
+                }
+            }
+            pa[i] = va;
+            pb[i] = vb;
+        }
+    };
+    fetch(rb);
+    for (long long rr0 = rb; rr0 < re; rr0 += MLP_BK) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { As[lr + 4 * i][lc] = pa[i]; Bs[lr + 4 * i][lc] = pb[i]; }
+        __syncthreads();
+        if (rr0 + MLP_BK < re) fetch(rr0 + MLP_BK);
+#pragma unroll
+        for (int k = 0; k < MLP_BK; ++k) {
+            const float4 av = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(aa[i], bb[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int o = m0 + ty * 4 + i;
+        if (o < a.cout)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = n0 + tx * 4 + j;
+                if (ci < a.cin) atomicAdd(a.dw + (size_t)o * a.cin + ci, acc[i][j]);
+            }
+    }
+}
+
+static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : 64); }
+
+}  // namespace i2p
+
+extern "C" {
+
+int i2p_pw_num_tiles(int rows) { return (rows + i2p::MLP_BM - 1) / i2p::MLP_BM; }
+
+int i2p_pw_linear_fwd(int rows, int cin, int cout, const float *x, const float *in_scale, const float *in_shift,
+                      float in_slope, const float *w, const float *bias, float *y, float *tile_stats, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(rows >= 0 && cin >= 1 && cout >= 1, "pw_linear_fwd: bad sizes");
+    if (rows == 0) return I2P_OK;
+    FwdArgs a{rows, cin, cout, x, in_scale, in_shift, in_slope, w, bias, y, tile_stats};
+    const int bn = pick_bn(cout);
+    dim3 grid(ceil_div(rows, MLP_BM), ceil_div(cout, bn));
+    cudaStream_t s = as_stream(stream);
+    if (bn == 16) pw_linear_fwd_kernel<16><<<grid, MLP_THREADS, 0, s>>>(a);
+    else if (bn == 32) pw_linear_fwd_kernel<32><<<grid, MLP_THREADS, 0, s>>>(a);
+    else pw_linear_fwd_kernel<64><<<grid, MLP_THREADS, 0, s>>>(a);
+    return check_launch("pw_linear_fwd");
+}
+
+int i2p_bn_finalize(int rows, int cout, const float *tile_stats, const float *gamma, const float *beta, float eps,
+                    float *mean, float *rstd, float *scale, float *shift, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(rows >= 1 && cout >= 1, "bn_finalize: bad sizes");
+    bn_finalize_kernel<<<ceil_div(cout, 4), 128, 0, as_stream(stream)>>>(rows, cout, ceil_div(rows, MLP_BM), tile_stats,
+                                                                        gamma, beta, eps, mean, rstd, scale, shift);
+    return check_launch("bn_finalize");
+}
+
+int i2p_bn_act(long long rows, int c, const float *y, const float *scale, const float *shift, float slope, float *out,
+               void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(rows >= 0 && c >= 4 && (c & 3) == 0, "bn_act: channel count must be a multiple of 4");
+    if (rows == 0) return I2P_OK;
+    const long long total4 = rows * (c / 4);
+    const long long g = (total4 + 255) / 256;
+    bn_act_kernel<<<(int)(g < 148 * 16 ? g : 148 * 16), 256, 0, as_stream(stream)>>>(
+        total4, c / 4, reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(scale),
+        reinterpret_cast<const float4 *>(shift), slope, reinterpret_cast<float4 *>(out));
+    return check_launch("bn_act");
+}
+
+int i2p_bn_act_maxk(long long groups, int k, int c, const float *y, const float *scale, const float *shift,
+                    float slope, float *out, int32_t *arg, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(groups >= 0 && k >= 1 && c >= 1, "bn_act_maxk: bad sizes");
+    if (groups == 0) return I2P_OK;
+    const long long total = groups * c, g = (total + 255) / 256;
+    bn_act_maxk_kernel<<<(int)(g < 148 * 16 ? g : 148 * 16), 256, 0, as_stream(stream)>>>(total, k, c, y, scale, shift,
+                                                                                         slope, out, arg);
+    return check_launch("bn_act_maxk");
+}
+
+static i2p::GradSrc make_gs(const float *g_dense, const float *dout, const int32_t *arg, int k) {
+    i2p::GradSrc gs;
+    gs.dense = g_dense; gs.dout = dout; gs.arg = arg; gs.k = k > 0 ? k : 1;
+    return gs;
+}
+
+int i2p_bn_bwd_reduce(long long rows, int c, const float *g_dense, const float *dout, const int32_t *arg, int k,
+                      const float *y, const float *mean, const float *rstd, const float *scale, const float *shift,
+                      float slope, double *s12, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(rows >= 0 && c >= 16 && c % 16 == 0 && c <= MLP_MAXC, "bn_bwd_reduce: c must be a multiple of 16, <= 512");
+    I2P_REQUIRE(g_dense != nullptr || (dout != nullptr && arg != nullptr && k >= 1), "bn_bwd_reduce: no gradient source");
+    if (rows == 0) return I2P_OK;
+    const int cw = c < 64 ? c : 64;
+    int rpb = 4096;
+    if (g_dense == nullptr) rpb = (rpb / k) * k > 0 ? (rpb / k) * k : k;   // whole groups per block
+    dim3 grid(ceil_div(rows, rpb), ceil_div(c, cw));
+    BnRef bn{y, mean, rstd, scale, shift, slope};
+    bn_bwd_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, c, make_gs(g_dense, dout, arg, k), bn, rpb, s12);
+    return check_launch("bn_bwd_reduce");
+}
+
+int i2p_pw_linear_bwd_dx(int rows, int cin, int cout, const float *g_dense, const float *dout, const int32_t *arg,
+                         int k, const float *y, const float *mean, const float *rstd, const float *scale,
+                         const float *shift, float slope, const double *s12, const float *w, float *dx,
+                         const float *prev_y, const float *prev_mean, const float *prev_rstd, const float *prev_scale,
+                         const float *prev_shift, float prev_slope, double *prev_s12, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(rows >= 0 && cin >= 1 && cout >= 1 && cout <= MLP_MAXC, "pw_linear_bwd_dx: bad sizes");
+    if (rows == 0) return I2P_OK;
+    DxArgs a;
+    a.rows = rows; a.cin = cin; a.cout = cout; a.gs = make_gs(g_dense, dout, arg, k);
+    a.bn = BnRef{y, mean, rstd, scale, shift, slope};
+    a.s12 = s12; a.w = w; a.dx = dx;
+    a.prev = BnRef{prev_y, prev_mean, prev_rstd, prev_scale, prev_shift, prev_slope};
+    a.prev_s12 = prev_s12;
+    const int bn = pick_bn(cin);
+    dim3 grid(ceil_div(rows, MLP_BM), ceil_div(cin, bn));
+    const size_t smem = sizeof(DyTables);
+    cudaStream_t s = as_stream(stream);
+    if (bn == 16) pw_linear_bwd_dx_kernel<16><<<grid, MLP_THREADS, smem, s>>>(a);
+    else if (bn == 32) pw_linear_bwd_dx_kernel<32><<<grid, MLP_THREADS, smem, s>>>(a);
+    else pw_linear_bwd_dx_kernel<64><<<grid, MLP_THREADS, smem, s>>>(a);
+    return check_launch("pw_linear_bwd_dx");
+}
+
+int i2p_pw_linear_bwd_dw(int rows, int cin, int cout, const float *g_dense, const float *dout, const int32_t *arg,
+                         int k, const float *y, const float *mean, const float *rstd, const float *scale,
+                         const float *shift, float slope, const double *s12, const float *x, const float *prev_scale,
+                         const float *prev_shift, float prev_slope, float *dw, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(rows >= 0 && cin >= 1 && cout >= 1 && cout <= MLP_MAXC, "pw_linear_bwd_dw: bad sizes");
+    if (rows == 0) return I2P_OK;
+    DwArgs a;
+    a.rows = rows; a.cin = cin; a.cout = cout; a.gs = make_gs(g_dense, dout, arg, k);
+    a.bn = BnRef{y, mean, rstd, scale, shift, slope};
+    a.s12 = s12; a.x = x;
+    a.prev = BnRef{nullptr, nullptr, nullptr, prev_scale, prev_shift, prev_slope};
+    a.dw = dw;
+    const int tiles = ceil_div(cout, 64) * ceil_div(cin, 64);
+    // about four waves of CTAs over the 148 SMs, at least 256 rows per CTA
+    int chunks = (4 * 148 + tiles - 1) / tiles;
+    int rpb = (rows + chunks - 1) / chunks;
+    rpb = ((rpb + MLP_BK - 1) / MLP_BK) * MLP_BK;
+    if (rpb < 256) rpb = 256;
+    a.rows_per_block = rpb;
+    dim3 grid(ceil_div(rows, rpb), ceil_div(cout, 64), ceil_div(cin, 64));
+    pw_linear_bwd_dw_kernel<<<grid, MLP_THREADS, sizeof(DyTables), as_stream(stream)>>>(a);
+    return check_launch("pw_linear_bwd_dw");
+}
+}

@@ -5,8 +5,7 @@
 // per-thread arrays in local memory, an O(K * kH*kW) scalar selection sort.
 // This design: one WARP per centre, grid over all B*npoints centres.  The kH*kW window
 // slots live in registers, slot t in lane t%32 register t/32 (<= 5 registers for the
-// reference's 150-slot limit); window loads are issued before the centre is inspected so the
-// two memory latencies overlap.  Valid slots are compacted (ballot + popc) into a per-warp
+// reference's 150-slot limit); an empty centre exits after a single load.  Valid slots are compacted (ballot + popc) into a per-warp
 // shared list and every candidate computes its output position as its RANK in that list --
 // independent compares, no serial chain.  Only when two valid distances are bit-equal does
 // the emitted order depend on the reference's swap history; that (rare) case replays its
@@ -28,6 +27,7 @@ struct SelectArgs {
     const float *xyz1, *xyz2;
     const int32_t *idx_n2, *random_hw;
     int out_w, stride_ch, stride_cw;  // regular centre grid when idx_n2 == nullptr
+    unsigned kw_magic;                // ceil(2^32 / kW): division by multiplication
     int64_t *sel_b, *sel_h, *sel_w;   // drop-in outputs (partial writes)
     float *sel_mask;
     int32_t *flat_idx;                // compact outputs (full writes)
@@ -77,44 +77,42 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectAr
 
     const float *pc = a.xyz1 + (((size_t)b * a.H + sH) * a.W + sW) * 3;
     const float xc = __ldg(pc), yc = __ldg(pc + 1), zc = __ldg(pc + 2);
+    const float dist_c = fmaxf(sqlen(xc, yc, zc), 1e-10f);  // :72
+    const bool centre_valid = !(dist_c <= 1e-10f);           // :74-78 empty centre -> nothing written
 
-    // Window slots: issued before the centre is inspected, so that the two global-memory
-    // latencies overlap instead of chaining.
-    const int half_H = a.kH / 2, half_W = a.kW / 2;
-    const int base_h = sH / a.stride_h - half_H, base_w = sW / a.stride_w - half_W;  // :89-92
-    const float *x2 = a.xyz2 + (size_t)b * a.small_h * a.small_w * 3;
     float qx[R], qy[R], qz[R];
     int hw[R];
     bool inside[R];
+    if (centre_valid) {  // warp-uniform: an empty centre costs one load and the output stores
+        const int half_H = a.kH / 2, half_W = a.kW / 2;
+        const int base_h = sH / a.stride_h - half_H, base_w = sW / a.stride_w - half_W;  // :89-92
+        const float *x2 = a.xyz2 + (size_t)b * a.small_h * a.small_w * 3;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int t = r * 32 + lane;
-        inside[r] = false;
-        hw[r] = 0;
-        qx[r] = qy[r] = qz[r] = 0.f;
-        if (t < total) {
-            const int khw = a.random_hw != nullptr ? __ldg(a.random_hw + t) : t;  // utils.py:84 arange
-            int kh = base_h + khw / a.kW;
-            int kw = base_w + khw % a.kW;
-            bool ok = (kh >= 0) && (kh < a.small_h);
-            if (a.flag & I2P_FLAG_SHIFT) {  // :96-113 the range image is circular in width
-                if (kw < 0) kw += a.small_w;
-                if (kw >= a.small_w) kw -= a.small_w;
-            }
-            // (a window wider than the image can still fall outside after one wrap; the reference
-            // would read out of bounds there, this kernel drops the slot)
-            ok = ok && (kw >= 0) && (kw < a.small_w);
-            if (ok) {
-                const float *q = x2 + ((size_t)kh * a.small_w + kw) * 3;
-                qx[r] = __ldg(q); qy[r] = __ldg(q + 1); qz[r] = __ldg(q + 2);
-                hw[r] = (kh << 16) | kw;
-                inside[r] = true;
+        for (int r = 0; r < R; ++r) {
+            const int t = r * 32 + lane;
+            inside[r] = false;
+            hw[r] = 0;
+            qx[r] = qy[r] = qz[r] = 0.f;
+            if (t < total) {
+                const unsigned khw = a.random_hw != nullptr ? (unsigned)__ldg(a.random_hw + t) : (unsigned)t;
+                const unsigned q = __umulhi(khw, a.kw_magic);  // khw / kW, exact for khw, kW < 2^16
+                int kh = base_h + (int)q;
+                int kw = base_w + (int)(khw - q * (unsigned)a.kW);
+                if (a.flag & I2P_FLAG_SHIFT) {  // :96-113 the range image is circular in width
+                    if (kw < 0) kw += a.small_w;
+                    if (kw >= a.small_w) kw -= a.small_w;
+                }
+                // (a window wider than the image can still fall outside after one wrap; the reference
+                // would read out of bounds there, this kernel drops the slot)
+                if (kh >= 0 && kh < a.small_h && kw >= 0 && kw < a.small_w) {
+                    const float *q3 = x2 + (unsigned)(kh * a.small_w + kw) * 3u;
+                    qx[r] = __ldg(q3); qy[r] = __ldg(q3 + 1); qz[r] = __ldg(q3 + 2);
+                    hw[r] = (kh << 16) | kw;
+                    inside[r] = true;
+                }
             }
         }
     }
-
-    const float dist_c = fmaxf(sqlen(xc, yc, zc), 1e-10f);  // :72
-    const bool centre_valid = !(dist_c <= 1e-10f);           // :74-78 empty centre -> nothing written
 
     if (centre_valid) {
         const float dist_square = __fmul_rn(a.distance, a.distance);  // :26
@@ -225,18 +223,20 @@ static int launch_select(const SelectArgs &a, cudaStream_t stream) {
     I2P_REQUIRE(total >= 1 && total <= SEL_MAX_K && a.K <= SEL_MAX_K,
                 "select: kH*kW=%d or K=%d exceeds 150, the reference's per-thread array size "
                 "(fused_conv_go.cu:52-53)", total, a.K);
-    I2P_REQUIRE(a.small_w < 65536 && a.small_h < 32768 && a.stride_h >= 1 && a.stride_w >= 1,
-                "select: image too large or stride < 1");
+    I2P_REQUIRE(a.small_w < 65536 && a.small_h < 32768 && (long long)a.small_h * a.small_w < (1LL << 30) &&
+                    a.stride_h >= 1 && a.stride_w >= 1, "select: image too large or stride < 1");
     const long long centres = (long long)a.batch * a.npoints;
     if (centres == 0) return I2P_OK;
+    SelectArgs b = a;
+    b.kw_magic = (unsigned)((0x100000000ULL + (unsigned)a.kW - 1) / (unsigned)a.kW);
     const int grid = ceil_div(centres, SEL_WARPS);
     const int block = SEL_WARPS * 32;
     switch ((total + 31) / 32) {
-        case 1: select_k_kernel<1, FLAT><<<grid, block, 0, stream>>>(a); break;
-        case 2: select_k_kernel<2, FLAT><<<grid, block, 0, stream>>>(a); break;
-        case 3: select_k_kernel<3, FLAT><<<grid, block, 0, stream>>>(a); break;
-        case 4: select_k_kernel<4, FLAT><<<grid, block, 0, stream>>>(a); break;
-        default: select_k_kernel<5, FLAT><<<grid, block, 0, stream>>>(a); break;
+        case 1: select_k_kernel<1, FLAT><<<grid, block, 0, stream>>>(b); break;
+        case 2: select_k_kernel<2, FLAT><<<grid, block, 0, stream>>>(b); break;
+        case 3: select_k_kernel<3, FLAT><<<grid, block, 0, stream>>>(b); break;
+        case 4: select_k_kernel<4, FLAT><<<grid, block, 0, stream>>>(b); break;
+        default: select_k_kernel<5, FLAT><<<grid, block, 0, stream>>>(b); break;
     }
     return check_launch("fused_conv_select_k");
 }

@@ -21,8 +21,24 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..modules.basicConv import Conv1d
+from . import fused_mlp as _fm
 from .utils import (FLAG_COPY, FLAG_SHIFT, StrideGrid, check_valid, gather_rows, gather_torch, knn_point,
                     select_flat)
+
+
+USE_FUSED_MLP = True   # False: the layer-by-layer ATen formulation (kept for A/B parity tests)
+
+
+def run_mlp(convs, x, reduce_k=False):
+    """Apply a chain of Conv2d blocks to channels-last x (b, n, k, c); reduce_k: max over the k axis.
+    CUDA tensors take the fused kernels (fused_mlp.py); the layer-by-layer path remains for layer
+    configurations outside the fused kernels' coverage and for the CPU host-logic tests."""
+    convs = list(convs)
+    if USE_FUSED_MLP and x.is_cuda and len(convs) > 0 and _fm.fusable(convs):
+        return _fm.fused_mlp(x, convs, reduce_k)
+    for conv in convs:
+        x = conv._forward_layer(x)
+    return torch.max(x, dim=2)[0] if reduce_k else x
 
 
 class Conv2d(nn.Module):
@@ -44,6 +60,9 @@ class Conv2d(nn.Module):
             self.relu = nn.ReLU(inplace=True) if not leaky_relu else nn.LeakyReLU(0.1, inplace=True)
 
     def forward(self, x):
+        return run_mlp([self], x)
+
+    def _forward_layer(self, x):
         lead = x.shape[:-1]
         y = F.linear(x.reshape(-1, self.in_channels), self.conv.weight.view(self.out_channels, self.in_channels),
                      self.conv.bias)
@@ -143,9 +162,7 @@ class ProjectPointNet(nn.Module):
         return sample_idx, new_xyz_proj_raw, new_xyz_proj, flat, grouped_xyz, grouped_xyz_norm
 
     def _mlp_max(self, new_points, B):
-        for conv in self.mlp_convs:
-            new_points = conv(new_points)
-        return torch.max(new_points, dim=2)[0].view(B, self.out_h, self.out_w, -1)
+        return run_mlp(self.mlp_convs, new_points, reduce_k=True).view(B, self.out_h, self.out_w, -1)
 
     def forward(self, xyz_proj_raw, xyz_proj, feature_proj, sample_idx=None, cfg=None, raw_feat_point=False):
         """xyz_proj_raw / xyz_proj (B,H,W,3), feature_proj (B,H,W,C) ->
@@ -214,15 +231,15 @@ class ProjSetUpconvModule(nn.Module):
         src2, src1 = (xyz2_raw, xyz1_raw) if raw_feat_point else (xyz2, xyz1)
         xyz_diff = gather_rows(src2, flat) - src1.reshape(B, n, 1, 3)
         upfeats = torch.cat([gather_rows(feat2, flat), xyz_diff], dim=3)   # B,N,K,C+3
-        if self.mlp is not None:
-            for conv in self.mlp_conv:
-                upfeats = conv(upfeats)
-        feat1_new = torch.max(upfeats, dim=2)[0].view(B, self.out_h, self.out_w, -1)
+        if self.mlp is not None and len(self.mlp_conv) > 0:
+            feat1_new = run_mlp(self.mlp_conv, upfeats, reduce_k=True)
+        else:
+            feat1_new = torch.max(upfeats, dim=2)[0]
+        feat1_new = feat1_new.view(B, self.out_h, self.out_w, -1)
         if feat1 is not None:
             feat1_new = torch.cat([feat1_new, feat1], dim=3)
         if self.mlp2 is not None:
-            for conv in self.mlp2_conv:
-                feat1_new = conv(feat1_new)
+            feat1_new = run_mlp(self.mlp2_conv, feat1_new)
         return feat1_new.reshape(B, n, -1)
 
     def set_bn(self):
@@ -286,11 +303,9 @@ class CostVolume(nn.Module):
             masked = corr * valid + -1e10 * (1 - valid)
             parts.append(torch.max(masked, 1, keepdim=True)[0].expand(-1, N, -1, -1))
         pi_feat1_new = torch.cat(parts, dim=3)
-        for conv in self.mlp1_convs:
-            pi_feat1_new = conv(pi_feat1_new)
+        pi_feat1_new = run_mlp(self.mlp1_convs, pi_feat1_new)
         pi_concat = torch.cat([self.pi_encoding(pi_xyz_diff_concat), pi_feat1_new], dim=3)
-        for conv in self.mlp2_convs:
-            pi_concat = conv(pi_concat)
+        pi_concat = run_mlp(self.mlp2_convs, pi_concat)
         pi_feat1_new = torch.sum(F.softmax(pi_concat, dim=2) * pi_feat1_new, dim=2)   # B,N,mlp1[-1]
 
         # second stage: re-weight over the nsample 3-D neighbours of every point
@@ -306,8 +321,7 @@ class CostVolume(nn.Module):
         pc_euc_diff = torch.sqrt(torch.sum(pc_xyz_diff * pc_xyz_diff, dim=3, keepdim=True) + 1e-20)
         pc_xyz_encoding = self.pc_encoding(torch.cat([pc_xyz_new, pc_xyz_grouped, pc_xyz_diff, pc_euc_diff], dim=3))
         pc_concat = torch.cat([pc_xyz_encoding, pc_points_new, pc_points_grouped], dim=-1)
-        for conv in self.mlp2_convs_2:
-            pc_concat = conv(pc_concat)
+        pc_concat = run_mlp(self.mlp2_convs_2, pc_concat)
         pc_concat = pc_concat * valid_mask + -1e10 * (1 - valid_mask)
         pc_feat1_new = torch.sum(F.softmax(pc_concat, dim=2) * pc_points_grouped, dim=2)
         return pc_feat1_new.view(B, self.H, self.W, -1)
@@ -365,10 +379,7 @@ class FlowPredictor(nn.Module):
 
     def forward(self, points_f1, upsampled_feat, cost_volume):
         parts = [points_f1, cost_volume] + ([upsampled_feat] if upsampled_feat is not None else [])
-        x = torch.cat(parts, -1).unsqueeze(2)
-        for conv in self.mlp_conv:
-            x = conv(x)
-        return x.squeeze(2)
+        return run_mlp(self.mlp_conv, torch.cat(parts, -1).unsqueeze(2)).squeeze(2)
 
     def set_bn(self):
         for conv in self.mlp_conv:

@@ -1,0 +1,136 @@
+"""Fused shared MLP: a chain of [1x1 conv -> batch-statistics BatchNorm -> (Leaky)ReLU] layers over a
+channels-last (rows, C) tensor, optionally max-reduced over groups of K consecutive rows, as ONE
+autograd.Function on the kernels of i2pnet_b200/csrc/mlp.cu.
+
+The reference runs each layer as permute / nn.Conv2d / BatchNorm2d / activation / permute
+(src/projectPN/PPBackbone_center.py:35-46) and the reduction as torch.max(dim=2) (:127, :198, :284);
+autograd then replays every one of those passes backwards.  Here only the raw layer outputs y_l
+touch HBM: one GEMM launch + one tiny finalize per layer forward, two GEMM launches per layer
+backward (see mlp.cu for the algebra).  Numerically it is the same f32 computation with exact
+(merged Welford) batch statistics; the bias feeding a BatchNorm gets an exactly zero gradient
+instead of autograd's rounding noise.
+"""
+import torch
+from torch.autograd import Function
+
+from .. import _cabi
+from .._cabi import _ptr, call, f32, i32
+
+f64 = torch.float64
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class FusedMLPFunction(Function):
+    @staticmethod
+    def forward(ctx, x, reduce_k, slopes, eps, *params):
+        """x (rows, cin) f32 contiguous; params = (w_1 (c1,cin), b_1, gamma_1, beta_1, w_2, ...);
+        reduce_k: 0 -> out (rows, c_L); K > 0 -> out (rows / K, c_L) = max over each K consecutive rows."""
+        dev = x.device
+        rows = x.shape[0]
+        L = len(params) // 4
+        ntiles = _cabi.lib().i2p_pw_num_tiles(rows)
+        ys, stats = [], []
+        inp, in_stats, in_slope = x, None, 1.0
+        for l in range(L):
+            w, b, gamma, beta = params[4 * l:4 * l + 4]
+            cout, cin = w.shape
+            y = torch.empty(rows, cout, dtype=f32, device=dev)
+            tiles = torch.empty(ntiles, cout, 2, dtype=f32, device=dev)
+            call("i2p_pw_linear_fwd", dev, rows, cin, cout, _ptr(inp, f32, "x", dev),
+                 _p(in_stats[2]) if in_stats is not None else None, _p(in_stats[3]) if in_stats is not None else None,
+                 float(in_slope), _ptr(w, f32, "weight", dev), _ptr(b, f32, "bias", dev), y.data_ptr(), tiles.data_ptr())
+            st = torch.empty(4, cout, dtype=f32, device=dev)  # mean, rstd, scale, shift
+            call("i2p_bn_finalize", dev, rows, cout, tiles.data_ptr(), _ptr(gamma, f32, "gamma", dev),
+                 _ptr(beta, f32, "beta", dev), float(eps[l]), st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(),
+                 st[3].data_ptr())
+            ys.append(y)
+            stats.append(st)
+            inp, in_stats, in_slope = y, st, slopes[l]
+        c_last = ys[-1].shape[1]
+        st = stats[-1]
+        arg = None
+        if reduce_k:
+            groups = rows // reduce_k
+            out = torch.empty(groups, c_last, dtype=f32, device=dev)
+            arg = torch.empty(groups, c_last, dtype=i32, device=dev)
+            call("i2p_bn_act_maxk", dev, groups, reduce_k, c_last, ys[-1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(),
+                 float(slopes[-1]), out.data_ptr(), arg.data_ptr())
+        else:
+            out = torch.empty(rows, c_last, dtype=f32, device=dev)
+            call("i2p_bn_act", dev, rows, c_last, ys[-1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), float(slopes[-1]),
+                 out.data_ptr())
+        ctx.save_for_backward(x, *params, *ys, *stats, *([arg] if arg is not None else []))
+        ctx.meta = (L, reduce_k, tuple(slopes))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        L, reduce_k, slopes = ctx.meta
+        saved = ctx.saved_tensors
+        x, params = saved[0], saved[1:1 + 4 * L]
+        ys, stats = saved[1 + 4 * L:1 + 5 * L], saved[1 + 5 * L:1 + 6 * L]
+        arg = saved[1 + 6 * L] if reduce_k else None
+        dev = x.device
+        rows = x.shape[0]
+        grad_out = grad_out.contiguous()
+        s12 = [torch.zeros(2, ys[l].shape[1], dtype=f64, device=dev) for l in range(L)]
+
+        def src(l, g):  # (g_dense, dout, arg, k) of layer l
+            if l == L - 1 and reduce_k:
+                return None, grad_out.data_ptr(), arg.data_ptr(), reduce_k
+            return g.data_ptr(), None, None, 1
+
+        def bn(l):
+            st = stats[l]
+            return (ys[l].data_ptr(), st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(),
+                    float(slopes[l]))
+
+        g = None if reduce_k else grad_out
+        c_last = ys[-1].shape[1]
+        call("i2p_bn_bwd_reduce", dev, rows, c_last, *src(L - 1, g), *bn(L - 1), s12[L - 1].data_ptr())
+        grads = [None] * (4 * L)
+        dx = None
+        for l in range(L - 1, -1, -1):
+            w = params[4 * l]
+            cout, cin = w.shape
+            inp = ys[l - 1] if l > 0 else x
+            pst = stats[l - 1] if l > 0 else None
+            dw = torch.zeros(cout, cin, dtype=f32, device=dev)
+            call("i2p_pw_linear_bwd_dw", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
+                 _p(pst[2]) if pst is not None else None, _p(pst[3]) if pst is not None else None,
+                 float(slopes[l - 1]) if l > 0 else 1.0, dw.data_ptr())
+            grads[4 * l] = dw
+            grads[4 * l + 1] = torch.zeros(cout, dtype=f32, device=dev)  # bias under BN: exactly zero
+            grads[4 * l + 2] = s12[l][1].to(f32)                          # d gamma = sum dz * yhat
+            grads[4 * l + 3] = s12[l][0].to(f32)                          # d beta  = sum dz
+            if l > 0 or ctx.needs_input_grad[0]:
+                dx = torch.empty(rows, cin, dtype=f32, device=dev)
+                call("i2p_pw_linear_bwd_dx", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), w.data_ptr(),
+                     dx.data_ptr(), *(bn(l - 1) if l > 0 else (None, None, None, None, None, 1.0)),
+                     s12[l - 1].data_ptr() if l > 0 else None)
+                g = dx
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None, *grads)
+
+
+def fusable(convs):
+    """The fused path covers the configuration every model in the reference uses (use_bn_p,
+    use_bn_input: affine BatchNorm on batch statistics after every 1x1 conv)."""
+    return all(c.bn and not c.bn_linear.track_running_stats and c.bn_linear.affine and c.out_channels % 16 == 0
+               and c.out_channels <= 512 for c in convs)
+
+
+def fused_mlp(x, convs, reduce_k=False):
+    """x (..., [K,] cin) -> (..., [K,] c_L), or (..., c_L) with the max over the K axis when reduce_k."""
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    params, slopes, eps = [], [], []
+    for c in convs:
+        params += [c.conv.weight.view(c.out_channels, c.in_channels), c.conv.bias, c.bn_linear.weight, c.bn_linear.bias]
+        slopes.append(1.0 if not c.activation_fn else (0.1 if c.leaky_relu else 0.0))
+        eps.append(c.bn_linear.eps)
+    k = int(lead[-1]) if reduce_k else 0
+    out = FusedMLPFunction.apply(x2, k, tuple(slopes), tuple(eps), *params)
+    return out.view(*(lead[:-1] if reduce_k else lead), out.shape[-1])

@@ -131,6 +131,48 @@ int i2p_project_seq(int b, int n, int H, int W, float fup_deg, float fdown_deg, 
                     const float *const *feats, const int *fdims, float *xyz_proj, float *const *feat_projs,
                     int32_t *owner, void *stream);
 
+/* ---- shared per-point MLP: replaces the Conv2d block of src/projectPN/PPBackbone_center.py:10-46 ----
+ * (permute -> 1x1 nn.Conv2d -> BatchNorm2d on batch statistics -> (Leaky)ReLU -> permute), forward and
+ * backward, on channels-last (rows, C) tensors.  Only the raw pre-normalisation outputs y are
+ * materialised; normalise + activation are folded into the next kernel's operand load.
+ * Activation: act(z) = z > 0 ? z : slope * z  (slope 0 = ReLU, 0.1 = LeakyReLU(0.1), 1 = identity). */
+
+/* Number of 128-row tiles (rows of the tile_stats buffer). */
+int i2p_pw_num_tiles(int rows);
+/* y = f(x) W^T + bias, f(x) = act(x * in_scale + in_shift) or x when in_scale == NULL.
+ * x (rows,cin), w (cout,cin), y (rows,cout); tile_stats (ntiles,cout,2) per-tile (mean, M2) or NULL. */
+int i2p_pw_linear_fwd(int rows, int cin, int cout, const float *x, const float *in_scale, const float *in_shift,
+                      float in_slope, const float *w, const float *bias, float *y, float *tile_stats, void *stream);
+/* Exact (f64, Chan) merge of the tile statistics -> mean, rstd = 1/sqrt(var_biased + eps),
+ * scale = gamma * rstd, shift = beta - mean * scale.  All (cout). */
+int i2p_bn_finalize(int rows, int cout, const float *tile_stats, const float *gamma, const float *beta, float eps,
+                    float *mean, float *rstd, float *scale, float *shift, void *stream);
+/* out = act(y * scale + shift), (rows, c), c % 4 == 0 */
+int i2p_bn_act(long long rows, int c, const float *y, const float *scale, const float *shift, float slope, float *out,
+               void *stream);
+/* out[g,c] = max_k act(y[g,k,c] * scale + shift), arg[g,c] = first k attaining it; y (groups,k,c) */
+int i2p_bn_act_maxk(long long groups, int k, int c, const float *y, const float *scale, const float *shift,
+                    float slope, float *out, int32_t *arg, void *stream);
+/* Batch-norm backward sums of a layer: s12[0,c] = sum_r dz, s12[1,c] = sum_r dz * yhat (f64, pre-zeroed),
+ * dz = g * act'(y*scale+shift).  g is either dense (rows,c) or, when g_dense == NULL, the gradient
+ * dout (rows/k, c) of a max-over-k output routed through arg. */
+int i2p_bn_bwd_reduce(long long rows, int c, const float *g_dense, const float *dout, const int32_t *arg, int k,
+                      const float *y, const float *mean, const float *rstd, const float *scale, const float *shift,
+                      float slope, double *s12, void *stream);
+/* dx (rows,cin) = dY W with dY = scale * (dz - S1/n - yhat * S2/n) rebuilt on the fly; when prev_y != NULL
+ * (the input was itself a normalised layer, raw output prev_y (rows,cin)) the epilogue accumulates that
+ * layer's s12 into prev_s12 (pre-zeroed). */
+int i2p_pw_linear_bwd_dx(int rows, int cin, int cout, const float *g_dense, const float *dout, const int32_t *arg,
+                         int k, const float *y, const float *mean, const float *rstd, const float *scale,
+                         const float *shift, float slope, const double *s12, const float *w, float *dx,
+                         const float *prev_y, const float *prev_mean, const float *prev_rstd, const float *prev_scale,
+                         const float *prev_shift, float prev_slope, double *prev_s12, void *stream);
+/* dw (cout,cin) += dY^T A, A = act(x * prev_scale + prev_shift) or x when prev_scale == NULL; dw pre-zeroed. */
+int i2p_pw_linear_bwd_dw(int rows, int cin, int cout, const float *g_dense, const float *dout, const int32_t *arg,
+                         int k, const float *y, const float *mean, const float *rstd, const float *scale,
+                         const float *shift, float slope, const double *s12, const float *x, const float *prev_scale,
+                         const float *prev_shift, float prev_slope, float *dw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,7 +80,7 @@ def _select(x1, x2, idx_n2, kernel, K, flag, dist, sh=1, sw=1):
     _, h, w, m = orc.fused_conv_select_k(x1.detach().cpu().numpy(), x2.detach().cpu().numpy(), idx_n2,
                                          np.arange(kernel[0] * kernel[1], dtype=np.int32), kernel[0], kernel[1], K,
                                          flag, dist, sh, sw)
-    return torch.from_numpy(h * x2.shape[2] + w).to(x1.device), torch.from_numpy(m)[..., None].to(x1.device)
+    return torch.from_numpy(h * x2.shape[2] + w).to(x1.device), torch.from_numpy(m)[..., None].to(x1.device, x1.dtype)
 
 
 def _gather(feature, flat):
@@ -218,7 +218,8 @@ def forward(sd, rgb, lidar, lidar_raw, intrinsic, lidar_feature=None, cfg=KittiS
     feat0 = torch.zeros(B, N, 3) if lidar_feature is None else lidar_feature.cpu()
     raw_img, (_, cam_img) = orc.project_seq(lidar_raw.cpu().numpy(), [feat0.numpy(), lidar.cpu().numpy()], cfg.init_H,
                                             cfg.init_W, cfg.fup, cfg.fdown)                # M:247, U:111-187
-    raw_l, xyz_l, feat_l = torch.from_numpy(raw_img).to(dev), torch.from_numpy(cam_img).to(dev), None
+    dt = rgb.dtype     # f32 everywhere except the f64 "truth" run of the GPU gradient test
+    raw_l, xyz_l, feat_l = torch.from_numpy(raw_img).to(dev, dt), torch.from_numpy(cam_img).to(dev, dt), None
     Hs = [int(np.ceil(cfg.init_H / s)) for s in np.cumprod(cfg.stride_Hs)]
     Ws = [int(np.ceil(cfg.init_W / s)) for s in np.cumprod(cfg.stride_Ws)]
     levels = []
@@ -231,12 +232,12 @@ def forward(sd, rgb, lidar, lidar_raw, intrinsic, lidar_feature=None, cfg=KittiS
     keep("LiDAR_lv2", levels[1][2]), keep("LiDAR_lv3", LF3)
     H3, W3, H4, W4 = Hs[2], Ws[2], Hs[3], Ws[3]
 
-    K3 = intrinsic.float().clone()                                                         # M:443-449
+    K3 = intrinsic.to(dt).clone()                                                          # M:443-449
     h, w = RF.shape[2:]
     K3[:, 0, 0] *= w / rgb.shape[3]; K3[:, 0, 2] *= w / rgb.shape[3]
     K3[:, 1, 1] *= h / rgb.shape[2]; K3[:, 1, 2] *= h / rgb.shape[2]
-    jj, ii = torch.meshgrid(torch.arange(w, dtype=torch.float32, device=dev),
-                            torch.arange(h, dtype=torch.float32, device=dev), indexing="xy")
+    jj, ii = torch.meshgrid(torch.arange(w, dtype=dt, device=dev), torch.arange(h, dtype=dt, device=dev),
+                            indexing="xy")
     pix = torch.stack([jj, ii, torch.ones_like(jj)], -1).reshape(1, -1, 3).repeat(B, 1, 1)
     RF_index = torch.bmm(torch.inverse(K3), pix.permute(0, 2, 1)).permute(0, 2, 1)         # M:282-284
     RF3 = RF.reshape(B, RF.shape[1], -1).permute(0, 2, 1)
@@ -254,8 +255,8 @@ def forward(sd, rgb, lidar, lidar_raw, intrinsic, lidar_feature=None, cfg=KittiS
     l4_w = l4_w * v4 + -1e10 * (1 - v4)
     q4, t4 = _head(sd, "l4_head", l4_pred, l4_w)
 
-    zero = torch.zeros(B, 1, device=dev)
-    homo = torch.cat([torch.zeros(B, H3 * W3, 1, device=dev), P3_l4], -1)                  # W:78-94
+    zero = torch.zeros(B, 1, device=dev, dtype=dt)
+    homo = torch.cat([torch.zeros(B, H3 * W3, 1, device=dev, dtype=dt), P3_l4], -1)        # W:78-94
     homo = _mul_q(_mul_q(q4, homo), _inv_q(q4)) + torch.cat([zero, t4], -1).reshape(B, 1, 4)
     P3_w = homo[:, :, 1:4] * _check_valid(P3_l4)
     w_up = _upconv(sd, "set_upconv0_w_upsample", 0, cfg, P3, P4, P3_raw, P4_raw, LF3, l4_w.view(B, H4, W4, -1))
