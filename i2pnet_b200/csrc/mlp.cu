@@ -18,6 +18,8 @@
 //       accumulates the S1, S2 sums the NEXT (earlier) layer's batch-norm backward needs.
 // All arithmetic is f32 FMA (the parity configuration: 1e-4 relative rules out TF32); tiles are
 // 128 x {16,32,64} x 16 with 8 x {1,2,4} register blocking.
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace i2p {
@@ -41,8 +43,21 @@ struct FwdArgs {
     float *y, *tile_stats;  // tile_stats (ntiles, cout, 2) or nullptr
 };
 
+template <int TN>
+__device__ __forceinline__ void load_bvec(float (&bv)[TN], const float *p) {
+    if (TN == 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(p);
+        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+    } else if (TN == 2) {
+        const float2 v = *reinterpret_cast<const float2 *>(p);
+        bv[0] = v.x; bv[1] = v.y;
+    } else {
+        bv[0] = p[0];
+    }
+}
+
 template <int BN>
-__global__ void __launch_bounds__(MLP_THREADS) pw_linear_fwd_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(MLP_THREADS, 2) pw_linear_fwd_kernel(const FwdArgs a) {
     constexpr int TN = BN / 16, TM = 8, LDA = MLP_BM + 4, LDB = BN + 4;
     __shared__ __align__(16) float As[MLP_BK][LDA];
     __shared__ __align__(16) float Bs[MLP_BK][LDB];
@@ -52,6 +67,7 @@ __global__ void __launch_bounds__(MLP_THREADS) pw_linear_fwd_kernel(const FwdArg
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int r0 = blockIdx.x * MLP_BM, n0 = blockIdx.y * BN;
     const int lk = tid & 15, lm = tid >> 4;  // loader coordinates: 16 consecutive k per row
+    const bool has_tf = a.in_scale != nullptr;
 
     float acc[TM][TN];
 #pragma unroll
@@ -59,21 +75,18 @@ __global__ void __launch_bounds__(MLP_THREADS) pw_linear_fwd_kernel(const FwdArg
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    float pa[MLP_BM / 16], pb[BN / 16];
+    // Software pipeline: fetch() only ISSUES the global loads of the next k-tile (raw values, no
+    // dependent arithmetic); stage() applies the input transform and writes shared memory one
+    // iteration later, so the load latency is covered by the FMAs of the current tile.
+    float pa[MLP_BM / 16], pb[BN / 16], psc = 1.f, psh = 0.f;
     auto fetch = [&](int k0) {
         const int k = k0 + lk;
         const bool kin = k < a.cin;
-        float sc = 1.f, sh = 0.f;
-        if (a.in_scale != nullptr && kin) { sc = __ldg(a.in_scale + k); sh = __ldg(a.in_shift + k); }
+        if (has_tf && kin) { psc = __ldg(a.in_scale + k); psh = __ldg(a.in_shift + k); }
 #pragma unroll
         for (int i = 0; i < MLP_BM / 16; ++i) {
             const int r = r0 + lm + 16 * i;
-            float v = 0.f;
-            if (kin && r < a.rows) {
-                v = __ldg(a.x + (size_t)r * a.cin + k);
-                if (a.in_scale != nullptr) v = act_fwd(__fmaf_rn(v, sc, sh), a.in_slope);
-            }
-            pa[i] = v;
+            pa[i] = (kin && r < a.rows) ? __ldg(a.x + (size_t)r * a.cin + k) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < BN / 16; ++i) {
@@ -81,9 +94,14 @@ __global__ void __launch_bounds__(MLP_THREADS) pw_linear_fwd_kernel(const FwdArg
             pb[i] = (kin && n < a.cout) ? __ldg(a.w + (size_t)n * a.cin + k) : 0.f;
         }
     };
-    auto stage = [&]() {
+    auto stage = [&](int k0) {
+        const bool kin = k0 + lk < a.cin;
 #pragma unroll
-        for (int i = 0; i < MLP_BM / 16; ++i) As[lk][lm + 16 * i] = pa[i];
+        for (int i = 0; i < MLP_BM / 16; ++i) {
+            float v = pa[i];
+            if (has_tf) v = (kin && r0 + lm + 16 * i < a.rows) ? act_fwd(__fmaf_rn(v, psc, psh), a.in_slope) : 0.f;
+            As[lk][lm + 16 * i] = v;
+        }
 #pragma unroll
         for (int i = 0; i < BN / 16; ++i) Bs[lk][lm + 16 * i] = pb[i];
     };
@@ -91,16 +109,15 @@ __global__ void __launch_bounds__(MLP_THREADS) pw_linear_fwd_kernel(const FwdArg
     fetch(0);
     for (int k0 = 0; k0 < a.cin; k0 += MLP_BK) {
         __syncthreads();
-        stage();
+        stage(k0);
         __syncthreads();
-        if (k0 + MLP_BK < a.cin) fetch(k0 + MLP_BK);  // next tile's global loads fly during the FMAs
+        if (k0 + MLP_BK < a.cin) fetch(k0 + MLP_BK);
 #pragma unroll
         for (int k = 0; k < MLP_BK; ++k) {
             float av[TM], bv[TN];
             *reinterpret_cast<float4 *>(&av[0]) = *reinterpret_cast<const float4 *>(&As[k][ty * TM]);
             *reinterpret_cast<float4 *>(&av[4]) = *reinterpret_cast<const float4 *>(&As[k][ty * TM + 4]);
-#pragma unroll
-            for (int j = 0; j < TN; ++j) bv[j] = Bs[k][tx * TN + j];
+            load_bvec<TN>(bv, &Bs[k][tx * TN]);
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -170,42 +187,44 @@ __global__ void __launch_bounds__(MLP_THREADS) pw_linear_fwd_kernel(const FwdArg
     }
 }
 
-// One warp per channel merges the per-tile (count, mean, M2) triples in f64 (Chan et al.).
+// One 128-thread block per channel merges the per-tile (count, mean, M2) triples (Chan et al.).
+// The merge formula only ever ADDS non-negative terms to M2, so f32 is accurate here; the final
+// variance -> rstd step is done in f64.
+__device__ __forceinline__ void chan_merge(float &n, float &mu, float &m2, float n2, float mu2, float s2) {
+    if (n2 > 0.f) {
+        const float tot = n + n2, d = mu2 - mu, f = n2 / tot;
+        mu += d * f;
+        m2 += s2 + d * d * n * f;
+        n = tot;
+    }
+}
+
 __global__ void __launch_bounds__(128) bn_finalize_kernel(int rows, int cout, int ntiles, const float *tile_stats,
                                                           const float *gamma, const float *beta, float eps,
                                                           float *mean, float *rstd, float *scale, float *shift) {
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (c >= cout) return;
-    double n = 0.0, mu = 0.0, m2 = 0.0;
-    for (int t = lane; t < ntiles; t += 32) {
-        const double nt = (double)min(MLP_BM, rows - t * MLP_BM);
-        const double mt = tile_stats[((size_t)t * cout + c) * 2], st = tile_stats[((size_t)t * cout + c) * 2 + 1];
-        const double tot = n + nt, d = mt - mu;
-        mu += d * nt / tot;
-        m2 += st + d * d * n * nt / tot;
-        n = tot;
+    __shared__ float sn[4], smu[4], sm2[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x;
+    float n = 0.f, mu = 0.f, m2 = 0.f;
+    for (int t = threadIdx.x; t < ntiles; t += 128) {
+        const float2 ts = __ldg(reinterpret_cast<const float2 *>(tile_stats) + (size_t)t * cout + c);
+        chan_merge(n, mu, m2, (float)min(MLP_BM, rows - t * MLP_BM), ts.x, ts.y);
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double n2 = __shfl_down_sync(FULL, n, off), mu2 = __shfl_down_sync(FULL, mu, off),
-                     s2 = __shfl_down_sync(FULL, m2, off);
-        const double tot = n + n2;
-        if (n2 > 0.0) {
-            const double d = mu2 - mu;
-            mu += d * n2 / tot;
-            m2 += s2 + d * d * n * n2 / tot;
-            n = tot;
-        }
-    }
-    if (lane == 0) {
-        const double var = m2 / n;  // biased, as BatchNorm normalises
+    for (int off = 16; off > 0; off >>= 1)
+        chan_merge(n, mu, m2, __shfl_down_sync(FULL, n, off), __shfl_down_sync(FULL, mu, off),
+                   __shfl_down_sync(FULL, m2, off));
+    if (lane == 0) { sn[warp] = n; smu[warp] = mu; sm2[warp] = m2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 4; ++w) chan_merge(n, mu, m2, sn[w], smu[w], sm2[w]);
+        const double var = (double)m2 / (double)n;  // biased, as BatchNorm normalises
         const float r = (float)(1.0 / sqrt(var + (double)eps));
         const float g = gamma != nullptr ? gamma[c] : 1.f, b = beta != nullptr ? beta[c] : 0.f;
-        mean[c] = (float)mu;
+        mean[c] = mu;
         rstd[c] = r;
         scale[c] = g * r;
-        shift[c] = b - (float)mu * g * r;
+        shift[c] = b - mu * g * r;
     }
 }
 
@@ -325,6 +344,31 @@ __device__ __forceinline__ float make_dy(const DyTables &t, float g, float yv, i
     return t.scale[ch] * (dz - t.s1n[ch] - yhat * t.s2n[ch]);
 }
 
+// Raw operands of one dY element, as fetched (no dependent arithmetic until stage time).
+struct RawDy {
+    float g, y;
+    int arg;  // max-k source: the arg-max row offset of this (group, channel); dense source: unused
+};
+
+__device__ __forceinline__ RawDy fetch_dy(const GradSrc &gs, const float *y, long long r, int ch, int c) {
+    RawDy v;
+    v.y = __ldg(y + (size_t)r * c + ch);
+    if (gs.dense != nullptr) {
+        v.g = __ldg(gs.dense + (size_t)r * c + ch);
+        v.arg = INT_MIN;  // dense source: always taken
+    } else {
+        const long long g = r / gs.k;
+        v.g = __ldg(gs.dout + (size_t)g * c + ch);
+        v.arg = __ldg(gs.arg + (size_t)g * c + ch) - (int)(r - g * gs.k);  // 0 <=> this row is the arg-max
+    }
+    return v;
+}
+
+__device__ __forceinline__ float finish_dy(const DyTables &t, const RawDy &v, int ch, float slope) {
+    const float g = (v.arg == 0 || v.arg == INT_MIN) ? v.g : 0.f;
+    return make_dy(t, g, v.y, ch, slope);
+}
+
 struct DxArgs {
     int rows, cin, cout;
     GradSrc gs;     // gradient w.r.t. this layer's activated output (rows, cout)
@@ -338,7 +382,7 @@ struct DxArgs {
 
 // dx[r,i] = sum_o dY[r,o] W[o,i]; epilogue accumulates the previous layer's S1/S2.
 template <int BN>
-__global__ void __launch_bounds__(MLP_THREADS) pw_linear_bwd_dx_kernel(const DxArgs a) {
+__global__ void __launch_bounds__(MLP_THREADS, 2) pw_linear_bwd_dx_kernel(const DxArgs a) {
     constexpr int TN = BN / 16, TM = 8, LDA = MLP_BM + 4, LDB = BN + 4;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     DyTables &tab = *reinterpret_cast<DyTables *>(dyn_smem);
@@ -350,9 +394,8 @@ __global__ void __launch_bounds__(MLP_THREADS) pw_linear_bwd_dx_kernel(const DxA
     const int r0 = blockIdx.x * MLP_BM, n0 = blockIdx.y * BN;
     const int lk = tid & 15, lm = tid >> 4;     // A loader: 16 consecutive k (= cout) per row
     const int bn_ = tid % BN, bk = tid / BN;    // B loader: consecutive n (= cin), 256/BN k per pass
-    constexpr int BPASS = MLP_BK * BN / MLP_THREADS > 0 ? MLP_BK * BN / MLP_THREADS : 1;
+    constexpr int BPASS = MLP_BK * BN / MLP_THREADS;
     load_dy_tables(tab, a.bn, a.s12, a.cout, a.rows);
-    __syncthreads();
 
     float acc[TM][TN];
 #pragma unroll
@@ -360,35 +403,34 @@ __global__ void __launch_bounds__(MLP_THREADS) pw_linear_bwd_dx_kernel(const DxA
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    float pa[MLP_BM / 16], pb[BPASS];
+    RawDy pa[MLP_BM / 16];
+    float pb[BPASS];
     auto fetch = [&](int k0) {
         const int k = k0 + lk;
 #pragma unroll
         for (int i = 0; i < MLP_BM / 16; ++i) {
             const int r = r0 + lm + 16 * i;
-            float v = 0.f;
-            if (k < a.cout && r < a.rows)
-                v = make_dy(tab, a.gs.at(r, k, a.cout), __ldg(a.bn.y + (size_t)r * a.cout + k), k, a.bn.slope);
-            pa[i] = v;
+            if (k < a.cout && r < a.rows) pa[i] = fetch_dy(a.gs, a.bn.y, r, k, a.cout);
         }
 #pragma unroll
         for (int i = 0; i < BPASS; ++i) {
             const int kk = k0 + bk + i * (MLP_THREADS / BN), n = n0 + bn_;
-            pb[i] = (bk + i * (MLP_THREADS / BN) < MLP_BK && kk < a.cout && n < a.cin) ? __ldg(a.w + (size_t)kk * a.cin + n) : 0.f;
+            pb[i] = (kk < a.cout && n < a.cin) ? __ldg(a.w + (size_t)kk * a.cin + n) : 0.f;
         }
     };
-    auto stage = [&]() {
+    auto stage = [&](int k0) {
+        const int k = k0 + lk;
 #pragma unroll
-        for (int i = 0; i < MLP_BM / 16; ++i) As[lk][lm + 16 * i] = pa[i];
+        for (int i = 0; i < MLP_BM / 16; ++i)
+            As[lk][lm + 16 * i] = (k < a.cout && r0 + lm + 16 * i < a.rows) ? finish_dy(tab, pa[i], k, a.bn.slope) : 0.f;
 #pragma unroll
-        for (int i = 0; i < BPASS; ++i)
-            if (bk + i * (MLP_THREADS / BN) < MLP_BK) Bs[bk + i * (MLP_THREADS / BN)][bn_] = pb[i];
+        for (int i = 0; i < BPASS; ++i) Bs[bk + i * (MLP_THREADS / BN)][bn_] = pb[i];
     };
 
     fetch(0);
     for (int k0 = 0; k0 < a.cout; k0 += MLP_BK) {
-        __syncthreads();
-        stage();
+        __syncthreads();   // (first iteration: also publishes the dY tables)
+        stage(k0);
         __syncthreads();
         if (k0 + MLP_BK < a.cout) fetch(k0 + MLP_BK);
 #pragma unroll
@@ -396,8 +438,7 @@ __global__ void __launch_bounds__(MLP_THREADS) pw_linear_bwd_dx_kernel(const DxA
             float av[TM], bv[TN];
             *reinterpret_cast<float4 *>(&av[0]) = *reinterpret_cast<const float4 *>(&As[k][ty * TM]);
             *reinterpret_cast<float4 *>(&av[4]) = *reinterpret_cast<const float4 *>(&As[k][ty * TM + 4]);
-#pragma unroll
-            for (int j = 0; j < TN; ++j) bv[j] = Bs[k][tx * TN + j];
+            load_bvec<TN>(bv, &Bs[k][tx * TN]);
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -421,14 +462,18 @@ __global__ void __launch_bounds__(MLP_THREADS) pw_linear_bwd_dx_kernel(const DxA
         float s1 = 0.f, s2 = 0.f;
         if (ch < a.cin) {
             const float mu = a.prev.mean[ch], rs = a.prev.rstd[ch], sc = a.prev.scale[ch], sh = a.prev.shift[ch];
+            float yv[TM];
 #pragma unroll
             for (int i = 0; i < TM; ++i) {
                 const int r = r0 + ty * TM + i;
-                if (r < a.rows) {
-                    const float yv = __ldg(a.prev.y + (size_t)r * a.cin + ch);
-                    const float dz = acc[i][j] * act_grad(__fmaf_rn(yv, sc, sh), a.prev.slope);
+                yv[i] = r < a.rows ? __ldg(a.prev.y + (size_t)r * a.cin + ch) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                if (r0 + ty * TM + i < a.rows) {
+                    const float dz = acc[i][j] * act_grad(__fmaf_rn(yv[i], sc, sh), a.prev.slope);
                     s1 += dz;
-                    s2 += dz * ((yv - mu) * rs);
+                    s2 += dz * ((yv[i] - mu) * rs);
                 }
             }
         }
@@ -455,75 +500,102 @@ struct DwArgs {
     float *dw;       // (cout, cin), pre-zeroed, accumulated with atomics
 };
 
-// dW[o,i] += sum_{r in chunk} dY[r,o] * A_prev[r,i]     64 x 64 output tile, 4 x 4 per thread
-__global__ void __launch_bounds__(MLP_THREADS) pw_linear_bwd_dw_kernel(const DwArgs a) {
-    constexpr int BMo = 64, BNi = 64, LD = 64 + 4;
+// dW[o,i] += sum_{r in chunk} dY[r,o] * A_prev[r,i].  BMo x BNi output tile, 16 x 16 threads with a
+// (BMo/16) x (BNi/16) register block, BK rows per step (more rows per step for skinny tiles, so that
+// every thread keeps several independent loads in flight).
+template <int BMo, int BNi, int BK>
+__global__ void __launch_bounds__(MLP_THREADS, 2) pw_linear_bwd_dw_kernel(const DwArgs a) {
+    constexpr int TMo = BMo / 16, TNi = BNi / 16, LDA = BMo + 4, LDB = BNi + 4;
+    constexpr int APT = BK * BMo / MLP_THREADS, BPT = BK * BNi / MLP_THREADS;  // elements per thread per step
+    constexpr int AROWS = MLP_THREADS / BMo, BROWS = MLP_THREADS / BNi;       // rows covered per loader pass
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     DyTables &tab = *reinterpret_cast<DyTables *>(dyn_smem);
-    __shared__ __align__(16) float As[MLP_BK][LD];  // [row r][o]
-    __shared__ __align__(16) float Bs[MLP_BK][LD];  // [row r][i]
+    __shared__ __align__(16) float As[BK][LDA];  // [row r][o]
+    __shared__ __align__(16) float Bs[BK][LDB];  // [row r][i]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BMo, n0 = blockIdx.z * BNi;
     const long long rb = (long long)blockIdx.x * a.rows_per_block;
     const long long re = min((long long)a.rows, rb + a.rows_per_block);
-    const int lc = tid & 63, lr = tid >> 6;  // loader: 64 consecutive channels, 4 rows per pass
+    const int ac = tid % BMo, ar = tid / BMo, bc = tid % BNi, br = tid / BNi;
+    const bool has_tf = a.prev.scale != nullptr;
     load_dy_tables(tab, a.bn, a.s12, a.cout, a.rows);
-    __syncthreads();
+    float bsc = 1.f, bsh = 0.f;
+    if (has_tf && n0 + bc < a.cin) { bsc = __ldg(a.prev.scale + n0 + bc); bsh = __ldg(a.prev.shift + n0 + bc); }
 
-    float acc[4][4];
+    float acc[TMo][TNi];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TMo; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TNi; ++j) acc[i][j] = 0.f;
 
-    float pa[4], pb[4];
+    RawDy pa[APT];
+    float pb[BPT];
     auto fetch = [&](long long rr0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long r = rr0 + lr + 4 * i;
-            const int o = m0 + lc, ci = n0 + lc;
-            float va = 0.f, vb = 0.f;
-            if (r < re) {
-                if (o < a.cout)
-                    va = make_dy(tab, a.gs.at(r, o, a.cout), __ldg(a.bn.y + (size_t)r * a.cout + o), o, a.bn.slope);
-                if (ci < a.cin) {
-                    vb = __ldg(a.x + (size_t)r * a.cin + ci);
-                    if (a.prev.scale != nullptr)
-                        vb = act_fwd(__fmaf_rn(vb, __ldg(a.prev.scale + ci), __ldg(a.prev.shift + ci)), a.prev.slope);
-                }
-            }
-            pa[i] = va;
-            pb[i] = vb;
+        for (int i = 0; i < APT; ++i) {
+            const long long r = rr0 + ar + AROWS * i;
+            if (r < re && m0 + ac < a.cout) pa[i] = fetch_dy(a.gs, a.bn.y, r, m0 + ac, a.cout);
+        }
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const long long r = rr0 + br + BROWS * i;
+            pb[i] = (r < re && n0 + bc < a.cin) ? __ldg(a.x + (size_t)r * a.cin + n0 + bc) : 0.f;
         }
     };
+    auto stage = [&](long long rr0) {
+#pragma unroll
+        for (int i = 0; i < APT; ++i)
+            As[ar + AROWS * i][ac] = (rr0 + ar + AROWS * i < re && m0 + ac < a.cout)
+                                         ? finish_dy(tab, pa[i], m0 + ac, a.bn.slope) : 0.f;
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            float v = pb[i];
+            if (has_tf) v = (rr0 + br + BROWS * i < re && n0 + bc < a.cin) ? act_fwd(__fmaf_rn(v, bsc, bsh), a.prev.slope) : 0.f;
+            Bs[br + BROWS * i][bc] = v;
+        }
+    };
+
     fetch(rb);
-    for (long long rr0 = rb; rr0 < re; rr0 += MLP_BK) {
+    for (long long rr0 = rb; rr0 < re; rr0 += BK) {
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { As[lr + 4 * i][lc] = pa[i]; Bs[lr + 4 * i][lc] = pb[i]; }
+        stage(rr0);
         __syncthreads();
-        if (rr0 + MLP_BK < re) fetch(rr0 + MLP_BK);
+        if (rr0 + BK < re) fetch(rr0 + BK);
 #pragma unroll
-        for (int k = 0; k < MLP_BK; ++k) {
-            const float4 av = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
-            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
-            const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+        for (int k = 0; k < BK; ++k) {
+            float av[TMo], bv[TNi];
+            load_bvec<TMo>(av, &As[k][ty * TMo]);
+            load_bvec<TNi>(bv, &Bs[k][tx * TNi]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TMo; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(aa[i], bb[j], acc[i][j]);
+                for (int j = 0; j < TNi; ++j) acc[i][j] = __fmaf_rn(av[i], bv[j], acc[i][j]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int o = m0 + ty * 4 + i;
+    for (int i = 0; i < TMo; ++i) {
+        const int o = m0 + ty * TMo + i;
         if (o < a.cout)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ci = n0 + tx * 4 + j;
+            for (int j = 0; j < TNi; ++j) {
+                const int ci = n0 + tx * TNi + j;
                 if (ci < a.cin) atomicAdd(a.dw + (size_t)o * a.cin + ci, acc[i][j]);
             }
     }
+}
+
+template <int BMo, int BNi, int BK>
+static int launch_dw(DwArgs a, cudaStream_t s) {
+    const int tiles = ceil_div(a.cout, BMo) * ceil_div(a.cin, BNi);
+    // about four waves of CTAs (2 resident per SM) over the 148 SMs, at least 8 steps per CTA
+    const int chunks = (8 * 148 + tiles - 1) / tiles;
+    int rpb = (a.rows + chunks - 1) / chunks;
+    rpb = ((rpb + BK - 1) / BK) * BK;
+    if (rpb < 8 * BK) rpb = 8 * BK;
+    a.rows_per_block = rpb;
+    dim3 grid(ceil_div(a.rows, rpb), ceil_div(a.cout, BMo), ceil_div(a.cin, BNi));
+    pw_linear_bwd_dw_kernel<BMo, BNi, BK><<<grid, MLP_THREADS, sizeof(DyTables), s>>>(a);
+    return check_launch("pw_linear_bwd_dw");
 }
 
 static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : 64); }
@@ -553,7 +625,7 @@ int i2p_bn_finalize(int rows, int cout, const float *tile_stats, const float *ga
                     float *mean, float *rstd, float *scale, float *shift, void *stream) {
     using namespace i2p;
     I2P_REQUIRE(rows >= 1 && cout >= 1, "bn_finalize: bad sizes");
-    bn_finalize_kernel<<<ceil_div(cout, 4), 128, 0, as_stream(stream)>>>(rows, cout, ceil_div(rows, MLP_BM), tile_stats,
+    bn_finalize_kernel<<<cout, 128, 0, as_stream(stream)>>>(rows, cout, ceil_div(rows, MLP_BM), tile_stats,
                                                                         gamma, beta, eps, mean, rstd, scale, shift);
     return check_launch("bn_finalize");
 }
@@ -596,11 +668,14 @@ int i2p_bn_bwd_reduce(long long rows, int c, const float *g_dense, const float *
     I2P_REQUIRE(g_dense != nullptr || (dout != nullptr && arg != nullptr && k >= 1), "bn_bwd_reduce: no gradient source");
     if (rows == 0) return I2P_OK;
     const int cw = c < 64 ? c : 64;
-    int rpb = 4096;
-    if (g_dense == nullptr) rpb = (rpb / k) * k > 0 ? (rpb / k) * k : k;   // whole groups per block
+    // about four waves of blocks; each block owns whole groups of k rows
+    long long rpb = rows / (4 * 148 / ceil_div(c, cw) + 1) + 1;
+    if (rpb < 64) rpb = 64;
+    const int kk = g_dense == nullptr ? k : 1;
+    rpb = ((rpb + kk - 1) / kk) * kk;
     dim3 grid(ceil_div(rows, rpb), ceil_div(c, cw));
     BnRef bn{y, mean, rstd, scale, shift, slope};
-    bn_bwd_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, c, make_gs(g_dense, dout, arg, k), bn, rpb, s12);
+    bn_bwd_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, c, make_gs(g_dense, dout, arg, k), bn, (int)rpb, s12);
     return check_launch("bn_bwd_reduce");
 }
 
@@ -641,15 +716,10 @@ int i2p_pw_linear_bwd_dw(int rows, int cin, int cout, const float *g_dense, cons
     a.s12 = s12; a.x = x;
     a.prev = BnRef{nullptr, nullptr, nullptr, prev_scale, prev_shift, prev_slope};
     a.dw = dw;
-    const int tiles = ceil_div(cout, 64) * ceil_div(cin, 64);
-    // about four waves of CTAs over the 148 SMs, at least 256 rows per CTA
-    int chunks = (4 * 148 + tiles - 1) / tiles;
-    int rpb = (rows + chunks - 1) / chunks;
-    rpb = ((rpb + MLP_BK - 1) / MLP_BK) * MLP_BK;
-    if (rpb < 256) rpb = 256;
-    a.rows_per_block = rpb;
-    dim3 grid(ceil_div(rows, rpb), ceil_div(cout, 64), ceil_div(cin, 64));
-    pw_linear_bwd_dw_kernel<<<grid, MLP_THREADS, sizeof(DyTables), as_stream(stream)>>>(a);
-    return check_launch("pw_linear_bwd_dw");
+    cudaStream_t st = as_stream(stream);
+    if (cout <= 16) return cin <= 16 ? launch_dw<16, 16, 64>(a, st) : launch_dw<16, 64, 32>(a, st);
+    if (cout <= 32) return cin <= 16 ? launch_dw<32, 16, 32>(a, st) : launch_dw<32, 64, 32>(a, st);
+    return cin <= 16 ? launch_dw<64, 16, 32>(a, st) : launch_dw<64, 64, 16>(a, st);
 }
 }
+

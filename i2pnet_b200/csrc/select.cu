@@ -57,10 +57,10 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectAr
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const long long centre = (long long)blockIdx.x * SEL_WARPS + warp;
-    if (centre >= (long long)a.batch * a.npoints) return;
-    const int b = (int)(centre / a.npoints);
-    const int cn = (int)(centre % a.npoints);
+    const unsigned centre = blockIdx.x * SEL_WARPS + warp;   // 32-bit: a 64-bit divide costs ~150 instructions
+    if (centre >= (unsigned)a.batch * (unsigned)a.npoints) return;
+    const int b = (int)(centre / (unsigned)a.npoints);
+    const int cn = (int)(centre - (unsigned)b * (unsigned)a.npoints);
     const int total = a.kH * a.kW;
     const int K = a.K;
 
@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectAr
         sH = __ldg(c);
         sW = __ldg(c + 1);
     } else {
-        sH = (cn / a.out_w) * a.stride_ch;
-        sW = (cn % a.out_w) * a.stride_cw;
+        const unsigned ch = (unsigned)cn / (unsigned)a.out_w;
+        sH = (int)ch * a.stride_ch;
+        sW = (cn - (int)ch * a.out_w) * a.stride_cw;
     }
     for (int k = lane; k < K; k += 32) s_hw[warp][k] = -1;
 
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectAr
     bool inside[R];
     if (centre_valid) {  // warp-uniform: an empty centre costs one load and the output stores
         const int half_H = a.kH / 2, half_W = a.kW / 2;
-        const int base_h = sH / a.stride_h - half_H, base_w = sW / a.stride_w - half_W;  // :89-92
+        const int base_h = (int)((unsigned)sH / (unsigned)a.stride_h) - half_H;           // :89-92
+        const int base_w = (int)((unsigned)sW / (unsigned)a.stride_w) - half_W;
         const float *x2 = a.xyz2 + (size_t)b * a.small_h * a.small_w * 3;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -227,6 +229,7 @@ static int launch_select(const SelectArgs &a, cudaStream_t stream) {
                     a.stride_h >= 1 && a.stride_w >= 1, "select: image too large or stride < 1");
     const long long centres = (long long)a.batch * a.npoints;
     if (centres == 0) return I2P_OK;
+    I2P_REQUIRE(centres < (1LL << 31), "select: batch * npoints exceeds 2^31");
     SelectArgs b = a;
     b.kw_magic = (unsigned)((0x100000000ULL + (unsigned)a.kW - 1) / (unsigned)a.kW);
     const int grid = ceil_div(centres, SEL_WARPS);
