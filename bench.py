@@ -173,7 +173,8 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = False   # f32 parity configuration (north_star: 1e-4 relative)
     torch.backends.cudnn.allow_tf32 = False
 
-    eng = TrainStep(BATCH, N_POINTS, IMAGE_HW, device=device, seed=0, use_graph=not args.no_graph)
+    eng = TrainStep(BATCH, N_POINTS, IMAGE_HW, device=device, seed=0, use_graph=not args.no_graph,
+                    channels_last_rgb=args.channels_last)
     nb = 4  # distinct batches, cycled
     host = [make_pairs(BATCH, N_POINTS, IMAGE_HW, seed=100 * rank + i) for i in range(nb)]
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
@@ -232,7 +233,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points": N_POINTS, "image": list(IMAGE_HW), "per_gpu_batch": BATCH,
-                       "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
+                       "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "rgb_channels_last": args.channels_last,
                        "l2": "256 MB flush write between steps", "tf32": False, "final_loss": loss},
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -252,6 +253,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--channels-last", action="store_true", help="NHWC memory format for the RGB conv stack")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

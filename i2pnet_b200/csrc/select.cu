@@ -27,12 +27,16 @@ struct SelectArgs {
     const float *xyz1, *xyz2;
     const int32_t *idx_n2, *random_hw;
     int out_w, stride_ch, stride_cw;  // regular centre grid when idx_n2 == nullptr
-    unsigned kw_magic;                // ceil(2^32 / kW): division by multiplication
+    unsigned kw_magic, ow_magic, sh_magic, sw_magic;  // ceil(2^32 / d) for d = kW, out_w, stride_h, stride_w:
+                                                      // q = umulhi(n, magic) is exact for n, d < 2^16
     int64_t *sel_b, *sel_h, *sel_w;   // drop-in outputs (partial writes)
     float *sel_mask;
     int32_t *flat_idx;                // compact outputs (full writes)
     float *flat_mask;
 };
+
+// n / d through the precomputed magic (0 encodes d == 1)
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned magic) { return magic == 0u ? n : __umulhi(n, magic); }
 
 template <int R>
 __device__ __forceinline__ float pick(const float (&a)[R], int r) {
@@ -57,10 +61,9 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectAr
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const unsigned centre = blockIdx.x * SEL_WARPS + warp;   // 32-bit: a 64-bit divide costs ~150 instructions
-    if (centre >= (unsigned)a.batch * (unsigned)a.npoints) return;
-    const int b = (int)(centre / (unsigned)a.npoints);
-    const int cn = (int)(centre - (unsigned)b * (unsigned)a.npoints);
+    const int b = blockIdx.y;                                 // no integer division anywhere on this path:
+    const int cn = blockIdx.x * SEL_WARPS + warp;             // four of them cost more than the rest of an
+    if (cn >= a.npoints) return;                              // empty centre's work
     const int total = a.kH * a.kW;
     const int K = a.K;
 
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectAr
         sH = __ldg(c);
         sW = __ldg(c + 1);
     } else {
-        const unsigned ch = (unsigned)cn / (unsigned)a.out_w;
+        const unsigned ch = fastdiv((unsigned)cn, a.ow_magic);
         sH = (int)ch * a.stride_ch;
         sW = (cn - (int)ch * a.out_w) * a.stride_cw;
     }
@@ -86,8 +89,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectAr
     bool inside[R];
     if (centre_valid) {  // warp-uniform: an empty centre costs one load and the output stores
         const int half_H = a.kH / 2, half_W = a.kW / 2;
-        const int base_h = (int)((unsigned)sH / (unsigned)a.stride_h) - half_H;           // :89-92
-        const int base_w = (int)((unsigned)sW / (unsigned)a.stride_w) - half_W;
+        const int base_h = (int)fastdiv((unsigned)sH, a.sh_magic) - half_H;              // :89-92  sH / stride_h
+        const int base_w = (int)fastdiv((unsigned)sW, a.sw_magic) - half_W;
         const float *x2 = a.xyz2 + (size_t)b * a.small_h * a.small_w * 3;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_k_kernel(const SelectAr
             qx[r] = qy[r] = qz[r] = 0.f;
             if (t < total) {
                 const unsigned khw = a.random_hw != nullptr ? (unsigned)__ldg(a.random_hw + t) : (unsigned)t;
-                const unsigned q = __umulhi(khw, a.kw_magic);  // khw / kW, exact for khw, kW < 2^16
+                const unsigned q = fastdiv(khw, a.kw_magic);  // khw / kW, exact for khw, kW < 2^16
                 int kh = base_h + (int)q;
                 int kw = base_w + (int)(khw - q * (unsigned)a.kW);
                 if (a.flag & I2P_FLAG_SHIFT) {  // :96-113 the range image is circular in width
@@ -230,9 +233,15 @@ static int launch_select(const SelectArgs &a, cudaStream_t stream) {
     const long long centres = (long long)a.batch * a.npoints;
     if (centres == 0) return I2P_OK;
     I2P_REQUIRE(centres < (1LL << 31), "select: batch * npoints exceeds 2^31");
+    I2P_REQUIRE(a.H < 65536 && a.W < 65536 && a.batch <= 65535 && (a.idx_n2 != nullptr || a.npoints < 65536),
+                "select: image or centre grid too large");
     SelectArgs b = a;
-    b.kw_magic = (unsigned)((0x100000000ULL + (unsigned)a.kW - 1) / (unsigned)a.kW);
-    const int grid = ceil_div(centres, SEL_WARPS);
+    auto magic = [](int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)d - 1) / (unsigned)d); };
+    b.kw_magic = magic(a.kW);
+    b.ow_magic = magic(a.out_w);
+    b.sh_magic = magic(a.stride_h);
+    b.sw_magic = magic(a.stride_w);
+    const dim3 grid(ceil_div(a.npoints, SEL_WARPS), a.batch);
     const int block = SEL_WARPS * 32;
     switch ((total + 31) / 32) {
         case 1: select_k_kernel<1, FLAT><<<grid, block, 0, stream>>>(b); break;
