@@ -58,7 +58,8 @@ _SIGNATURES = {
 
 def exported_symbols():
     """Every entry point include/i2p_b200.h declares."""
-    return sorted(list(_SIGNATURES) + ["i2p_last_error", "i2p_abi_version", "i2p_launch_count", "i2p_pw_num_tiles"])
+    return sorted(list(_SIGNATURES) + ["i2p_last_error", "i2p_abi_version", "i2p_launch_count", "i2p_pw_num_tiles",
+                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores"])
 
 
 def lib():
@@ -78,6 +79,9 @@ def lib():
         L.i2p_launch_count.restype = ctypes.c_uint64
         L.i2p_pw_num_tiles.argtypes = [_int]
         L.i2p_pw_num_tiles.restype = _int
+        L.i2p_set_mlp_tensor_cores.argtypes = [_int]
+        L.i2p_set_mlp_tensor_cores.restype = None
+        L.i2p_get_mlp_tensor_cores.restype = _int
         _lib = L
     return _lib
 

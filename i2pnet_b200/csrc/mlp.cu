@@ -19,8 +19,10 @@
 // All arithmetic is f32 FMA (the parity configuration: 1e-4 relative rules out TF32); tiles are
 // 128 x {16,32,64} x 16 with 8 x {1,2,4} register blocking.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace i2p {
 
@@ -41,6 +43,7 @@ struct FwdArgs {
     float in_slope;
     const float *w, *bias;
     float *y, *tile_stats;  // tile_stats (ntiles, cout, 2) or nullptr
+    int dbg;                // profiling aid (I2P_TC_DBG): bit0 no proxy fence, bit1 no MMA, bit2 no loads, bit3 no stores
 };
 
 template <int TN>
@@ -184,6 +187,214 @@ __global__ void __launch_bounds__(MLP_THREADS, 2) pw_linear_fwd_kernel(const Fwd
         float *ts = a.tile_stats + ((size_t)blockIdx.x * a.cout + n0 + tid) * 2;
         ts[0] = colmean[tid];
         ts[1] = s;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// forward GEMM on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM)
+// -------------------------------------------------------------------------------------------
+// Same contract as pw_linear_fwd_kernel.  One CTA owns a 128-row x BN-column output tile; the K
+// loop runs in chunks of 32 through a two-stage shared-memory ring.  All 256 threads fetch the raw
+// operands of chunk c+1 from global memory, apply the fused input transform, split every element
+// into tf32 (hi, lo) and store both into the UMMA canonical layout (umma.cuh); one elected thread
+// then issues 4 k-steps x 3 MMAs (hi*hi, lo*hi, hi*lo) and commits them to the stage's mbarrier, so
+// the tensor core works on chunk c while the CTA stages chunk c+1.  The epilogue pulls the
+// accumulator out of TMEM (tcgen05.ld), adds the bias, parks the tile in shared memory, writes it
+// with coalesced 128-bit stores and reduces the per-tile batch-norm statistics from it.
+constexpr int TC_BK = 32;
+
+// Byte stride between the k-column blocks of a [ROWS x 32] operand tile: ROWS * 16 plus one 16-byte
+// pad, so that 32 lanes writing 32 consecutive k of one row hit 32 different banks (the staging
+// loads are coalesced along k; without the pad every store would be an 8-way bank conflict).
+template <int ROWS>
+struct TcTile {
+    static constexpr uint32_t LBO = ROWS * 16 + 16, SBO = 128, BYTES = (TC_BK / 4) * LBO;
+};
+
+constexpr int TC_THREADS = 256;   // 8 warps: lane = k within the chunk, warp = row phase
+
+// Occupancy is the latency-hiding mechanism here, exactly as in the FMA kernels: a CTA is light
+// (one 50 KB shared-memory stage, 64 TMEM columns, <= 64 registers per thread) so that four of them
+// share an SM -- while one waits for its global loads or drains its epilogue, the others stage
+// operands and keep the tensor core busy.
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 4) pw_linear_fwd_tc_kernel(const FwdArgs a) {
+    using TA = TcTile<MLP_BM>;
+    using TB = TcTile<BN>;
+    constexpr int NA = MLP_BM / 8, NB = BN / 8;
+    extern __shared__ __align__(1024) unsigned char tc_smem[];   // A hi | A lo | B hi | B lo
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * BN, r0 = blockIdx.y * MLP_BM;   // column tiles of one row tile are adjacent CTAs
+    const bool has_tf = a.in_scale != nullptr;
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
+    if (tid == 0) {
+        umma::mbar_init(&mma_bar, 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t smem_base = umma::smem_u32(tc_smem);
+    constexpr uint32_t idesc = umma::instr_desc_tf32(BN);
+
+    // staging coordinates: row = warp + 8 i  ->  (row >> 3) * 128 + (row & 7) * 16 = i * 128 + warp * 16
+    const uint32_t koff_a = (uint32_t)(lane >> 2) * TA::LBO + (uint32_t)(lane & 3) * 4u + (uint32_t)warp * 16u;
+    const uint32_t koff_b = (uint32_t)(lane >> 2) * TB::LBO + (uint32_t)(lane & 3) * 4u + (uint32_t)warp * 16u;
+    const int nchunks = (a.cin + TC_BK - 1) / TC_BK;
+    const float *xbase = a.x + (size_t)(r0 + warp) * a.cin + lane;
+    const float *wbase = a.w + (size_t)(n0 + warp) * a.cin + lane;
+
+    // Interior tiles (all 128 rows, all BN channels valid) take unguarded loads; the activation is
+    // max(z, slope * z), valid for the slopes in use (0 <= slope <= 1: ReLU, LeakyReLU(0.1), identity).
+    const bool interior = r0 + MLP_BM <= a.rows && n0 + BN <= a.cout;
+    const int astride = 8 * a.cin;   // elements between this thread's consecutive rows
+    float ra[NA], rb[NB], psc = 1.f, psh = 0.f;
+    auto fetch = [&](int c) {   // issue the global loads of chunk c; nothing depends on them yet
+        const int k = c * TC_BK + lane;
+        const bool kin = k < a.cin;
+        const float *xp = xbase + c * TC_BK, *wp = wbase + c * TC_BK;
+        if (has_tf && kin) { psc = __ldg(a.in_scale + k); psh = __ldg(a.in_shift + k); }
+        if (a.dbg & 4) {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) ra[i] = (float)(i + lane);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) rb[i] = (float)(i - lane);
+        } else if (interior && kin) {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) ra[i] = __ldg(xp + i * astride);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) rb[i] = __ldg(wp + i * astride);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) ra[i] = (kin && r0 + warp + 8 * i < a.rows) ? __ldg(xp + i * astride) : 0.f;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) rb[i] = (kin && n0 + warp + 8 * i < a.cout) ? __ldg(wp + i * astride) : 0.f;
+        }
+    };
+
+    fetch(0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);   // the tensor core is done with the stage
+        const bool kin = c * TC_BK + lane < a.cin;
+        if (has_tf) {
+            if (interior && kin) {
+#pragma unroll
+                for (int i = 0; i < NA; ++i) {
+                    const float z = __fmaf_rn(ra[i], psc, psh);
+                    ra[i] = fmaxf(z, z * a.in_slope);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NA; ++i) {
+                    const float z = __fmaf_rn(ra[i], psc, psh);
+                    ra[i] = (kin && r0 + warp + 8 * i < a.rows) ? fmaxf(z, z * a.in_slope) : 0.f;
+                }
+            }
+        }
+        if (!(a.dbg & 8))
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            uint32_t hi, lo;
+            umma::split_tf32(ra[i], hi, lo);
+            *reinterpret_cast<uint32_t *>(tc_smem + koff_a + i * 128) = hi;
+            *reinterpret_cast<uint32_t *>(tc_smem + TA::BYTES + koff_a + i * 128) = lo;
+        }
+        if (!(a.dbg & 8))
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            uint32_t hi, lo;
+            umma::split_tf32(rb[i], hi, lo);
+            *reinterpret_cast<uint32_t *>(tc_smem + 2 * TA::BYTES + koff_b + i * 128) = hi;
+            *reinterpret_cast<uint32_t *>(tc_smem + 2 * TA::BYTES + TB::BYTES + koff_b + i * 128) = lo;
+        }
+        if (!(a.dbg & 1)) umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            const uint32_t sa = smem_base, sb = sa + 2 * TA::BYTES;
+#pragma unroll
+            for (int j = 0; j < TC_BK / 8; ++j) {
+                const uint64_t a_hi = umma::smem_desc(sa + j * 2 * TA::LBO, TA::LBO, TA::SBO);
+                const uint64_t a_lo = umma::smem_desc(sa + TA::BYTES + j * 2 * TA::LBO, TA::LBO, TA::SBO);
+                const uint64_t b_hi = umma::smem_desc(sb + j * 2 * TB::LBO, TB::LBO, TB::SBO);
+                const uint64_t b_lo = umma::smem_desc(sb + TB::BYTES + j * 2 * TB::LBO, TB::LBO, TB::SBO);
+                if (a.dbg & 2) continue;
+                umma::mma_tf32(tmem_d, a_hi, b_hi, idesc, c > 0 || j > 0);
+                umma::mma_tf32(tmem_d, a_lo, b_hi, idesc, true);
+                umma::mma_tf32(tmem_d, a_hi, b_lo, idesc, true);
+            }
+            umma::commit(&mma_bar);
+        }
+        if (c + 1 < nchunks) fetch(c + 1);   // global loads in flight while the tensor core runs
+    }
+    umma::mbar_wait(&mma_bar, (uint32_t)(nchunks - 1) & 1u);
+    umma::fence_after_sync();
+    __syncthreads();   // every thread is past its last shared-memory operand write / wait
+
+    // epilogue: TMEM -> registers (+bias) -> shared tile [128][BN+4]
+    float *tile = reinterpret_cast<float *>(tc_smem);
+    constexpr int LDT = BN + 4;
+    {
+        const int row = (warp & 3) * 32 + lane;                 // a warp can only read its own 32 TMEM lanes
+        constexpr int CQ = BN / 2;                              // warps 0-3: first half of the columns, 4-7: second
+        const int cbase = (warp >> 2) * CQ;
+#pragma unroll
+        for (int c0 = 0; c0 < CQ; c0 += 16) {
+            float v[16];
+            umma::tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbase + c0), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + cbase + c0 + j;
+                tile[row * LDT + cbase + c0 + j] = v[j] + ((n < a.cout && a.bias != nullptr) ? __ldg(a.bias + n) : 0.f);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+
+    const int vr = min(MLP_BM, a.rows - r0);
+    for (int e = tid; e < MLP_BM * (BN / 4); e += TC_THREADS) {   // coalesced 128-bit stores
+        const int row = e / (BN / 4), c4 = e % (BN / 4);
+        if (row < vr && n0 + c4 * 4 + 3 < a.cout)
+            *reinterpret_cast<float4 *>(a.y + (size_t)(r0 + row) * a.cout + n0 + c4 * 4) =
+                *reinterpret_cast<const float4 *>(&tile[row * LDT + c4 * 4]);
+    }
+    if (a.tile_stats == nullptr) return;
+    // per-tile (mean, M2): 4 threads per column, 32 rows each, merged with Chan's formula
+    {
+        const int col = tid >> 2, part = tid & 3;
+        float n = 0.f, mu = 0.f, m2 = 0.f;
+        if (col < BN) {
+            const int rb0 = part * 32, re0 = min(vr, rb0 + 32);
+            float sum = 0.f;
+            for (int r = rb0; r < re0; ++r) sum += tile[r * LDT + col];
+            n = (float)max(re0 - rb0, 0);
+            mu = n > 0.f ? sum / n : 0.f;
+            for (int r = rb0; r < re0; ++r) { const float d = tile[r * LDT + col] - mu; m2 += d * d; }
+        }
+        // BN * 4 = 256 threads: the four parts of a column are adjacent lanes
+        for (int off = 1; off < 4; off <<= 1) {
+            const float n2 = __shfl_xor_sync(FULL, n, off), mu2 = __shfl_xor_sync(FULL, mu, off),
+                        s2 = __shfl_xor_sync(FULL, m2, off);
+            const float tot = n + n2;
+            if (tot > 0.f) {
+                const float d = mu2 - mu;
+                const float nmu = mu + d * (n2 / tot);
+                m2 = m2 + s2 + d * d * n * (n2 / tot);
+                mu = nmu;
+                n = tot;
+            }
+        }
+        if (col < BN && part == 0 && n0 + col < a.cout) {
+            float *ts = a.tile_stats + ((size_t)blockIdx.y * a.cout + n0 + col) * 2;
+            ts[0] = mu;
+            ts[1] = m2;
+        }
     }
 }
 
@@ -600,9 +811,23 @@ static int launch_dw(DwArgs a, cudaStream_t s) {
 
 static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : 64); }
 
+// Tensor-core (tcgen05, 3xTF32) forward path for layers with cout % 64 == 0 (default on);
+// I2P_MLP_TC=0 selects the f32 FMA kernels everywhere.
+static int g_mlp_tc = -1;
+static bool mlp_tensor_cores() {
+    if (g_mlp_tc < 0) {
+        const char *e = getenv("I2P_MLP_TC");
+        g_mlp_tc = (e == nullptr) ? 1 : (atoi(e) != 0);
+    }
+    return g_mlp_tc != 0;
+}
+
 }  // namespace i2p
 
 extern "C" {
+
+void i2p_set_mlp_tensor_cores(int on) { i2p::g_mlp_tc = on ? 1 : 0; }
+int i2p_get_mlp_tensor_cores(void) { return i2p::mlp_tensor_cores() ? 1 : 0; }
 
 int i2p_pw_num_tiles(int rows) { return (rows + i2p::MLP_BM - 1) / i2p::MLP_BM; }
 
@@ -611,10 +836,20 @@ int i2p_pw_linear_fwd(int rows, int cin, int cout, const float *x, const float *
     using namespace i2p;
     I2P_REQUIRE(rows >= 0 && cin >= 1 && cout >= 1, "pw_linear_fwd: bad sizes");
     if (rows == 0) return I2P_OK;
-    FwdArgs a{rows, cin, cout, x, in_scale, in_shift, in_slope, w, bias, y, tile_stats};
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("I2P_TC_DBG"); dbg = e ? atoi(e) : 0; }
+    FwdArgs a{rows, cin, cout, x, in_scale, in_shift, in_slope, w, bias, y, tile_stats, dbg};
+    cudaStream_t s = as_stream(stream);
+    if (mlp_tensor_cores() && cout >= 64 && cout % 64 == 0 && cin <= MLP_MAXC) {
+        // tcgen05 path: 128 x 64 tiles, accumulator in TMEM, four CTAs per SM
+        constexpr int smem = 2 * TcTile<MLP_BM>::BYTES + 2 * TcTile<64>::BYTES;
+        static bool once = false;
+        if (!once) { cudaFuncSetAttribute(pw_linear_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }
+        pw_linear_fwd_tc_kernel<64><<<dim3(cout / 64, ceil_div(rows, MLP_BM)), TC_THREADS, smem, s>>>(a);
+        return check_launch("pw_linear_fwd(tcgen05)");
+    }
     const int bn = pick_bn(cout);
     dim3 grid(ceil_div(rows, MLP_BM), ceil_div(cout, bn));
-    cudaStream_t s = as_stream(stream);
     if (bn == 16) pw_linear_fwd_kernel<16><<<grid, MLP_THREADS, 0, s>>>(a);
     else if (bn == 32) pw_linear_fwd_kernel<32><<<grid, MLP_THREADS, 0, s>>>(a);
     else pw_linear_fwd_kernel<64><<<grid, MLP_THREADS, 0, s>>>(a);

@@ -137,6 +137,10 @@ int i2p_project_seq(int b, int n, int H, int W, float fup_deg, float fdown_deg, 
  * materialised; normalise + activation are folded into the next kernel's operand load.
  * Activation: act(z) = z > 0 ? z : slope * z  (slope 0 = ReLU, 0.1 = LeakyReLU(0.1), 1 = identity). */
 
+/* Select the tcgen05 (tensor core, 3xTF32 split, f32-accurate) kernels for layers with cout % 64 == 0;
+ * 0 = f32 FMA kernels everywhere.  Default: environment variable I2P_MLP_TC, else 1. */
+void i2p_set_mlp_tensor_cores(int on);
+int i2p_get_mlp_tensor_cores(void);
 /* Number of 128-row tiles (rows of the tile_stats buffer). */
 int i2p_pw_num_tiles(int rows);
 /* y = f(x) W^T + bias, f(x) = act(x * in_scale + in_shift) or x when in_scale == NULL.

@@ -32,8 +32,19 @@ def _reference_f64(x, mods, reduce_k):
     return y.max(dim=2)[0] if reduce_k else y
 
 
+@pytest.fixture(params=[0, 1], ids=["fma", "tcgen05"])
+def tensor_cores(request):
+    """Both kernel families: f32 FMA and tcgen05 tf32 with the 3-term hi/lo split."""
+    from i2pnet_b200 import _cabi
+    L = _cabi.lib()
+    before = L.i2p_get_mlp_tensor_cores()
+    L.i2p_set_mlp_tensor_cores(request.param)
+    yield request.param
+    L.i2p_set_mlp_tensor_cores(before)
+
+
 @pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: "cin%d_%s_k%d" % (c[0], "x".join(map(str, c[1])), c[4]))
-def test_fused_mlp_matches_layerwise_and_f64(cfg):
+def test_fused_mlp_matches_layerwise_and_f64(cfg, tensor_cores):
     from i2pnet_b200.projectPN import PPBackbone_center as P
     cin, chans, B, n, k, reduce_k, leaky, need_grad = cfg
     dev = torch.device("cuda:0")
@@ -65,15 +76,34 @@ def test_fused_mlp_matches_layerwise_and_f64(cfg):
         res[mode] = dict(out=out.detach().double(), dx=x.grad.double() if need_grad else None,
                          grads=[(n_, p.grad.double().clone()) for m in mods for n_, p in m.named_parameters()])
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    l2 = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
     truth = res["f64"]
     for mode in ("fused", "layerwise"):
         r = res[mode]
         assert rel(r["out"], truth["out"]) < 1e-5, mode
+    # Gradients.  act'(z) is discontinuous at z = 0: a forward rounding difference of 1e-6 flips the
+    # slope (1 <-> 0.1 or 0) of a few dozen of the ~5e6 pre-activations, and each flip changes one row
+    # of dx by tens of percent.  The max-norm therefore measures luck, not accuracy (the f32-FMA path
+    # differs from f64 by 1e-7 per layer and usually flips nothing; the tcgen05 3xTF32 path differs
+    # by 2e-6 and flips ~50).  Gradients are compared in relative L2, plus the fraction of elements
+    # off by more than 1e-4 of the maximum.
     f, lw = res["fused"], res["layerwise"]
+
+    def check(name, g, t):
+        assert l2(g, t) < 2e-3, (name, l2(g, t))
+        outliers = float(((g - t).abs() > 1e-4 * t.abs().max()).float().mean())
+        assert outliers < 2e-3, (name, outliers)
+
     if need_grad:
-        assert rel(f["dx"], truth["dx"]) < max(1e-4, 3 * rel(lw["dx"], truth["dx"]))
-    for (name, gf), (_, gl), (_, gt) in zip(f["grads"], lw["grads"], truth["grads"]):
+        check("dx", f["dx"], truth["dx"])
+    for (name, gf), (_, gt) in zip(f["grads"], truth["grads"]):
         if name == "conv.bias":
             assert float(gf.abs().max()) == 0.0          # exactly zero under batch-norm
             continue
-        assert rel(gf, gt) < max(1e-4, 3 * rel(gl, gt)), (name, rel(gf, gt), rel(gl, gt))
+        check(name, gf, gt)
+    if not tensor_cores:   # the f32 FMA kernels are as close to f64 as the ATen formulation
+        if need_grad:
+            assert l2(f["dx"], truth["dx"]) < max(1e-5, 3 * l2(lw["dx"], truth["dx"]))
+        for (name, gf), (_, gl), (_, gt) in zip(f["grads"], lw["grads"], truth["grads"]):
+            if name != "conv.bias":
+                assert l2(gf, gt) < max(1e-5, 3 * l2(gl, gt)), (name, l2(gf, gt), l2(gl, gt))
