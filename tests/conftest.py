@@ -21,3 +21,14 @@ def oracle_backend(monkeypatch):
     from tests import cpu_backend
     cpu_backend.patch(monkeypatch)
     yield
+
+
+@pytest.fixture(params=[0, 1], ids=["fma", "tcgen05"])
+def tensor_cores(request):
+    """Both shared-MLP kernel families: f32 FMA and tcgen05 tf32 with the 3-term hi/lo split."""
+    from i2pnet_b200 import _cabi
+    L = _cabi.lib()
+    before = L.i2p_get_mlp_tensor_cores()
+    L.i2p_set_mlp_tensor_cores(request.param)
+    yield request.param
+    L.i2p_set_mlp_tensor_cores(before)
