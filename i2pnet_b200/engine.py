@@ -26,20 +26,42 @@ INPUT_KEYS = ("rgb", "lidar", "raw_point_xyz", "lidar_feats", "intrinsic", "q_gt
 
 
 class FlatGradBucket:
-    """One contiguous gradient buffer for all parameters; `p.grad` alias slices of it."""
+    """One contiguous gradient buffer for all parameters.
+
+    Autograd accumulates into an existing `p.grad` with one `add_` launch per parameter (299 tiny
+    kernels per step here) and the buffer would need a memset first.  Instead `release()` drops every
+    `p.grad` before backward, so that autograd simply keeps the gradient tensors its functions produce,
+    and `gather()` packs them into the flat buffer with a single batched concatenation; `p.grad` then
+    alias slices of the flat buffer for the all-reduce, the clip and the optimiser."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self._alias()
+
+    def _alias(self):
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def release(self):
+        for p in self.params:
+            p.grad = None
+
+    def gather(self):
+        pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        torch.cat(pieces, out=self.flat)
+        self._alias()
 
     def zero(self):
         self.flat.zero_()
+        self._alias()
 
     def all_reduce_mean(self, group=None):
         """Sum over ranks / world size: the single exchange step of the data-parallel path."""
@@ -82,11 +104,12 @@ class TrainStep:
     # ---- one eager step on the static buffers
     def _step_body(self):
         x = self.inputs
-        self.bucket.zero()
+        self.bucket.release()
         out3, out4, _, _, sx, sq = self.model(x["rgb"], x["lidar"], x["raw_point_xyz"], None, x["intrinsic"], None,
                                               None, None, x["lidar_feats"], self.cfg)
         loss, _, _ = Get_loss(out3, out4, x["q_gt"], x["t_gt"], sx, sq, self.cfg)
         loss.backward()
+        self.bucket.gather()
         self.bucket.all_reduce_mean(self.group)
         self.bucket.clip_(self.clip)
         self.opt.step()

@@ -2,11 +2,98 @@
 createCNNs :6-20, Conv1d :63-85).  Module indices inside the Sequential -- hence the
 state_dict keys `RGB_net1.{0,1,4,5,...}` -- follow the reference: block i owns slots
 4i (conv), 4i+1 (BatchNorm2d), 4i+2 (LeakyReLU 0.1), 4i+3 (MaxPool 3x3)."""
+import torch
 import torch.nn as nn
+from torch.autograd import Function
+
+from .. import _cabi
+from .._cabi import _ptr, call, f32
+
+USE_FUSED_RGB_TAIL = True   # False: nn.BatchNorm2d -> nn.LeakyReLU -> nn.MaxPool2d through ATen / cuDNN
+
+
+class _BlockTail(Function):
+    """BatchNorm2d -> LeakyReLU -> MaxPool2d(3, stride, 1) of one pyramid block on the kernels of
+    csrc/rgb.cu: one statistics pass + one pooled write forward, one reduction + one write backward,
+    nothing but the convolution output y and an int8 arg-max kept for backward."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, bn, slope, stride):
+        dev = y.device
+        B, C, H, W = y.shape
+        L = _cabi.lib()
+        Ho, Wo = L.i2p_rgb_pool_out(H, stride), L.i2p_rgb_pool_out(W, stride)
+        stats = torch.empty(4, C, dtype=f32, device=dev)
+        s12 = torch.empty(2, C, dtype=torch.float64, device=dev)
+        batch_stats = bn.training or not bn.track_running_stats
+        yp = _ptr(y, f32, "conv output", dev)
+        if batch_stats:
+            ntiles = B * L.i2p_rgb_num_chunks(H * W)
+            tiles = torch.empty(C, ntiles, 3, dtype=f32, device=dev)
+            call("i2p_rgb_bn_stats", dev, B, C, H, W, yp, tiles.data_ptr())
+            track = bn.track_running_stats and bn.running_mean is not None
+            call("i2p_rgb_bn_finalize", dev, C, ntiles, tiles.data_ptr(), _ptr(gamma, f32, "bn weight", dev),
+                 _ptr(beta, f32, "bn bias", dev), float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1),
+                 bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                 bn.num_batches_tracked.data_ptr() if track else None, stats.data_ptr(), s12.data_ptr())
+        else:
+            call("i2p_rgb_bn_from_running", dev, C, _ptr(gamma, f32, "bn weight", dev), _ptr(beta, f32, "bn bias", dev),
+                 float(bn.eps), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), stats.data_ptr(), s12.data_ptr())
+        out = torch.empty(B, C, Ho, Wo, dtype=f32, device=dev)
+        arg = torch.empty(B, C, Ho, Wo, dtype=torch.int8, device=dev)
+        call("i2p_rgb_bn_act_pool_fwd", dev, B, C, H, W, stride, yp, stats.data_ptr(), float(slope), out.data_ptr(),
+             arg.data_ptr())
+        ctx.save_for_backward(y, stats, arg, s12)
+        ctx.meta = (stride, float(slope), bool(batch_stats))
+        ctx.used = False
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, stats, arg, s12 = ctx.saved_tensors
+        stride, slope, batch_stats = ctx.meta
+        dev = y.device
+        B, C, H, W = y.shape
+        if ctx.used:          # a second backward through the same graph: the sums start from zero again
+            s12.zero_()
+        ctx.used = True
+        dout = dout.contiguous()
+        dy = torch.empty_like(y)
+        dgb = torch.empty(2, C, dtype=f32, device=dev)
+        call("i2p_rgb_bn_act_pool_bwd", dev, B, C, H, W, stride, int(batch_stats), y.data_ptr(), stats.data_ptr(), slope,
+             _ptr(dout, f32, "grad_output", dev), arg.data_ptr(), s12.data_ptr(), dy.data_ptr(), dgb[0].data_ptr(),
+             dgb[1].data_ptr())
+        return dy, dgb[0], dgb[1], None, None, None
+
+
+def _fusable(y, bn, act, pool):
+    def one(v):
+        return v if isinstance(v, int) else (v[0] if v[0] == v[1] else None)
+    return (USE_FUSED_RGB_TAIL and y.is_cuda and y.dtype == f32 and y.is_contiguous() and bn.affine
+            and isinstance(act, nn.LeakyReLU) and one(pool.kernel_size) == 3 and one(pool.padding) == 1
+            and one(pool.stride) in (1, 2) and one(pool.dilation) == 1 and not pool.ceil_mode
+            and (bn.training or bn.track_running_stats))
+
+
+class _Pyramid(nn.Sequential):
+    """The Sequential the reference builds (same slots, same state_dict keys); on CUDA the three
+    element-wise slots of every block run as one fused operator behind the library convolution."""
+
+    def forward(self, x):
+        mods = list(self)
+        for i in range(0, len(mods), 4):
+            conv, bn, act, pool = mods[i:i + 4]
+            y = conv(x)
+            if _fusable(y, bn, act, pool):
+                stride = pool.stride if isinstance(pool.stride, int) else pool.stride[0]
+                x = _BlockTail.apply(y, bn.weight, bn.bias, bn, act.negative_slope, stride)
+            else:
+                x = pool(act(bn(y)))
+        return x
 
 
 def createCNNs(in_channel, channels, strides):
-    layers = nn.Sequential()
+    layers = _Pyramid()
     last = in_channel
     for i, (out_channel, stride) in enumerate(zip(channels, strides)):
         layers.add_module(str(4 * i), nn.Conv2d(last, out_channel, kernel_size=3, stride=1, padding=1, bias=True))

@@ -76,7 +76,22 @@ class FusedMLPFunction(Function):
         dev = x.device
         rows = x.shape[0]
         grad_out = grad_out.contiguous()
-        s12 = [torch.zeros(2, ys[l].shape[1], dtype=f64, device=dev) for l in range(L)]
+        # one zero-filled f64 buffer for every layer's batch-norm sums and one f32 buffer for every dW and
+        # (identically zero) bias gradient: two fill launches per chain instead of three per layer
+        couts = [ys[l].shape[1] for l in range(L)]
+        s12_all = torch.zeros(2 * sum(couts), dtype=f64, device=dev)
+        wsizes = [params[4 * l].numel() for l in range(L)]
+        wz = torch.zeros(sum(wsizes) + sum(couts), dtype=f32, device=dev)
+        s12, dws, dbs = [], [], []
+        o12 = ow = 0
+        for l in range(L):
+            s12.append(s12_all[o12:o12 + 2 * couts[l]].view(2, couts[l]))
+            o12 += 2 * couts[l]
+            dws.append(wz[ow:ow + wsizes[l]].view(params[4 * l].shape))
+            ow += wsizes[l]
+        for l in range(L):
+            dbs.append(wz[ow:ow + couts[l]])
+            ow += couts[l]
 
         def src(l, g):  # (g_dense, dout, arg, k) of layer l
             if l == L - 1 and reduce_k:
@@ -98,20 +113,23 @@ class FusedMLPFunction(Function):
             cout, cin = w.shape
             inp = ys[l - 1] if l > 0 else x
             pst = stats[l - 1] if l > 0 else None
-            dw = torch.zeros(cout, cin, dtype=f32, device=dev)
             call("i2p_pw_linear_bwd_dw", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
                  _p(pst[2]) if pst is not None else None, _p(pst[3]) if pst is not None else None,
-                 float(slopes[l - 1]) if l > 0 else 1.0, dw.data_ptr())
-            grads[4 * l] = dw
-            grads[4 * l + 1] = torch.zeros(cout, dtype=f32, device=dev)  # bias under BN: exactly zero
-            grads[4 * l + 2] = s12[l][1].to(f32)                          # d gamma = sum dz * yhat
-            grads[4 * l + 3] = s12[l][0].to(f32)                          # d beta  = sum dz
+                 float(slopes[l - 1]) if l > 0 else 1.0, dws[l].data_ptr())
+            grads[4 * l] = dws[l]
+            grads[4 * l + 1] = dbs[l]                                       # bias under BN: exactly zero
             if l > 0 or ctx.needs_input_grad[0]:
                 dx = torch.empty(rows, cin, dtype=f32, device=dev)
                 call("i2p_pw_linear_bwd_dx", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), w.data_ptr(),
                      dx.data_ptr(), *(bn(l - 1) if l > 0 else (None, None, None, None, None, 1.0)),
                      s12[l - 1].data_ptr() if l > 0 else None)
                 g = dx
+        gb = s12_all.to(f32)          # every layer's (d beta = sum dz, d gamma = sum dz * yhat), one conversion
+        o12 = 0
+        for l in range(L):
+            grads[4 * l + 3] = gb[o12:o12 + couts[l]]
+            grads[4 * l + 2] = gb[o12 + couts[l]:o12 + 2 * couts[l]]
+            o12 += 2 * couts[l]
         return (dx if ctx.needs_input_grad[0] else None, None, None, None, *grads)
 
 

@@ -27,6 +27,13 @@ def _worker(rank, world, port, ret):
     bucket.zero()
     torch.nn.functional.mse_loss(net(x), y).backward()     # accumulates INTO the flat buffer
     local = bucket.flat.clone()
+    # the step engine's form: drop p.grad, let autograd keep its own tensors, pack them with one cat
+    bucket.release()
+    assert all(p.grad is None for p in net.parameters())
+    torch.nn.functional.mse_loss(net(x), y).backward()
+    bucket.gather()
+    assert torch.equal(bucket.flat, local)
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())
     bucket.all_reduce_mean()
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
