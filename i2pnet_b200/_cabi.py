@@ -52,6 +52,10 @@ _SIGNATURES = {
     "i2p_bn_act_maxk": [_ll, _int, _int, _vp, _vp, _vp, _flt, _vp, _vp, _vp],
     "i2p_bn_bwd_reduce": [_ll, _int, _vp, _vp, _vp, _int] + [_vp] * 5 + [_flt, _vp, _vp],
     "i2p_pw_linear_bwd_dx": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 3 + [_vp] * 5 + [_flt, _vp, _vp],
+    "i2p_pw_pack_weights": [_int, _int, _vp, _vp, _vp],
+    "i2p_pw_linear_fwd_tc": [_int] * 3 + [_vp] * 3 + [_flt] + [_vp] * 5,
+    "i2p_pw_linear_bwd_dx_tc": [_int] * 3 + [_vp] * 6 + [_flt] + [_vp] * 3 + [_vp] * 5 + [_flt, _vp, _vp],
+    "i2p_pw_linear_bwd_dw_tc": [_int] * 3 + [_vp] * 6 + [_flt] + [_vp] * 4 + [_flt, _vp, _vp],
     "i2p_rgb_bn_stats": [_int] * 4 + [_vp, _vp, _vp],
     "i2p_rgb_bn_finalize": [_int, _int, _vp, _vp, _vp, _flt, _flt, _vp, _vp, _vp, _vp, _vp, _vp],
     "i2p_rgb_bn_from_running": [_int, _vp, _vp, _flt, _vp, _vp, _vp, _vp, _vp],
@@ -64,7 +68,7 @@ _SIGNATURES = {
 def exported_symbols():
     """Every entry point include/i2p_b200.h declares."""
     return sorted(list(_SIGNATURES) + ["i2p_last_error", "i2p_abi_version", "i2p_launch_count", "i2p_pw_num_tiles",
-                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out"])
+                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out", "i2p_pw_tc_supported", "i2p_pw_pack_floats"])
 
 
 def lib():
@@ -84,6 +88,10 @@ def lib():
         L.i2p_launch_count.restype = ctypes.c_uint64
         L.i2p_pw_num_tiles.argtypes = [_int]
         L.i2p_pw_num_tiles.restype = _int
+        L.i2p_pw_tc_supported.argtypes = [_int] * 4
+        L.i2p_pw_tc_supported.restype = _int
+        L.i2p_pw_pack_floats.argtypes = [_int, _int]
+        L.i2p_pw_pack_floats.restype = _ll
         L.i2p_rgb_num_chunks.argtypes = [_int]
         L.i2p_rgb_num_chunks.restype = _int
         L.i2p_rgb_pool_out.argtypes = [_int, _int]

@@ -811,23 +811,24 @@ static int launch_dw(DwArgs a, cudaStream_t s) {
 
 static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : 64); }
 
-// Tensor-core (tcgen05, 3xTF32) forward path for layers with cout % 64 == 0 (default on);
-// I2P_MLP_TC=0 selects the f32 FMA kernels everywhere.
+// Which shared-MLP GEMMs run on the tensor cores (tcgen05, 3xTF32; kernels in mlp_tc.cu), as a bit mask:
+// 1 forward, 2 dX, 4 dW, 8 the first-generation forward kernel of this file (kept for A/B measurements).
+// Default 7; environment variable I2P_MLP_TC overrides; 0 = f32 FMA kernels everywhere.
 static int g_mlp_tc = -1;
-static bool mlp_tensor_cores() {
+static int mlp_tc_mask() {
     if (g_mlp_tc < 0) {
         const char *e = getenv("I2P_MLP_TC");
-        g_mlp_tc = (e == nullptr) ? 1 : (atoi(e) != 0);
+        g_mlp_tc = (e == nullptr) ? 7 : atoi(e);
     }
-    return g_mlp_tc != 0;
+    return g_mlp_tc;
 }
 
 }  // namespace i2p
 
 extern "C" {
 
-void i2p_set_mlp_tensor_cores(int on) { i2p::g_mlp_tc = on ? 1 : 0; }
-int i2p_get_mlp_tensor_cores(void) { return i2p::mlp_tensor_cores() ? 1 : 0; }
+void i2p_set_mlp_tensor_cores(int mask) { i2p::g_mlp_tc = mask < 0 ? 0 : mask; }
+int i2p_get_mlp_tensor_cores(void) { return i2p::mlp_tc_mask(); }
 
 int i2p_pw_num_tiles(int rows) { return (rows + i2p::MLP_BM - 1) / i2p::MLP_BM; }
 
@@ -840,8 +841,8 @@ int i2p_pw_linear_fwd(int rows, int cin, int cout, const float *x, const float *
     if (dbg < 0) { const char *e = getenv("I2P_TC_DBG"); dbg = e ? atoi(e) : 0; }
     FwdArgs a{rows, cin, cout, x, in_scale, in_shift, in_slope, w, bias, y, tile_stats, dbg};
     cudaStream_t s = as_stream(stream);
-    if (mlp_tensor_cores() && cout >= 64 && cout % 64 == 0 && cin <= MLP_MAXC) {
-        // tcgen05 path: 128 x 64 tiles, accumulator in TMEM, four CTAs per SM
+    if ((mlp_tc_mask() & 8) && cout >= 64 && cout % 64 == 0 && cin <= MLP_MAXC) {
+        // first-generation tcgen05 path: 128 x 64 tiles, scalar staging, four CTAs per SM
         constexpr int smem = 2 * TcTile<MLP_BM>::BYTES + 2 * TcTile<64>::BYTES;
         static bool once = false;
         if (!once) { cudaFuncSetAttribute(pw_linear_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }

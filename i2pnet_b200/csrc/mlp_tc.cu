@@ -1,0 +1,799 @@
+// Shared per-point MLP on the 5th-generation tensor cores: forward, dX and dW GEMMs of mlp.cu's layer
+// algebra as tcgen05.mma kind::tf32 with the 3-term hi/lo split (f32-accurate, see umma.cuh) and the
+// accumulator in tensor memory.
+//
+// Why the operands are staged by the CTA's threads and not by TMA: every activation operand needs a
+// per-element transform on its way in -- the previous layer's batch-norm + activation (forward, dW) or
+// the reconstruction of dY from (g, y) (dX, dW) -- and the split into (hi, lo) tf32 halves.  What TMA
+// would buy (no register round trip) does not apply; what matters instead is the instruction count of
+// that round trip, which bounded the first version of the forward kernel (ncu: 19 instructions per
+// element, MIO-throttle stalls from scalar STS).  Here
+//   * a thread moves 4 consecutive k of one row: one LDG.128 (or .64 / .32 when the row stride does not
+//     allow it), the transform, one STS.128 for hi and one for lo -- the UMMA canonical no-swizzle
+//     layouts keep 16 bytes of K (K-major) or of M/N (MN-major) contiguous, and the lane -> (row, k)
+//     mapping makes every 8-lane store phase cover 128 contiguous bytes (no bank conflicts);
+//   * the weight operand is split and laid out ONCE per layer and step by a tiny pack kernel; the GEMM
+//     CTAs then fetch it with cp.async 16-byte copies (no registers, no arithmetic);
+//   * dW reads both operands in their natural row-major form as MN-major UMMA operands (K = rows), so
+//     nothing is transposed through shared memory.
+// One CTA = one 128-row (forward, dX) or 128-channel (dW) tile, 256 threads, one shared-memory stage;
+// three to four CTAs share an SM so that staging, tensor-core work and epilogues of different tiles
+// overlap (the same occupancy-based latency hiding as the FMA kernels).
+#include <limits.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace i2p {
+namespace tc {
+
+constexpr int BM = 128, BK = 32, THREADS = 256;
+constexpr int MAXC = 256;   // widest batch-normalised layer the dY tables hold
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void sts128(unsigned char *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d);
+}
+
+// split 4 values and store the hi / lo quadruples (16 bytes each) at the same offset of the two tiles
+__device__ __forceinline__ void split_store4(unsigned char *hi_tile, unsigned char *lo_tile, uint32_t off, float v0,
+                                             float v1, float v2, float v3) {
+    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+    umma::split_tf32(v0, h0, l0);
+    umma::split_tf32(v1, h1, l1);
+    umma::split_tf32(v2, h2, l2);
+    umma::split_tf32(v3, h3, l3);
+    sts128(hi_tile + off, h0, h1, h2, h3);
+    sts128(lo_tile + off, l0, l1, l2, l3);
+}
+
+// 4 consecutive floats of a row whose start is only VEC-element aligned; elements at or beyond `valid` read 0
+template <int VEC>
+__device__ __forceinline__ float4 load4(const float *p, int valid) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (VEC == 4) {
+        if (valid >= 4) v = __ldg(reinterpret_cast<const float4 *>(p));
+    } else if (VEC == 2) {
+        if (valid >= 2) { const float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v.x = t.x; v.y = t.y; }
+        if (valid >= 4) { const float2 t = __ldg(reinterpret_cast<const float2 *>(p + 2)); v.z = t.x; v.w = t.y; }
+    } else {
+        if (valid >= 1) v.x = __ldg(p);
+        if (valid >= 2) v.y = __ldg(p + 1);
+        if (valid >= 3) v.z = __ldg(p + 2);
+        if (valid >= 4) v.w = __ldg(p + 3);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight pack: W (cout, cin) -> tf32 (hi, lo) halves in the UMMA canonical K-major layout, per
+// (n-tile, k-chunk) block [hi: BN x 32 | lo: BN x 32], zero-padded.  Two sections:
+//   F (forward, y = A W^T):  n = output channel, k = input channel;  BN = 64 if cout <= 64 else 128
+//   X (dX = dY W):           n = input channel,  k = output channel; BN = 64 if cin  <= 64 else 128
+// ---------------------------------------------------------------------------------------------
+struct PackGeom {
+    int bn_f, nt_f, nc_f, bn_x, nt_x, nc_x;
+    long long floats_f, floats_x;
+};
+
+__host__ __device__ inline PackGeom pack_geom(int cin, int cout) {
+    PackGeom g;
+    g.bn_f = cout <= 64 ? 64 : 128;
+    g.nt_f = (cout + g.bn_f - 1) / g.bn_f;
+    g.nc_f = (cin + BK - 1) / BK;
+    g.floats_f = (long long)g.nt_f * g.nc_f * 2 * g.bn_f * BK;
+    g.bn_x = cin <= 64 ? 64 : 128;
+    g.nt_x = (cin + g.bn_x - 1) / g.bn_x;
+    g.nc_x = (cout + BK - 1) / BK;
+    g.floats_x = (long long)g.nt_x * g.nc_x * 2 * g.bn_x * BK;
+    return g;
+}
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(int cin, int cout, const float *__restrict__ w,
+                                                           float *__restrict__ pack) {
+    const PackGeom g = pack_geom(cin, cout);
+    const long long half_f = g.floats_f / 2, half_x = g.floats_x / 2;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < half_f + half_x; e += (long long)gridDim.x * 256) {
+        const bool fwd = e < half_f;
+        const long long q = fwd ? e : e - half_f;
+        const int bn = fwd ? g.bn_f : g.bn_x, nc = fwd ? g.nc_f : g.nc_x;
+        const int per = bn * BK;                       // elements of one (tile, chunk) half-block
+        const long long blk = q / per;
+        const int r = (int)(q - blk * per);
+        const int nt = (int)(blk / nc), c = (int)(blk - (long long)nt * nc);
+        // canonical order inside the half-block: ((k / 4) * bn + n) * 4 + k % 4
+        const int k4 = r / (bn * 4), rem = r - k4 * bn * 4, nl = rem >> 2, kl = k4 * 4 + (rem & 3);
+        const int n = nt * bn + nl, k = c * BK + kl;
+        float v = 0.f;
+        if (fwd) { if (n < cout && k < cin) v = __ldg(w + (size_t)n * cin + k); }
+        else     { if (n < cin && k < cout) v = __ldg(w + (size_t)k * cin + n); }
+        uint32_t hi, lo;
+        umma::split_tf32(v, hi, lo);
+        float *base = pack + (fwd ? 0 : g.floats_f) + blk * 2 * per;
+        base[r] = __uint_as_float(hi);
+        base[per + r] = __uint_as_float(lo);
+    }
+}
+
+// instruction descriptor, kind::tf32, f32 accumulate, M = 128; a_mn / b_mn: the operand is MN-major
+__host__ __device__ constexpr uint32_t idesc_tf32(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// One chunk of K = 32: four k-steps of 8, each as hi*hi + lo*hi + hi*lo into the same accumulator.
+// `a_step` / `b_step`: byte distance between consecutive k-steps of an operand tile.
+__device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t a_sbo,
+                                            uint32_t a_step, uint32_t b_hi, uint32_t b_lo, uint32_t b_lbo, uint32_t b_sbo,
+                                            uint32_t b_step, uint32_t idesc, bool first_chunk) {
+#pragma unroll
+    for (int j = 0; j < BK / 8; ++j) {
+        const uint64_t ah = umma::smem_desc(a_hi + j * a_step, a_lbo, a_sbo), al = umma::smem_desc(a_lo + j * a_step, a_lbo, a_sbo);
+        const uint64_t bh = umma::smem_desc(b_hi + j * b_step, b_lbo, b_sbo), bl = umma::smem_desc(b_lo + j * b_step, b_lbo, b_sbo);
+        umma::mma_tf32(tmem_d, ah, bh, idesc, !(first_chunk && j == 0));
+        umma::mma_tf32(tmem_d, al, bh, idesc, true);
+        umma::mma_tf32(tmem_d, ah, bl, idesc, true);
+    }
+}
+
+struct Prologue {
+    uint32_t tmem_d;
+};
+
+// TMEM allocation + mbarrier set-up shared by the three kernels
+template <int COLS>
+__device__ __forceinline__ uint32_t tc_prologue(uint64_t *bar, uint32_t *slot) {
+    if ((threadIdx.x >> 5) == 0) umma::tmem_alloc(slot, COLS);
+    if (threadIdx.x == 0) {
+        umma::mbar_init(bar, 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    return *slot;
+}
+
+// accumulator (128 lanes x BN columns) -> shared tile[128][BN + 4] (+ per-column addend), conflict-free 128-bit stores
+template <int BN>
+__device__ __forceinline__ void tmem_to_tile(uint32_t tmem_d, float *tile, const float *addend, int n0, int nvalid) {
+    constexpr int LDT = BN + 4, CQ = BN / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = (warp & 3) * 32 + lane;      // a warp can only read its own 32 TMEM lanes
+    const int cbase = (warp >> 2) * CQ;          // warps 0-3: first half of the columns, 4-7: second half
+#pragma unroll
+    for (int c0 = 0; c0 < CQ; c0 += 16) {
+        float v[16];
+        umma::tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbase + c0), v);
+        if (addend != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + cbase + c0 + j;
+                v[j] += n < nvalid ? __ldg(addend + n) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4 *>(&tile[row * LDT + cbase + c0 + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+}
+
+// tile[128][BN+4] -> out (rows, ld) at (r0, n0), coalesced; 128-bit stores when the row stride allows
+template <int BN>
+__device__ __forceinline__ void store_tile(const float *tile, float *out, int ld, int r0, int vr, int n0, int nvalid) {
+    constexpr int LDT = BN + 4;
+    if ((ld & 3) == 0) {
+        for (int e = threadIdx.x; e < BM * (BN / 4); e += THREADS) {
+            const int row = e / (BN / 4), c4 = e % (BN / 4);
+            if (row < vr && n0 + c4 * 4 < nvalid)   // ld % 4 == 0 and nvalid == ld: a quad is all in or all out
+                *reinterpret_cast<float4 *>(out + (size_t)(r0 + row) * ld + n0 + c4 * 4) =
+                    *reinterpret_cast<const float4 *>(&tile[row * LDT + c4 * 4]);
+        }
+    } else {
+        for (int e = threadIdx.x; e < BM * BN; e += THREADS) {
+            const int row = e / BN, c = e % BN;
+            if (row < vr && n0 + c < nvalid) out[(size_t)(r0 + row) * ld + n0 + c] = tile[row * LDT + c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward:  y = act(x * in_scale + in_shift) W^T + bias, per-tile (mean, M2) of y
+// ---------------------------------------------------------------------------------------------
+struct FwdArgs {
+    int rows, cin, cout;
+    const float *x, *in_scale, *in_shift;
+    float in_slope;
+    const float *wpack, *bias;
+    float *y, *tile_stats;
+};
+
+// Lane -> operand coordinates of the K-major activation tile (128 rows x 32 k): a warp pass covers 8 rows x
+// 16 k, lanes 0-7 / 8-15 / 16-23 / 24-31 hold the four 16-byte k-groups of rows 0-7, so that each group's
+// 128-bit stores of one phase are 128 contiguous bytes.  Warp w owns k-half (w & 1) and the row blocks
+// (w >> 1) + 4 p, p = 0..3: one thread sees a single k-group per chunk.
+struct KMajorCoords {
+    int rowl, kg, rbase;
+    uint32_t soff;   // byte offset of pass 0 inside a tile; pass p adds p * 4 * 128
+    __device__ KMajorCoords() {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        rowl = lane & 7;
+        kg = (warp & 1) * 4 + (lane >> 3);
+        rbase = (warp >> 1) * 8 + rowl;          // row of pass p: rbase + 32 p
+        soff = (uint32_t)kg * (BM * 16) + (uint32_t)rbase * 16;
+    }
+};
+
+template <int BN>
+__host__ __device__ constexpr int fwd_smem_bytes() {
+    return (2 * BM * BK * 4 + 2 * BN * BK * 4) > (BM * (BN + 4) * 4) ? (2 * BM * BK * 4 + 2 * BN * BK * 4) : (BM * (BN + 4) * 4);
+}
+
+template <int BN, int VEC>
+__global__ void __launch_bounds__(THREADS, BN == 128 ? 3 : 4) fwd_kernel(const FwdArgs a) {
+    constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, SBO = 128;
+    extern __shared__ __align__(1024) unsigned char smem[];   // A hi | A lo | B hi | B lo ; epilogue tile overlays
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float part_n[THREADS / BN][BN], part_mu[THREADS / BN][BN], part_m2[THREADS / BN][BN];
+
+    const int tid = threadIdx.x;
+    const int nt = blockIdx.x, n0 = nt * BN, r0 = blockIdx.y * BM;
+    const uint32_t tmem_d = tc_prologue<BN>(&mma_bar, &tmem_slot);
+    const uint32_t sbase = umma::smem_u32(smem);
+    constexpr uint32_t idesc = idesc_tf32(BN, false, false);
+    const KMajorCoords co;
+    const int nchunks = (a.cin + BK - 1) / BK;
+    const bool has_tf = a.in_scale != nullptr;
+    const float *wblk = a.wpack + (size_t)nt * nchunks * 2 * BN * BK;
+
+    float4 ra[4], sc4, sh4;
+    auto fetch = [&](int c) {
+        const int k = c * BK + co.kg * 4;
+        const int kvalid = a.cin - k;
+        if (has_tf) {
+            sc4 = load4<4>(a.in_scale + k, kvalid >= 4 ? 4 : 0);
+            sh4 = load4<4>(a.in_shift + k, kvalid >= 4 ? 4 : 0);
+            if (kvalid > 0 && kvalid < 4) {   // cin % 4 != 0 never happens for a batch-normalised input; kept for safety
+                sc4 = load4<1>(a.in_scale + k, kvalid);
+                sh4 = load4<1>(a.in_shift + k, kvalid);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int r = r0 + co.rbase + 32 * p;
+            ra[p] = load4<VEC>(a.x + (size_t)r * a.cin + k, r < a.rows ? kvalid : 0);
+        }
+    };
+
+    fetch(0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);   // the tensor core is done with the stage
+        {   // weights of this chunk: straight 16-byte copies of the packed (hi | lo) block
+            const float *src = wblk + (size_t)c * 2 * BN * BK;
+            constexpr int N16 = 2 * B_BYTES / 16;
+#pragma unroll
+            for (int i = 0; i < N16 / THREADS; ++i)
+                cp_async16(sbase + 2 * A_BYTES + (uint32_t)(tid + i * THREADS) * 16, src + (size_t)(tid + i * THREADS) * 4);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float4 v = ra[p];
+            if (has_tf) {   // previous layer's normalise + activation; max(z, slope z) is act for 0 <= slope <= 1
+                float z;
+                z = __fmaf_rn(v.x, sc4.x, sh4.x); v.x = fmaxf(z, z * a.in_slope);
+                z = __fmaf_rn(v.y, sc4.y, sh4.y); v.y = fmaxf(z, z * a.in_slope);
+                z = __fmaf_rn(v.z, sc4.z, sh4.z); v.z = fmaxf(z, z * a.in_slope);
+                z = __fmaf_rn(v.w, sc4.w, sh4.w); v.w = fmaxf(z, z * a.in_slope);
+            }
+            split_store4(smem, smem + A_BYTES, co.soff + (uint32_t)p * 512u, v.x, v.y, v.z, v.w);
+        }
+        cp_async_wait_all();
+        umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, 2 * A_LBO, sbase + 2 * A_BYTES, sbase + 2 * A_BYTES + B_BYTES,
+                        B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
+            umma::commit(&mma_bar);
+        }
+        if (c + 1 < nchunks) fetch(c + 1);   // global loads in flight while the tensor core runs
+    }
+    umma::mbar_wait(&mma_bar, (uint32_t)(nchunks - 1) & 1u);
+    umma::fence_after_sync();
+    __syncthreads();
+
+    float *tile = reinterpret_cast<float *>(smem);
+    constexpr int LDT = BN + 4;
+    tmem_to_tile<BN>(tmem_d, tile, a.bias, n0, a.cout);
+    umma::fence_before_sync();
+    __syncthreads();
+    if ((tid >> 5) == 0) umma::tmem_dealloc(tmem_d, BN);
+
+    const int vr = min(BM, a.rows - r0);
+    store_tile<BN>(tile, a.y, a.cout, r0, vr, n0, a.cout);
+    if (a.tile_stats == nullptr) return;
+    // per-tile (mean, M2): THREADS / BN row parts per column (lanes = consecutive columns), merged with Chan's formula
+    constexpr int PARTS = THREADS / BN, RPP = BM / PARTS;
+    {
+        const int col = tid % BN, part = tid / BN;
+        const int rb0 = part * RPP, re0 = min(vr, rb0 + RPP);
+        float sum = 0.f;
+        for (int r = rb0; r < re0; ++r) sum += tile[r * LDT + col];
+        const float n = (float)max(re0 - rb0, 0);
+        const float mu = n > 0.f ? sum / n : 0.f;
+        float m2 = 0.f;
+        for (int r = rb0; r < re0; ++r) { const float d = tile[r * LDT + col] - mu; m2 += d * d; }
+        part_n[part][col] = n; part_mu[part][col] = mu; part_m2[part][col] = m2;
+    }
+    __syncthreads();
+    if (tid < BN && n0 + tid < a.cout) {
+        float n = part_n[0][tid], mu = part_mu[0][tid], m2 = part_m2[0][tid];
+#pragma unroll
+        for (int p = 1; p < PARTS; ++p) {
+            const float n2 = part_n[p][tid];
+            if (n2 > 0.f) {
+                const float tot = n + n2, d = part_mu[p][tid] - mu, f = n2 / tot;
+                mu += d * f;
+                m2 += part_m2[p][tid] + d * d * n * f;
+                n = tot;
+            }
+        }
+        float *ts = a.tile_stats + ((size_t)blockIdx.y * a.cout + n0 + tid) * 2;
+        ts[0] = mu;
+        ts[1] = m2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dY tables: the per-channel constants that turn (g, y) into dY = scale (dz - S1/n - yhat S2/n)
+// ---------------------------------------------------------------------------------------------
+struct BnRef {
+    const float *y, *mean, *rstd, *scale, *shift;
+    float slope;
+};
+
+struct DyTab {   // [6][MAXC]: scale, shift, mean, rstd, s1n, s2n
+    float v[6][MAXC];
+};
+
+__device__ __forceinline__ void load_dytab(DyTab &t, const BnRef &bn, const double *s12, int c, long long rows) {
+    for (int i = threadIdx.x; i < c; i += THREADS) {
+        t.v[0][i] = bn.scale[i]; t.v[1][i] = bn.shift[i]; t.v[2][i] = bn.mean[i]; t.v[3][i] = bn.rstd[i];
+        t.v[4][i] = (float)(s12[i] / (double)rows);
+        t.v[5][i] = (float)(s12[c + i] / (double)rows);
+    }
+}
+
+__device__ __forceinline__ float dy1(float g, float y, float sc, float sh, float mu, float rs, float s1n, float s2n, float slope) {
+    const float dz = g * (__fmaf_rn(y, sc, sh) > 0.f ? 1.f : slope);
+    return sc * (dz - s1n - ((y - mu) * rs) * s2n);
+}
+
+// 4 channels ch..ch+3 of one row
+__device__ __forceinline__ float4 dy4(const DyTab &t, int ch, float4 g, float4 y, float slope) {
+    const float4 sc = *reinterpret_cast<const float4 *>(&t.v[0][ch]), sh = *reinterpret_cast<const float4 *>(&t.v[1][ch]);
+    const float4 mu = *reinterpret_cast<const float4 *>(&t.v[2][ch]), rs = *reinterpret_cast<const float4 *>(&t.v[3][ch]);
+    const float4 s1 = *reinterpret_cast<const float4 *>(&t.v[4][ch]), s2 = *reinterpret_cast<const float4 *>(&t.v[5][ch]);
+    return make_float4(dy1(g.x, y.x, sc.x, sh.x, mu.x, rs.x, s1.x, s2.x, slope), dy1(g.y, y.y, sc.y, sh.y, mu.y, rs.y, s1.y, s2.y, slope),
+                       dy1(g.z, y.z, sc.z, sh.z, mu.z, rs.z, s1.z, s2.z, slope), dy1(g.w, y.w, sc.w, sh.w, mu.w, rs.w, s1.w, s2.w, slope));
+}
+
+// ---------------------------------------------------------------------------------------------
+// dX = dY W  (rows x cin), dY rebuilt from (g, y) while the A tile is staged; K = cout (multiple of 32).
+// Epilogue: store, and the batch-norm backward sums of the PREVIOUS layer from the tile.
+// ---------------------------------------------------------------------------------------------
+struct DxArgs {
+    int rows, cin, cout;
+    const float *g;      // dense gradient w.r.t. this layer's activated output (rows, cout)
+    BnRef bn;
+    const double *s12;
+    const float *wpack;  // section X of the pack
+    float *dx;
+    BnRef prev;          // prev.y == nullptr: the input is not a batch-normalised layer
+    double *prev_s12;
+};
+
+template <int BN>
+__host__ __device__ constexpr int dx_smem_bytes() { return fwd_smem_bytes<BN>() + (int)sizeof(DyTab); }
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 3) dx_kernel(const DxArgs a) {
+    constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, SBO = 128;
+    constexpr int OPER = fwd_smem_bytes<BN>();
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float part1[THREADS / BN][BN], part2[THREADS / BN][BN];
+    DyTab &tab = *reinterpret_cast<DyTab *>(smem + OPER);
+
+    const int tid = threadIdx.x;
+    const int nt = blockIdx.x, n0 = nt * BN, r0 = blockIdx.y * BM;
+    load_dytab(tab, a.bn, a.s12, a.cout, a.rows);
+    const uint32_t tmem_d = tc_prologue<BN>(&mma_bar, &tmem_slot);   // (its barrier also publishes the tables)
+    const uint32_t sbase = umma::smem_u32(smem);
+    constexpr uint32_t idesc = idesc_tf32(BN, false, false);
+    const KMajorCoords co;
+    const int nchunks = a.cout / BK;
+    const float *wblk = a.wpack + (size_t)nt * nchunks * 2 * BN * BK;
+
+    float4 rg[4], ry[4];
+    auto fetch = [&](int c) {
+        const int k = c * BK + co.kg * 4;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int r = r0 + co.rbase + 32 * p;
+            const int valid = r < a.rows ? 4 : 0;
+            rg[p] = load4<4>(a.g + (size_t)r * a.cout + k, valid);
+            ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + k, valid);
+        }
+    };
+
+    fetch(0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);
+        {
+            const float *src = wblk + (size_t)c * 2 * BN * BK;
+            constexpr int N16 = 2 * B_BYTES / 16;
+#pragma unroll
+            for (int i = 0; i < N16 / THREADS; ++i)
+                cp_async16(sbase + 2 * A_BYTES + (uint32_t)(tid + i * THREADS) * 16, src + (size_t)(tid + i * THREADS) * 4);
+        }
+        const int ch = c * BK + co.kg * 4;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float4 v = dy4(tab, ch, rg[p], ry[p], a.bn.slope);   // rows beyond `rows` give finite garbage: never stored
+            split_store4(smem, smem + A_BYTES, co.soff + (uint32_t)p * 512u, v.x, v.y, v.z, v.w);
+        }
+        cp_async_wait_all();
+        umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, 2 * A_LBO, sbase + 2 * A_BYTES, sbase + 2 * A_BYTES + B_BYTES,
+                        B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
+            umma::commit(&mma_bar);
+        }
+        if (c + 1 < nchunks) fetch(c + 1);
+    }
+    umma::mbar_wait(&mma_bar, (uint32_t)(nchunks - 1) & 1u);
+    umma::fence_after_sync();
+    __syncthreads();
+
+    float *tile = reinterpret_cast<float *>(smem);
+    constexpr int LDT = BN + 4;
+    tmem_to_tile<BN>(tmem_d, tile, nullptr, n0, a.cin);
+    umma::fence_before_sync();
+    __syncthreads();
+    if ((tid >> 5) == 0) umma::tmem_dealloc(tmem_d, BN);
+
+    const int vr = min(BM, a.rows - r0);
+    store_tile<BN>(tile, a.dx, a.cin, r0, vr, n0, a.cin);
+    if (a.prev.y == nullptr) return;
+    constexpr int PARTS = THREADS / BN, RPP = BM / PARTS;
+    {
+        const int col = tid % BN, part = tid / BN, ch = n0 + col;
+        float s1 = 0.f, s2 = 0.f;
+        if (ch < a.cin) {
+            const float mu = a.prev.mean[ch], rs = a.prev.rstd[ch], sc = a.prev.scale[ch], sh = a.prev.shift[ch];
+            const int rb0 = part * RPP, re0 = min(vr, rb0 + RPP);
+            for (int r = rb0; r < re0; ++r) {
+                const float yv = __ldg(a.prev.y + (size_t)(r0 + r) * a.cin + ch);
+                const float dz = tile[r * LDT + col] * (__fmaf_rn(yv, sc, sh) > 0.f ? 1.f : a.prev.slope);
+                s1 += dz;
+                s2 += dz * ((yv - mu) * rs);
+            }
+        }
+        part1[part][col] = s1;
+        part2[part][col] = s2;
+    }
+    __syncthreads();
+    if (tid < BN && n0 + tid < a.cin) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p) { t1 += part1[p][tid]; t2 += part2[p][tid]; }
+        atomicAdd(a.prev_s12 + n0 + tid, (double)t1);
+        atomicAdd(a.prev_s12 + a.cin + n0 + tid, (double)t2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW^T tile:  D[i, o] = sum_r A_prev[r, i] dY[r, o]   (M = 128 input channels, N = BN output channels,
+// K = a chunk of rows), both operands MN-major straight from their row-major tensors; the CTA's
+// partial sum is added to dw (cout, cin) with coalesced atomics.
+// ---------------------------------------------------------------------------------------------
+struct DwArgs {
+    int rows, cin, cout, rows_per_block;
+    const float *g;
+    BnRef bn;
+    const double *s12;
+    const float *x;                 // (rows, cin) raw input / previous raw output
+    const float *prev_scale, *prev_shift;
+    float prev_slope;
+    float *dw;
+};
+
+template <int BN>
+__host__ __device__ constexpr int dw_smem_bytes() { return 2 * BM * BK * 4 + 2 * BN * BK * 4 + (int)sizeof(DyTab); }
+
+// MN-major tile of MN rows x 32 k: element (m, k) at (m % 4) * 4 + (m / 4) * 128 + (k % 8) * 16 + (k / 8) * MN * 32
+template <int BN, int VEC>
+__global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
+    constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr uint32_t A_LBO = BM * 32, B_LBO = BN * 32, SBO = 128;   // LBO: distance between 8-row k-groups
+    extern __shared__ __align__(1024) unsigned char smem[];   // A hi | A lo | B hi | B lo | dY tables
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    DyTab &tab = *reinterpret_cast<DyTab *>(smem + 2 * A_BYTES + 2 * B_BYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.z * BN;   // input-channel tile, output-channel tile
+    const long long rb = (long long)blockIdx.x * a.rows_per_block;
+    const long long re = min((long long)a.rows, rb + a.rows_per_block);
+    load_dytab(tab, a.bn, a.s12, a.cout, a.rows);
+    const uint32_t tmem_d = tc_prologue<BN>(&mma_bar, &tmem_slot);
+    const uint32_t sbase = umma::smem_u32(smem);
+    constexpr uint32_t idesc = idesc_tf32(BN, true, true);
+
+    // lane -> (row within an 8-row k-group, channel quad): 8 rows x 16 channels per warp pass, every 8-lane
+    // store phase writes the 128 contiguous bytes of one (channel quad, k-group) core matrix.
+    const int rl = lane & 7, ql = lane >> 3;
+    // A operand (input channels): warp w owns the 16-channel block w, passes p = 0..3 are the four k-groups
+    const int a_ch = m0 + warp * 16 + ql * 4;
+    const uint32_t a_off = (uint32_t)(warp * 4 + ql) * 128u + (uint32_t)rl * 16u;   // + p * A_LBO
+    // B operand (output channels): BN / 16 channel blocks; with BN = 64 the warps split the k-groups
+    constexpr int B_BLOCKS = BN / 16, B_PASSES = 4 * B_BLOCKS / 8;   // 4 (BN = 128) or 2 (BN = 64)
+    const int b_blk = warp % B_BLOCKS, b_kg0 = warp / B_BLOCKS;      // k-group of pass p: b_kg0 + p * (8 / B_BLOCKS)
+    const int b_ch = n0 + b_blk * 16 + ql * 4;
+    const uint32_t b_off = (uint32_t)(b_blk * 4 + ql) * 128u + (uint32_t)rl * 16u;
+    constexpr int B_KSTEP = 8 / B_BLOCKS;
+
+    const bool has_tf = a.prev_scale != nullptr;
+    float4 psc = make_float4(1.f, 1.f, 1.f, 1.f), psh = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int a_valid = a.cin - a_ch;          // > 0: some of the 4 channels exist
+    if (has_tf && a_valid > 0) {
+        psc = load4<1>(a.prev_scale + a_ch, a_valid);
+        psh = load4<1>(a.prev_shift + a_ch, a_valid);
+    }
+    const bool b_in = b_ch < a.cout;           // cout % 4 == 0: a quad is all in or all out
+
+    float4 rx[4], rg[B_PASSES], ry[B_PASSES];
+    auto fetch = [&](long long r0) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const long long r = r0 + p * 8 + rl;
+            rx[p] = load4<VEC>(a.x + (size_t)r * a.cin + a_ch, r < re ? a_valid : 0);
+        }
+#pragma unroll
+        for (int p = 0; p < B_PASSES; ++p) {
+            const long long r = r0 + (b_kg0 + p * B_KSTEP) * 8 + rl;
+            const int valid = (r < re && b_in) ? 4 : 0;
+            rg[p] = load4<4>(a.g + (size_t)r * a.cout + b_ch, valid);
+            ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + b_ch, valid);
+        }
+    };
+
+    const int nchunks = (int)((re - rb + BK - 1) / BK);
+    fetch(rb);
+    for (int c = 0; c < nchunks; ++c) {
+        const long long r0 = rb + (long long)c * BK;
+        if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float4 v = rx[p];
+            if (has_tf) {
+                float z;
+                z = __fmaf_rn(v.x, psc.x, psh.x); v.x = fmaxf(z, z * a.prev_slope);
+                z = __fmaf_rn(v.y, psc.y, psh.y); v.y = fmaxf(z, z * a.prev_slope);
+                z = __fmaf_rn(v.z, psc.z, psh.z); v.z = fmaxf(z, z * a.prev_slope);
+                z = __fmaf_rn(v.w, psc.w, psh.w); v.w = fmaxf(z, z * a.prev_slope);
+            }
+            // rows beyond the chunk end / channels beyond cin: the dY operand is forced to zero for such rows, and
+            // columns beyond cin are never written back, so finite values suffice here
+            split_store4(smem, smem + A_BYTES, a_off + (uint32_t)p * A_LBO, v.x, v.y, v.z, v.w);
+        }
+#pragma unroll
+        for (int p = 0; p < B_PASSES; ++p) {
+            const int kg = b_kg0 + p * B_KSTEP;
+            const long long r = r0 + kg * 8 + rl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < re && b_in) v = dy4(tab, b_ch, rg[p], ry[p], a.bn.slope);
+            split_store4(smem + 2 * A_BYTES, smem + 2 * A_BYTES + B_BYTES, b_off + (uint32_t)kg * B_LBO, v.x, v.y, v.z, v.w);
+        }
+        umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, A_LBO, sbase + 2 * A_BYTES, sbase + 2 * A_BYTES + B_BYTES,
+                        B_LBO, SBO, B_LBO, idesc, c == 0);
+            umma::commit(&mma_bar);
+        }
+        if (c + 1 < nchunks) fetch(r0 + BK);
+    }
+    if (nchunks > 0) umma::mbar_wait(&mma_bar, (uint32_t)(nchunks - 1) & 1u);
+    umma::fence_after_sync();
+
+    // epilogue: lane = input channel, 16 output channels per tcgen05.ld; coalesced red.add into dw (cout, cin)
+    if (nchunks > 0) {
+        const int i = m0 + (warp & 3) * 32 + lane;
+        constexpr int CQ = BN / 2;
+        const int cbase = (warp >> 2) * CQ;
+#pragma unroll
+        for (int c0 = 0; c0 < CQ; c0 += 16) {
+            float v[16];
+            umma::tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbase + c0), v);
+            if (i < a.cin) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int o = n0 + cbase + c0 + j;
+                    if (o < a.cout) atomicAdd(a.dw + (size_t)o * a.cin + i, v[j]);
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_d, BN);
+}
+
+template <typename K>
+static void allow_smem(K kernel, int bytes) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+// widest aligned access a (rows, ld) tensor at `p` allows for 4 consecutive elements of a row
+static int vec_of(int ld, const void *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if ((ld & 3) == 0 && (a & 15) == 0) return 4;
+    if ((ld & 1) == 0 && (a & 7) == 0) return 2;
+    return 1;
+}
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace tc
+}  // namespace i2p
+
+extern "C" {
+
+/* which shapes the tensor-core kernels cover; kind: 0 forward, 1 dX, 2 dW */
+int i2p_pw_tc_supported(int kind, int rows, int cin, int cout) {
+    using namespace i2p::tc;
+    if (rows < 1 || cin < 1 || cout < 64 || cout % 32 != 0) return 0;
+    if (kind == 0) return cin <= 4096 ? 1 : 0;
+    if (cout > MAXC) return 0;
+    return cin >= 32 ? 1 : 0;   // skinny inputs (xyz encodings) stay on the FMA kernels
+}
+
+long long i2p_pw_pack_floats(int cin, int cout) {
+    const i2p::tc::PackGeom g = i2p::tc::pack_geom(cin, cout);
+    return g.floats_f + g.floats_x;
+}
+
+int i2p_pw_pack_weights(int cin, int cout, const float *w, float *pack, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(cin >= 1 && cout >= 1, "pw_pack_weights: bad sizes");
+    const tc::PackGeom g = tc::pack_geom(cin, cout);
+    const long long total = (g.floats_f + g.floats_x) / 2;
+    const long long blocks = (total + 255) / 256;
+    tc::pack_weights_kernel<<<(int)(blocks < 592 ? blocks : 592), 256, 0, as_stream(stream)>>>(cin, cout, w, pack);
+    return check_launch("pw_pack_weights");
+}
+
+int i2p_pw_linear_fwd_tc(int rows, int cin, int cout, const float *x, const float *in_scale, const float *in_shift,
+                         float in_slope, const float *wpack, const float *bias, float *y, float *tile_stats, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(i2p_pw_tc_supported(0, rows, cin, cout), "pw_linear_fwd_tc: shape not covered (cout %% 32 == 0, cout >= 64)");
+    I2P_REQUIRE(in_slope >= 0.f && in_slope <= 1.f, "pw_linear_fwd_tc: activation slope must be in [0, 1]");
+    I2P_REQUIRE(tc::aligned16(wpack) && tc::aligned16(y) && tc::aligned16(in_scale) && tc::aligned16(in_shift),
+                "pw_linear_fwd_tc: wpack, y, in_scale, in_shift must be 16-byte aligned");
+    tc::FwdArgs a{rows, cin, cout, x, in_scale, in_shift, in_slope, wpack, bias, y, tile_stats};
+    const tc::PackGeom g = tc::pack_geom(cin, cout);
+    cudaStream_t s = as_stream(stream);
+    dim3 grid(g.nt_f, ceil_div(rows, tc::BM));
+    const int vec = tc::vec_of(cin, x);
+    static bool once = false;
+    if (!once) {
+        tc::allow_smem(tc::fwd_kernel<64, 4>, tc::fwd_smem_bytes<64>());
+        tc::allow_smem(tc::fwd_kernel<64, 2>, tc::fwd_smem_bytes<64>());
+        tc::allow_smem(tc::fwd_kernel<64, 1>, tc::fwd_smem_bytes<64>());
+        tc::allow_smem(tc::fwd_kernel<128, 4>, tc::fwd_smem_bytes<128>());
+        tc::allow_smem(tc::fwd_kernel<128, 2>, tc::fwd_smem_bytes<128>());
+        tc::allow_smem(tc::fwd_kernel<128, 1>, tc::fwd_smem_bytes<128>());
+        once = true;
+    }
+    if (g.bn_f == 64) {
+        constexpr int sm = tc::fwd_smem_bytes<64>();
+        if (vec == 4) tc::fwd_kernel<64, 4><<<grid, tc::THREADS, sm, s>>>(a);
+        else if (vec == 2) tc::fwd_kernel<64, 2><<<grid, tc::THREADS, sm, s>>>(a);
+        else tc::fwd_kernel<64, 1><<<grid, tc::THREADS, sm, s>>>(a);
+    } else {
+        constexpr int sm = tc::fwd_smem_bytes<128>();
+        if (vec == 4) tc::fwd_kernel<128, 4><<<grid, tc::THREADS, sm, s>>>(a);
+        else if (vec == 2) tc::fwd_kernel<128, 2><<<grid, tc::THREADS, sm, s>>>(a);
+        else tc::fwd_kernel<128, 1><<<grid, tc::THREADS, sm, s>>>(a);
+    }
+    return check_launch("pw_linear_fwd_tc");
+}
+
+int i2p_pw_linear_bwd_dx_tc(int rows, int cin, int cout, const float *g_dense, const float *y, const float *mean,
+                            const float *rstd, const float *scale, const float *shift, float slope, const double *s12,
+                            const float *wpack, float *dx, const float *prev_y, const float *prev_mean,
+                            const float *prev_rstd, const float *prev_scale, const float *prev_shift, float prev_slope,
+                            double *prev_s12, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(i2p_pw_tc_supported(1, rows, cin, cout) && g_dense != nullptr, "pw_linear_bwd_dx_tc: shape not covered");
+    I2P_REQUIRE(tc::aligned16(g_dense) && tc::aligned16(y) && tc::aligned16(wpack) && tc::aligned16(dx),
+                "pw_linear_bwd_dx_tc: g, y, wpack, dx must be 16-byte aligned");
+    const tc::PackGeom g = tc::pack_geom(cin, cout);
+    tc::DxArgs a;
+    a.rows = rows; a.cin = cin; a.cout = cout; a.g = g_dense;
+    a.bn = tc::BnRef{y, mean, rstd, scale, shift, slope};
+    a.s12 = s12; a.wpack = wpack + g.floats_f; a.dx = dx;
+    a.prev = tc::BnRef{prev_y, prev_mean, prev_rstd, prev_scale, prev_shift, prev_slope};
+    a.prev_s12 = prev_s12;
+    static bool once = false;
+    if (!once) {
+        tc::allow_smem(tc::dx_kernel<64>, tc::dx_smem_bytes<64>());
+        tc::allow_smem(tc::dx_kernel<128>, tc::dx_smem_bytes<128>());
+        once = true;
+    }
+    cudaStream_t s = as_stream(stream);
+    dim3 grid(g.nt_x, ceil_div(rows, tc::BM));
+    if (g.bn_x == 64) tc::dx_kernel<64><<<grid, tc::THREADS, tc::dx_smem_bytes<64>(), s>>>(a);
+    else tc::dx_kernel<128><<<grid, tc::THREADS, tc::dx_smem_bytes<128>(), s>>>(a);
+    return check_launch("pw_linear_bwd_dx_tc");
+}
+
+int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, const float *y, const float *mean,
+                            const float *rstd, const float *scale, const float *shift, float slope, const double *s12,
+                            const float *x, const float *prev_scale, const float *prev_shift, float prev_slope, float *dw,
+                            void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(i2p_pw_tc_supported(2, rows, cin, cout) && g_dense != nullptr, "pw_linear_bwd_dw_tc: shape not covered");
+    I2P_REQUIRE(prev_slope >= 0.f && prev_slope <= 1.f, "pw_linear_bwd_dw_tc: activation slope must be in [0, 1]");
+    I2P_REQUIRE(tc::aligned16(g_dense) && tc::aligned16(y), "pw_linear_bwd_dw_tc: g, y must be 16-byte aligned");
+    tc::DwArgs a;
+    a.rows = rows; a.cin = cin; a.cout = cout; a.g = g_dense;
+    a.bn = tc::BnRef{y, mean, rstd, scale, shift, slope};
+    a.s12 = s12; a.x = x; a.prev_scale = prev_scale; a.prev_shift = prev_shift; a.prev_slope = prev_slope; a.dw = dw;
+    const int bn = cout <= 64 ? 64 : 128;
+    const int mt = ceil_div(cin, tc::BM), ntl = ceil_div(cout, bn);
+    // about two waves of CTAs (2 resident per SM), at least 8 chunks of rows per CTA
+    int chunks = (2 * 2 * 148 + mt * ntl - 1) / (mt * ntl);
+    int rpb = (rows + chunks - 1) / chunks;
+    rpb = ((rpb + tc::BK - 1) / tc::BK) * tc::BK;
+    if (rpb < 8 * tc::BK) rpb = 8 * tc::BK;
+    a.rows_per_block = rpb;
+    static bool once = false;
+    if (!once) {
+        tc::allow_smem(tc::dw_kernel<64, 4>, tc::dw_smem_bytes<64>());
+        tc::allow_smem(tc::dw_kernel<64, 2>, tc::dw_smem_bytes<64>());
+        tc::allow_smem(tc::dw_kernel<64, 1>, tc::dw_smem_bytes<64>());
+        tc::allow_smem(tc::dw_kernel<128, 4>, tc::dw_smem_bytes<128>());
+        tc::allow_smem(tc::dw_kernel<128, 2>, tc::dw_smem_bytes<128>());
+        tc::allow_smem(tc::dw_kernel<128, 1>, tc::dw_smem_bytes<128>());
+        once = true;
+    }
+    cudaStream_t s = as_stream(stream);
+    dim3 grid(ceil_div(rows, rpb), mt, ntl);
+    const int vec = tc::vec_of(cin, x);
+    if (bn == 64) {
+        constexpr int sm = tc::dw_smem_bytes<64>();
+        if (vec == 4) tc::dw_kernel<64, 4><<<grid, tc::THREADS, sm, s>>>(a);
+        else if (vec == 2) tc::dw_kernel<64, 2><<<grid, tc::THREADS, sm, s>>>(a);
+        else tc::dw_kernel<64, 1><<<grid, tc::THREADS, sm, s>>>(a);
+    } else {
+        constexpr int sm = tc::dw_smem_bytes<128>();
+        if (vec == 4) tc::dw_kernel<128, 4><<<grid, tc::THREADS, sm, s>>>(a);
+        else if (vec == 2) tc::dw_kernel<128, 2><<<grid, tc::THREADS, sm, s>>>(a);
+        else tc::dw_kernel<128, 1><<<grid, tc::THREADS, sm, s>>>(a);
+    }
+    return check_launch("pw_linear_bwd_dw_tc");
+}
+}

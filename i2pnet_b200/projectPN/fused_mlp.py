@@ -31,23 +31,37 @@ class FusedMLPFunction(Function):
         dev = x.device
         rows = x.shape[0]
         L = len(params) // 4
-        ntiles = _cabi.lib().i2p_pw_num_tiles(rows)
-        ys, stats = [], []
+        lib = _cabi.lib()
+        ntiles = lib.i2p_pw_num_tiles(rows)
+        tc_mask = lib.i2p_get_mlp_tensor_cores()
+        ys, stats, packs = [], [], []
         inp, in_stats, in_slope = x, None, 1.0
         for l in range(L):
             w, b, gamma, beta = params[4 * l:4 * l + 4]
             cout, cin = w.shape
             y = torch.empty(rows, cout, dtype=f32, device=dev)
             tiles = torch.empty(ntiles, cout, 2, dtype=f32, device=dev)
-            call("i2p_pw_linear_fwd", dev, rows, cin, cout, _ptr(inp, f32, "x", dev),
-                 _p(in_stats[2]) if in_stats is not None else None, _p(in_stats[3]) if in_stats is not None else None,
-                 float(in_slope), _ptr(w, f32, "weight", dev), _ptr(b, f32, "bias", dev), y.data_ptr(), tiles.data_ptr())
+            fwd_tc = bool(tc_mask & 1) and lib.i2p_pw_tc_supported(0, rows, cin, cout)
+            dx_tc = bool(tc_mask & 2) and lib.i2p_pw_tc_supported(1, rows, cin, cout)
+            pack = None
+            if fwd_tc or dx_tc:   # tf32 (hi, lo) halves of W in the UMMA layout, both orientations, once per step
+                pack = torch.empty(lib.i2p_pw_pack_floats(cin, cout), dtype=f32, device=dev)
+                call("i2p_pw_pack_weights", dev, cin, cout, _ptr(w, f32, "weight", dev), pack.data_ptr())
+            scale_p = _p(in_stats[2]) if in_stats is not None else None
+            shift_p = _p(in_stats[3]) if in_stats is not None else None
+            if fwd_tc:
+                call("i2p_pw_linear_fwd_tc", dev, rows, cin, cout, _ptr(inp, f32, "x", dev), scale_p, shift_p, float(in_slope),
+                     pack.data_ptr(), _ptr(b, f32, "bias", dev), y.data_ptr(), tiles.data_ptr())
+            else:
+                call("i2p_pw_linear_fwd", dev, rows, cin, cout, _ptr(inp, f32, "x", dev), scale_p, shift_p, float(in_slope),
+                     _ptr(w, f32, "weight", dev), _ptr(b, f32, "bias", dev), y.data_ptr(), tiles.data_ptr())
             st = torch.empty(4, cout, dtype=f32, device=dev)  # mean, rstd, scale, shift
             call("i2p_bn_finalize", dev, rows, cout, tiles.data_ptr(), _ptr(gamma, f32, "gamma", dev),
                  _ptr(beta, f32, "beta", dev), float(eps[l]), st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(),
                  st[3].data_ptr())
             ys.append(y)
             stats.append(st)
+            packs.append(pack)
             inp, in_stats, in_slope = y, st, slopes[l]
         c_last = ys[-1].shape[1]
         st = stats[-1]
@@ -64,6 +78,7 @@ class FusedMLPFunction(Function):
                  out.data_ptr())
         ctx.save_for_backward(x, *params, *ys, *stats, *([arg] if arg is not None else []))
         ctx.meta = (L, reduce_k, tuple(slopes))
+        ctx.packs = packs     # the weights do not change between forward and backward
         return out
 
     @staticmethod
@@ -103,6 +118,11 @@ class FusedMLPFunction(Function):
             return (ys[l].data_ptr(), st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(),
                     float(slopes[l]))
 
+        lib = _cabi.lib()
+        tc_mask = lib.i2p_get_mlp_tensor_cores()
+        packs = ctx.packs
+        if not reduce_k and grad_out.data_ptr() % 16:
+            grad_out = grad_out.clone()        # the tensor-core kernels read gradients with 128-bit loads
         g = None if reduce_k else grad_out
         c_last = ys[-1].shape[1]
         call("i2p_bn_bwd_reduce", dev, rows, c_last, *src(L - 1, g), *bn(L - 1), s12[L - 1].data_ptr())
@@ -113,16 +133,28 @@ class FusedMLPFunction(Function):
             cout, cin = w.shape
             inp = ys[l - 1] if l > 0 else x
             pst = stats[l - 1] if l > 0 else None
-            call("i2p_pw_linear_bwd_dw", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
-                 _p(pst[2]) if pst is not None else None, _p(pst[3]) if pst is not None else None,
-                 float(slopes[l - 1]) if l > 0 else 1.0, dws[l].data_ptr())
+            dense = not (l == L - 1 and reduce_k)     # the max-over-K source is routed through arg-max: FMA kernels
+            pscale = _p(pst[2]) if pst is not None else None
+            pshift = _p(pst[3]) if pst is not None else None
+            pslope = float(slopes[l - 1]) if l > 0 else 1.0
+            if dense and (tc_mask & 4) and lib.i2p_pw_tc_supported(2, rows, cin, cout):
+                call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, g.data_ptr(), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
+                     pscale, pshift, pslope, dws[l].data_ptr())
+            else:
+                call("i2p_pw_linear_bwd_dw", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
+                     pscale, pshift, pslope, dws[l].data_ptr())
             grads[4 * l] = dws[l]
             grads[4 * l + 1] = dbs[l]                                       # bias under BN: exactly zero
             if l > 0 or ctx.needs_input_grad[0]:
                 dx = torch.empty(rows, cin, dtype=f32, device=dev)
-                call("i2p_pw_linear_bwd_dx", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), w.data_ptr(),
-                     dx.data_ptr(), *(bn(l - 1) if l > 0 else (None, None, None, None, None, 1.0)),
-                     s12[l - 1].data_ptr() if l > 0 else None)
+                prev = bn(l - 1) if l > 0 else (None, None, None, None, None, 1.0)
+                prev_s12 = s12[l - 1].data_ptr() if l > 0 else None
+                if dense and (tc_mask & 2) and packs[l] is not None and lib.i2p_pw_tc_supported(1, rows, cin, cout):
+                    call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, g.data_ptr(), *bn(l), s12[l].data_ptr(),
+                         packs[l].data_ptr(), dx.data_ptr(), *prev, prev_s12)
+                else:
+                    call("i2p_pw_linear_bwd_dx", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), w.data_ptr(),
+                         dx.data_ptr(), *prev, prev_s12)
                 g = dx
         gb = s12_all.to(f32)          # every layer's (d beta = sum dz, d gamma = sum dz * yhat), one conversion
         o12 = 0

@@ -23,9 +23,10 @@ def oracle_backend(monkeypatch):
     yield
 
 
-@pytest.fixture(params=[0, 1], ids=["fma", "tcgen05"])
+@pytest.fixture(params=[0, 7], ids=["fma", "tcgen05"])
 def tensor_cores(request):
-    """Both shared-MLP kernel families: f32 FMA and tcgen05 tf32 with the 3-term hi/lo split."""
+    """Both shared-MLP kernel families: f32 FMA (mask 0) and tcgen05 tf32 with the 3-term hi/lo split for
+    the forward, dX and dW GEMMs (mask 7, include/i2p_b200.h)."""
     from i2pnet_b200 import _cabi
     L = _cabi.lib()
     before = L.i2p_get_mlp_tensor_cores()
