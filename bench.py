@@ -9,7 +9,8 @@ step (forward + loss + backward + grad all-reduce + clip + Adam) on KITTI-shaped
 
 Keys follow the driver's contract: `value` = whole-job pairs/s with inputs resident in HBM,
 `e2e` = the same through TrainStep.step_from_host (pinned host batch -> device -> step -> loss on
-host), `roofline` = the dominant own kernel against the measured HBM peak, `cpu_baseline` = the
+host), `roofline` = the dominant own kernel (the tensor-core dW GEMM of the largest shared-MLP layer; the other hot
+kernels follow in `roofline_others`) against the measured HBM peak, `cpu_baseline` = the
 CPU oracle port (oracle/model_cpu.py) on a bounded sample.  The oracle is executed only in the
 cpu_baseline leg and the --impl reference arm.
 """
@@ -124,32 +125,84 @@ def run_reference(args):
     }))
 
 
-def time_select_kernel(device, peak):
-    """The dominant own kernel in isolation: projection-window select at the SA1 shape, batch 8,
-    CUDA events on the launching stream, L2 flushed between launches."""
+def _event_time(fn, flush, reps=25, skip=5):
+    """Median CUDA-event duration (ms) of fn() on torch's current stream, L2 flushed before every launch."""
     import torch
-    from i2pnet_b200.projectPN.utils import FLAG_COPY, FLAG_SHIFT, StrideGrid, project_seq, select_flat
-    from i2pnet_b200.synthetic import make_pairs
-    d = make_pairs(BATCH, N_POINTS, IMAGE_HW, seed=7)
-    _, (cam,) = project_seq(d["raw_point_xyz"].to(device), [d["lidar"].to(device)], 64, 1800, False)
-    grid = StrideGrid(BATCH, 16, 225, 4, 8, device)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     evs = []
-    for i in range(25):
+    for i in range(reps):
         flush.fill_(i & 0xff)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        select_flat(cam, cam, grid, [9, 15], 32, FLAG_SHIFT | FLAG_COPY, 0.75)
+        fn()
         b.record()
         evs.append((a, b))
-    torch.cuda.synchronize(device)
-    ms = statistics.median(a.elapsed_time(b) for a, b in evs[5:])
+    torch.cuda.synchronize()
+    return statistics.median(a.elapsed_time(b) for a, b in evs[skip:])
+
+
+def _traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(kernel)
+    except Exception:
+        return None
+
+
+def time_hot_kernels(device, peak):
+    """The own kernels that dominate the step, each alone at its largest shape of the workload (batch 8):
+    the three tensor-core GEMMs of cost-volume-1's first shared-MLP layer (rows = 8 x 228 x 80, 262 -> 128)
+    and the projection-window select at SA1.  -> (roofline of the dominant kernel, list for the others)"""
+    import torch
+    from i2pnet_b200 import _cabi
+    from i2pnet_b200._cabi import call
+    from i2pnet_b200.projectPN.utils import FLAG_COPY, FLAG_SHIFT, StrideGrid, project_seq, select_flat
+    from i2pnet_b200.synthetic import make_pairs
+    L = _cabi.lib()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    rows, cin, cout = BATCH * 228 * 80, 262, 128
+    g = torch.Generator(device=device).manual_seed(0)
+    x = torch.randn(rows, cin, device=device, generator=g)
+    w, b = torch.randn(cout, cin, device=device, generator=g) * 0.1, torch.randn(cout, device=device, generator=g)
+    gam, bet = torch.ones(cout, device=device), torch.zeros(cout, device=device)
+    y, gr = torch.empty(rows, cout, device=device), torch.randn(rows, cout, device=device, generator=g)
+    tiles = torch.empty(L.i2p_pw_num_tiles(rows), cout, 2, device=device)
+    st = torch.empty(4, cout, device=device)
+    pack = torch.empty(L.i2p_pw_pack_floats(cin, cout), device=device)
+    s12 = torch.zeros(2, cout, dtype=torch.float64, device=device)
+    dx, dw = torch.empty(rows, cin, device=device), torch.zeros(cout, cin, device=device)
+    call("i2p_pw_pack_weights", device, cin, cout, w.data_ptr(), pack.data_ptr())
+    fwd = lambda: call("i2p_pw_linear_fwd_tc", device, rows, cin, cout, x.data_ptr(), None, None, 1.0, pack.data_ptr(),
+                       b.data_ptr(), y.data_ptr(), tiles.data_ptr())
+    fwd()
+    call("i2p_bn_finalize", device, rows, cout, tiles.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-5, st[0].data_ptr(),
+         st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr())
+    bn = (y.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), 0.1)
+    none_prev = (None, None, None, None, None, 1.0, None)
+    dxf = lambda: call("i2p_pw_linear_bwd_dx_tc", device, rows, cin, cout, gr.data_ptr(), *bn, s12.data_ptr(), pack.data_ptr(),
+                       dx.data_ptr(), *none_prev)
+    dwf = lambda: call("i2p_pw_linear_bwd_dw_tc", device, rows, cin, cout, gr.data_ptr(), *bn, s12.data_ptr(), x.data_ptr(),
+                       None, None, 1.0, dw.data_ptr())
+    d = make_pairs(BATCH, N_POINTS, IMAGE_HW, seed=7)
+    _, (cam,) = project_seq(d["raw_point_xyz"].to(device), [d["lidar"].to(device)], 64, 1800, False)
+    grid = StrideGrid(BATCH, 16, 225, 4, 8, device)
+    sel = lambda: select_flat(cam, cam, grid, [9, 15], 32, FLAG_SHIFT | FLAG_COPY, 0.75)
     n, K = 3600, 32
-    alg = BATCH * (12 * 64 * 1800 + 8 * n * K)   # xyz2 once + int32 index + f32 mask (compact form)
-    achieved = alg / (ms * 1e-3) / 1e9
-    return {"kernel": "select_k_kernel<5,flat> @SA1 (64x1800, 3600 centres, 9x15, K=32, batch 8)", "bound": "hbm",
-            "achieved": achieved, "peak": peak[0], "peak_source": peak[1], "unit": "GB/s", "frac": achieved / peak[0],
-            "traffic": None, "algorithmic_bytes": alg, "us_per_launch": ms * 1e3}
+    shape = "cost-volume-1 mlp1 layer 1 (rows 8x228x80 = %d, 262 -> 128), batch 8" % rows
+    specs = [   # name, launcher, algorithmic bytes per launch (SURVEY.md section 8d)
+        ("tc::dw_kernel<128,2> @ " + shape, dwf, 4 * rows * (2 * cout + cin)),
+        ("tc::dx_kernel<128> @ " + shape, dxf, 4 * rows * (2 * cout + cin)),
+        ("tc::fwd_kernel<128,2> @ " + shape, fwd, 4 * rows * (cin + cout)),
+        ("select_k_kernel<5,flat> @ SA1 (64x1800, 3600 centres, 9x15, K=32), batch 8", sel, BATCH * (12 * 64 * 1800 + 8 * n * K)),
+    ]
+    out = []
+    for name, fn, alg in specs:
+        ms = _event_time(fn, flush)
+        achieved = alg / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak[0], "peak_source": peak[1],
+                    "unit": "GB/s", "frac": achieved / peak[0], "traffic": _traffic(name.split(" @")[0]),
+                    "algorithmic_bytes": alg, "us_per_launch": ms * 1e3})
+    return out[0], out[1:]
 
 
 def run_ours(args):
@@ -218,7 +271,7 @@ def run_ours(args):
 
     if rank == 0:
         peak = _peaks()
-        roof = time_select_kernel(device, peak)
+        roof, roof_others = time_hot_kernels(device, peak)
         value = world * BATCH * args.steps / (ms * 1e-3)
         e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
         h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in INPUT_KEYS)
@@ -234,12 +287,14 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points": N_POINTS, "image": list(IMAGE_HW), "per_gpu_batch": BATCH,
                        "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "rgb_channels_last": args.channels_last,
-                       "l2": "256 MB flush write between steps", "tf32": False, "final_loss": loss},
+                       "l2": "256 MB flush write between steps", "tf32": False,
+                       "shared_mlp": "tcgen05 3xTF32 split (f32-accurate), mask %d" % _cabi.lib().i2p_get_mlp_tensor_cores(),
+                       "final_loss": loss},
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(eng.launches_per_step) * args.steps,
             "gpu_launches_per_step": int(eng.launches_per_step),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "roofline_others": roof_others, "cpu_baseline": cpu,
         }))
     if world > 1:
         dist.destroy_process_group()

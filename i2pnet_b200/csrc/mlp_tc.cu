@@ -15,11 +15,14 @@
 //   * the weight operand is split and laid out ONCE per layer and step by a tiny pack kernel; the GEMM
 //     CTAs then fetch it with cp.async 16-byte copies (no registers, no arithmetic);
 //   * dW reads both operands in their natural row-major form as MN-major UMMA operands (K = rows), so
-//     nothing is transposed through shared memory.
+//     nothing is transposed through shared memory.  (For 32-bit elements the tensor core takes MN-major
+//     operands in one layout only, SWIZZLE_128B_BASE32B; with the no-swizzle layout it silently
+//     accumulates zeros -- measured, and CUTLASS's sm100 builder asserts the same.)
 // One CTA = one 128-row (forward, dX) or 128-channel (dW) tile, 256 threads, one shared-memory stage;
 // three to four CTAs share an SM so that staging, tensor-core work and epilogues of different tiles
 // overlap (the same occupancy-based latency hiding as the FMA kernels).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -522,11 +525,18 @@ struct DwArgs {
 template <int BN>
 __host__ __device__ constexpr int dw_smem_bytes() { return 2 * BM * BK * 4 + 2 * BN * BK * 4 + (int)sizeof(DyTab); }
 
-// MN-major tile of MN rows x 32 k: element (m, k) at (m % 4) * 4 + (m / 4) * 128 + (k % 8) * 16 + (k / 8) * MN * 32
+// MN-major operand tile (MN channels x 32 rows of K).  For 32-bit operands the tensor core accepts an MN-major
+// tile in exactly one shared-memory layout, UMMA SWIZZLE_128B_BASE32B: atoms of 4 k-rows x 32 channels (4 x 128 B,
+// channels contiguous), inside which the 32-byte chunk index (channel / 8) is XORed with the k-row index; atom
+// (channel block mb, row block kb) sits at mb * LBO + kb * SBO with LBO = 4096 (eight row blocks), SBO = 512.
+// One MMA (K = 8) reads two row blocks: the descriptor start advances by 1024 per k-step.
+// A warp pass stages one atom: lane -> (k-row r4, 16-byte half, 8-channel chunk c8); every 8-lane store phase
+// then covers 4 rows x 32 B in 4 different chunk positions = all 32 banks once, and every global row is read
+// as 128 contiguous bytes.
 template <int BN, int VEC>
 __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
     constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-    constexpr uint32_t A_LBO = BM * 32, B_LBO = BN * 32, SBO = 128;   // LBO: distance between 8-row k-groups
+    constexpr uint32_t LBO = 4096, SBO = 512, KSTEP_BYTES = 1024;
     extern __shared__ __align__(1024) unsigned char smem[];   // A hi | A lo | B hi | B lo | dY tables
     __shared__ uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
@@ -541,18 +551,17 @@ __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
     const uint32_t sbase = umma::smem_u32(smem);
     constexpr uint32_t idesc = idesc_tf32(BN, true, true);
 
-    // lane -> (row within an 8-row k-group, channel quad): 8 rows x 16 channels per warp pass, every 8-lane
-    // store phase writes the 128 contiguous bytes of one (channel quad, k-group) core matrix.
-    const int rl = lane & 7, ql = lane >> 3;
-    // A operand (input channels): warp w owns the 16-channel block w, passes p = 0..3 are the four k-groups
-    const int a_ch = m0 + warp * 16 + ql * 4;
-    const uint32_t a_off = (uint32_t)(warp * 4 + ql) * 128u + (uint32_t)rl * 16u;   // + p * A_LBO
-    // B operand (output channels): BN / 16 channel blocks; with BN = 64 the warps split the k-groups
-    constexpr int B_BLOCKS = BN / 16, B_PASSES = 4 * B_BLOCKS / 8;   // 4 (BN = 128) or 2 (BN = 64)
-    const int b_blk = warp % B_BLOCKS, b_kg0 = warp / B_BLOCKS;      // k-group of pass p: b_kg0 + p * (8 / B_BLOCKS)
-    const int b_ch = n0 + b_blk * 16 + ql * 4;
-    const uint32_t b_off = (uint32_t)(b_blk * 4 + ql) * 128u + (uint32_t)rl * 16u;
-    constexpr int B_KSTEP = 8 / B_BLOCKS;
+    const int r4 = lane & 3, half = (lane >> 2) & 1, c8 = lane >> 3;
+    const uint32_t in_atom = (uint32_t)r4 * 128u + ((uint32_t)(c8 ^ r4) << 5) + (uint32_t)half * 16u;
+    // A operand (input channels): warp w owns channel block (w & 3) and the row blocks (w >> 2) + 2 p, p = 0..3
+    const int a_kb0 = warp >> 2;
+    const int a_ch = m0 + (warp & 3) * 32 + c8 * 8 + half * 4;
+    const uint32_t a_off = (uint32_t)(warp & 3) * LBO + (uint32_t)a_kb0 * SBO + in_atom;   // + p * 2 * SBO
+    // B operand (output channels): BN / 32 channel blocks; row blocks b_kb0 + p * B_KSTEP
+    constexpr int B_MB = BN / 32, B_KSTEP = 8 / B_MB, B_PASSES = B_MB;   // BN = 128: 4, 2, 4;  BN = 64: 2, 4, 2
+    const int b_kb0 = warp / B_MB;
+    const int b_ch = n0 + (warp % B_MB) * 32 + c8 * 8 + half * 4;
+    const uint32_t b_off = (uint32_t)(warp % B_MB) * LBO + (uint32_t)b_kb0 * SBO + in_atom;   // + p * B_KSTEP * SBO
 
     const bool has_tf = a.prev_scale != nullptr;
     float4 psc = make_float4(1.f, 1.f, 1.f, 1.f), psh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -567,12 +576,12 @@ __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
     auto fetch = [&](long long r0) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const long long r = r0 + p * 8 + rl;
+            const long long r = r0 + (a_kb0 + 2 * p) * 4 + r4;
             rx[p] = load4<VEC>(a.x + (size_t)r * a.cin + a_ch, r < re ? a_valid : 0);
         }
 #pragma unroll
         for (int p = 0; p < B_PASSES; ++p) {
-            const long long r = r0 + (b_kg0 + p * B_KSTEP) * 8 + rl;
+            const long long r = r0 + (b_kb0 + p * B_KSTEP) * 4 + r4;
             const int valid = (r < re && b_in) ? 4 : 0;
             rg[p] = load4<4>(a.g + (size_t)r * a.cout + b_ch, valid);
             ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + b_ch, valid);
@@ -596,22 +605,29 @@ __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
             }
             // rows beyond the chunk end / channels beyond cin: the dY operand is forced to zero for such rows, and
             // columns beyond cin are never written back, so finite values suffice here
-            split_store4(smem, smem + A_BYTES, a_off + (uint32_t)p * A_LBO, v.x, v.y, v.z, v.w);
+            split_store4(smem, smem + A_BYTES, a_off + (uint32_t)p * 2u * SBO, v.x, v.y, v.z, v.w);
         }
 #pragma unroll
         for (int p = 0; p < B_PASSES; ++p) {
-            const int kg = b_kg0 + p * B_KSTEP;
-            const long long r = r0 + kg * 8 + rl;
+            const long long r = r0 + (b_kb0 + p * B_KSTEP) * 4 + r4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < re && b_in) v = dy4(tab, b_ch, rg[p], ry[p], a.bn.slope);
-            split_store4(smem + 2 * A_BYTES, smem + 2 * A_BYTES + B_BYTES, b_off + (uint32_t)kg * B_LBO, v.x, v.y, v.z, v.w);
+            split_store4(smem + 2 * A_BYTES, smem + 2 * A_BYTES + B_BYTES, b_off + (uint32_t)(p * B_KSTEP) * SBO, v.x, v.y, v.z, v.w);
         }
         umma::fence_smem_to_async();
         __syncthreads();
         if (tid == 0) {
             umma::fence_after_sync();
-            issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, A_LBO, sbase + 2 * A_BYTES, sbase + 2 * A_BYTES + B_BYTES,
-                        B_LBO, SBO, B_LBO, idesc, c == 0);
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j) {   // layout type 1 = SWIZZLE_128B_BASE32B
+                const uint64_t ah = umma::smem_desc(sbase + j * KSTEP_BYTES, LBO, SBO, 1);
+                const uint64_t al = umma::smem_desc(sbase + A_BYTES + j * KSTEP_BYTES, LBO, SBO, 1);
+                const uint64_t bh = umma::smem_desc(sbase + 2 * A_BYTES + j * KSTEP_BYTES, LBO, SBO, 1);
+                const uint64_t bl = umma::smem_desc(sbase + 2 * A_BYTES + B_BYTES + j * KSTEP_BYTES, LBO, SBO, 1);
+                umma::mma_tf32(tmem_d, ah, bh, idesc, !(c == 0 && j == 0));
+                umma::mma_tf32(tmem_d, al, bh, idesc, true);
+                umma::mma_tf32(tmem_d, ah, bl, idesc, true);
+            }
             umma::commit(&mma_bar);
         }
         if (c + 1 < nchunks) fetch(r0 + BK);

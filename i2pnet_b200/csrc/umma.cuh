@@ -22,11 +22,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 // cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 in [0,14), LBO >> 4 in [16,30),
 // SBO >> 4 in [32,46), version = 1 in [46,48), layout_type (swizzle) = 0 in [61,64).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 0 no swizzle, 1 SWIZZLE_128B_BASE32B (the only layout an MN-major 32-bit operand may use), 2 128B, 4 64B, 6 32B
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 0) {
     uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout_type & 7u) << 61;
     return d;
 }
 

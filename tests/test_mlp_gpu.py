@@ -75,15 +75,16 @@ def test_fused_mlp_matches_layerwise_and_f64(cfg, tensor_cores):
     # by ~10 %.  The max-norm therefore measures luck, not accuracy, and so does the plain L2 norm on
     # the small layers (one flipped row of 3712 is 2e-3 in relative L2) -- the layer-by-layer ATen
     # formulation in f32 shows the same distances to the f64 truth.  The bar: relative L2 within
-    # max(2e-3, 2 x the ATen formulation's own distance), and fewer than 0.2 % of the elements off by
-    # more than 1e-4 of the maximum.
+    # max(2e-3, 2 x the ATen formulation's own distance), and the fraction of elements off by more than
+    # 1e-4 of the maximum within max(0.2 %, 2 x the ATen formulation's).
     f, lw = res["fused"], res["layerwise"]
     report = []
 
     def check(name, g, g_lw, t):
         e, e_lw = l2(g, t), l2(g_lw, t)
-        outliers = float(((g - t).abs() > 1e-4 * t.abs().max()).float().mean())
-        ok = e < max(2e-3, 2 * e_lw) and outliers < 2e-3
+        frac = lambda a: float(((a - t).abs() > 1e-4 * t.abs().max()).float().mean())
+        outliers = frac(g)
+        ok = e < max(2e-3, 2 * e_lw) and outliers < max(2e-3, 2 * frac(g_lw))
         report.append("%s %-22s l2 %.2e (ATen formulation %.2e) outliers %.2e" % ("ok  " if ok else "FAIL", name, e, e_lw, outliers))
         return ok
 

