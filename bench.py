@@ -227,7 +227,7 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False
 
     eng = TrainStep(BATCH, N_POINTS, IMAGE_HW, device=device, seed=0, use_graph=not args.no_graph,
-                    channels_last_rgb=args.channels_last)
+                    channels_last_rgb=args.channels_last, cudnn_benchmark=args.cudnn_benchmark)
     nb = 4  # distinct batches, cycled
     host = [make_pairs(BATCH, N_POINTS, IMAGE_HW, seed=100 * rank + i) for i in range(nb)]
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
@@ -286,7 +286,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points": N_POINTS, "image": list(IMAGE_HW), "per_gpu_batch": BATCH,
-                       "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "rgb_channels_last": args.channels_last,
+                       "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "rgb_channels_last": args.channels_last, "cudnn_benchmark": args.cudnn_benchmark,
                        "l2": "256 MB flush write between steps", "tf32": False,
                        "shared_mlp": "tcgen05 3xTF32 split (f32-accurate), mask %d" % _cabi.lib().i2p_get_mlp_tensor_cores(),
                        "final_loss": loss},
@@ -309,6 +309,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--channels-last", action="store_true", help="NHWC memory format for the RGB conv stack")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="cuDNN algorithm search for the RGB convolutions")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -59,8 +59,8 @@ _SIGNATURES = {
     "i2p_rgb_bn_stats": [_int] * 4 + [_vp, _vp, _vp],
     "i2p_rgb_bn_finalize": [_int, _int, _vp, _vp, _vp, _flt, _flt, _vp, _vp, _vp, _vp, _vp, _vp],
     "i2p_rgb_bn_from_running": [_int, _vp, _vp, _flt, _vp, _vp, _vp, _vp, _vp],
-    "i2p_rgb_bn_act_pool_fwd": [_int] * 5 + [_vp, _vp, _flt, _vp, _vp, _vp],
-    "i2p_rgb_bn_act_pool_bwd": [_int] * 6 + [_vp, _vp, _flt] + [_vp] * 7,
+    "i2p_rgb_bn_act_pool_fwd": [_int] * 5 + [_vp, _vp, _flt, _vp, _vp],
+    "i2p_rgb_bn_act_pool_bwd": [_int] * 6 + [_vp, _vp, _flt] + [_vp] * 6,
     "i2p_pw_linear_bwd_dw": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 4 + [_flt, _vp, _vp],
 }
 
@@ -68,7 +68,7 @@ _SIGNATURES = {
 def exported_symbols():
     """Every entry point include/i2p_b200.h declares."""
     return sorted(list(_SIGNATURES) + ["i2p_last_error", "i2p_abi_version", "i2p_launch_count", "i2p_pw_num_tiles",
-                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out", "i2p_pw_tc_supported", "i2p_pw_pack_floats"])
+                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out", "i2p_rgb_s12_slots", "i2p_pw_tc_supported", "i2p_pw_pack_floats"])
 
 
 def lib():
@@ -94,6 +94,7 @@ def lib():
         L.i2p_pw_pack_floats.restype = _ll
         L.i2p_rgb_num_chunks.argtypes = [_int]
         L.i2p_rgb_num_chunks.restype = _int
+        L.i2p_rgb_s12_slots.restype = _int
         L.i2p_rgb_pool_out.argtypes = [_int, _int]
         L.i2p_rgb_pool_out.restype = _int
         L.i2p_set_mlp_tensor_cores.argtypes = [_int]

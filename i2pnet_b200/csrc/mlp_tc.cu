@@ -236,7 +236,7 @@ __host__ __device__ constexpr int fwd_smem_bytes() {
     return (2 * BM * BK * 4 + 2 * BN * BK * 4) > (BM * (BN + 4) * 4) ? (2 * BM * BK * 4 + 2 * BN * BK * 4) : (BM * (BN + 4) * 4);
 }
 
-template <int BN, int VEC>
+template <int BN, int VEC, int PF>   // PF: prefetch distance in chunks (1 or 2 register sets)
 __global__ void __launch_bounds__(THREADS, BN == 128 ? 3 : 4) fwd_kernel(const FwdArgs a) {
     constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
     constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, SBO = 128;
@@ -255,38 +255,37 @@ __global__ void __launch_bounds__(THREADS, BN == 128 ? 3 : 4) fwd_kernel(const F
     const bool has_tf = a.in_scale != nullptr;
     const float *wblk = a.wpack + (size_t)nt * nchunks * 2 * BN * BK;
 
-    float4 ra[4], sc4, sh4;
-    auto fetch = [&](int c) {
+    // Two register sets: the global loads of chunk c + 2 are issued as soon as chunk c has been staged, so a load
+    // has two chunk periods (staging + MMA of two chunks) to land -- one period is shorter than the DRAM latency
+    // under load (ncu: 44 % of warp time in long-scoreboard stalls with a single set).
+    float4 ra[PF][4];
+    auto fetch = [&](int c, float4 (&dst)[4]) {
         const int k = c * BK + co.kg * 4;
         const int kvalid = a.cin - k;
-        if (has_tf) {
-            sc4 = load4<4>(a.in_scale + k, kvalid >= 4 ? 4 : 0);
-            sh4 = load4<4>(a.in_shift + k, kvalid >= 4 ? 4 : 0);
-            if (kvalid > 0 && kvalid < 4) {   // cin % 4 != 0 never happens for a batch-normalised input; kept for safety
-                sc4 = load4<1>(a.in_scale + k, kvalid);
-                sh4 = load4<1>(a.in_shift + k, kvalid);
-            }
-        }
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int r = r0 + co.rbase + 32 * p;
-            ra[p] = load4<VEC>(a.x + (size_t)r * a.cin + k, r < a.rows ? kvalid : 0);
+            dst[p] = load4<VEC>(a.x + (size_t)r * a.cin + k, r < a.rows ? kvalid : 0);
         }
     };
-
-    fetch(0);
-    for (int c = 0; c < nchunks; ++c) {
+    auto stage_and_issue = [&](int c, float4 (&src)[4]) {
+        float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_tf) {   // per-channel constants of the fused input transform (L1-resident)
+            const int k = c * BK + co.kg * 4;
+            sc4 = load4<1>(a.in_scale + k, a.cin - k);
+            sh4 = load4<1>(a.in_shift + k, a.cin - k);
+        }
         if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);   // the tensor core is done with the stage
         {   // weights of this chunk: straight 16-byte copies of the packed (hi | lo) block
-            const float *src = wblk + (size_t)c * 2 * BN * BK;
+            const float *wsrc = wblk + (size_t)c * 2 * BN * BK;
             constexpr int N16 = 2 * B_BYTES / 16;
 #pragma unroll
             for (int i = 0; i < N16 / THREADS; ++i)
-                cp_async16(sbase + 2 * A_BYTES + (uint32_t)(tid + i * THREADS) * 16, src + (size_t)(tid + i * THREADS) * 4);
+                cp_async16(sbase + 2 * A_BYTES + (uint32_t)(tid + i * THREADS) * 16, wsrc + (size_t)(tid + i * THREADS) * 4);
         }
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            float4 v = ra[p];
+            float4 v = src[p];
             if (has_tf) {   // previous layer's normalise + activation; max(z, slope z) is act for 0 <= slope <= 1
                 float z;
                 z = __fmaf_rn(v.x, sc4.x, sh4.x); v.x = fmaxf(z, z * a.in_slope);
@@ -305,7 +304,24 @@ __global__ void __launch_bounds__(THREADS, BN == 128 ? 3 : 4) fwd_kernel(const F
                         B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
             umma::commit(&mma_bar);
         }
-        if (c + 1 < nchunks) fetch(c + 1);   // global loads in flight while the tensor core runs
+    };
+
+    fetch(0, ra[0]);
+    if (PF == 2) {
+        if (nchunks > 1) fetch(1, ra[PF - 1]);
+        for (int c = 0; c < nchunks; c += 2) {
+            stage_and_issue(c, ra[0]);
+            if (c + 2 < nchunks) fetch(c + 2, ra[0]);
+            if (c + 1 < nchunks) {
+                stage_and_issue(c + 1, ra[PF - 1]);
+                if (c + 3 < nchunks) fetch(c + 3, ra[PF - 1]);
+            }
+        }
+    } else {
+        for (int c = 0; c < nchunks; ++c) {
+            stage_and_issue(c, ra[0]);
+            if (c + 1 < nchunks) fetch(c + 1, ra[0]);
+        }
     }
     umma::mbar_wait(&mma_bar, (uint32_t)(nchunks - 1) & 1u);
     umma::fence_after_sync();
@@ -405,8 +421,8 @@ struct DxArgs {
 template <int BN>
 __host__ __device__ constexpr int dx_smem_bytes() { return fwd_smem_bytes<BN>() + (int)sizeof(DyTab); }
 
-template <int BN>
-__global__ void __launch_bounds__(THREADS, 3) dx_kernel(const DxArgs a) {
+template <int BN, int PF>
+__global__ void __launch_bounds__(THREADS, PF == 2 ? 2 : 3) dx_kernel(const DxArgs a) {
     constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
     constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, SBO = 128;
     constexpr int OPER = fwd_smem_bytes<BN>();
@@ -426,32 +442,30 @@ __global__ void __launch_bounds__(THREADS, 3) dx_kernel(const DxArgs a) {
     const int nchunks = a.cout / BK;
     const float *wblk = a.wpack + (size_t)nt * nchunks * 2 * BN * BK;
 
-    float4 rg[4], ry[4];
-    auto fetch = [&](int c) {
+    float4 rg[PF][4], ry[PF][4];   // PF = 2: two register sets, loads issued two chunks ahead (see the forward kernel)
+    auto fetch = [&](int c, float4 (&dg)[4], float4 (&dyv)[4]) {
         const int k = c * BK + co.kg * 4;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int r = r0 + co.rbase + 32 * p;
             const int valid = r < a.rows ? 4 : 0;
-            rg[p] = load4<4>(a.g + (size_t)r * a.cout + k, valid);
-            ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + k, valid);
+            dg[p] = load4<4>(a.g + (size_t)r * a.cout + k, valid);
+            dyv[p] = load4<4>(a.bn.y + (size_t)r * a.cout + k, valid);
         }
     };
-
-    fetch(0);
-    for (int c = 0; c < nchunks; ++c) {
+    auto stage_and_issue = [&](int c, float4 (&sg)[4], float4 (&sy)[4]) {
         if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);
         {
-            const float *src = wblk + (size_t)c * 2 * BN * BK;
+            const float *wsrc = wblk + (size_t)c * 2 * BN * BK;
             constexpr int N16 = 2 * B_BYTES / 16;
 #pragma unroll
             for (int i = 0; i < N16 / THREADS; ++i)
-                cp_async16(sbase + 2 * A_BYTES + (uint32_t)(tid + i * THREADS) * 16, src + (size_t)(tid + i * THREADS) * 4);
+                cp_async16(sbase + 2 * A_BYTES + (uint32_t)(tid + i * THREADS) * 16, wsrc + (size_t)(tid + i * THREADS) * 4);
         }
         const int ch = c * BK + co.kg * 4;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const float4 v = dy4(tab, ch, rg[p], ry[p], a.bn.slope);   // rows beyond `rows` give finite garbage: never stored
+            const float4 v = dy4(tab, ch, sg[p], sy[p], a.bn.slope);   // rows beyond `rows` give finite garbage: never stored
             split_store4(smem, smem + A_BYTES, co.soff + (uint32_t)p * 512u, v.x, v.y, v.z, v.w);
         }
         cp_async_wait_all();
@@ -463,7 +477,24 @@ __global__ void __launch_bounds__(THREADS, 3) dx_kernel(const DxArgs a) {
                         B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
             umma::commit(&mma_bar);
         }
-        if (c + 1 < nchunks) fetch(c + 1);
+    };
+
+    fetch(0, rg[0], ry[0]);
+    if (PF == 2) {
+        if (nchunks > 1) fetch(1, rg[PF - 1], ry[PF - 1]);
+        for (int c = 0; c < nchunks; c += 2) {
+            stage_and_issue(c, rg[0], ry[0]);
+            if (c + 2 < nchunks) fetch(c + 2, rg[0], ry[0]);
+            if (c + 1 < nchunks) {
+                stage_and_issue(c + 1, rg[PF - 1], ry[PF - 1]);
+                if (c + 3 < nchunks) fetch(c + 3, rg[PF - 1], ry[PF - 1]);
+            }
+        }
+    } else {
+        for (int c = 0; c < nchunks; ++c) {
+            stage_and_issue(c, rg[0], ry[0]);
+            if (c + 1 < nchunks) fetch(c + 1, rg[0], ry[0]);
+        }
     }
     umma::mbar_wait(&mma_bar, (uint32_t)(nchunks - 1) & 1u);
     umma::fence_after_sync();
@@ -672,6 +703,16 @@ static int vec_of(int ld, const void *p) {
 }
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// register prefetch distance of the forward / dX kernels: environment variable I2P_TC_PREFETCH (1 or 2), default 2
+static int prefetch_distance() {
+    static int pf = 0;
+    if (pf == 0) {
+        const char *e = getenv("I2P_TC_PREFETCH");
+        pf = (e != nullptr && atoi(e) == 1) ? 1 : 2;
+    }
+    return pf;
+}
+
 }  // namespace tc
 }  // namespace i2p
 
@@ -713,27 +754,18 @@ int i2p_pw_linear_fwd_tc(int rows, int cin, int cout, const float *x, const floa
     cudaStream_t s = as_stream(stream);
     dim3 grid(g.nt_f, ceil_div(rows, tc::BM));
     const int vec = tc::vec_of(cin, x);
-    static bool once = false;
-    if (!once) {
-        tc::allow_smem(tc::fwd_kernel<64, 4>, tc::fwd_smem_bytes<64>());
-        tc::allow_smem(tc::fwd_kernel<64, 2>, tc::fwd_smem_bytes<64>());
-        tc::allow_smem(tc::fwd_kernel<64, 1>, tc::fwd_smem_bytes<64>());
-        tc::allow_smem(tc::fwd_kernel<128, 4>, tc::fwd_smem_bytes<128>());
-        tc::allow_smem(tc::fwd_kernel<128, 2>, tc::fwd_smem_bytes<128>());
-        tc::allow_smem(tc::fwd_kernel<128, 1>, tc::fwd_smem_bytes<128>());
-        once = true;
-    }
-    if (g.bn_f == 64) {
-        constexpr int sm = tc::fwd_smem_bytes<64>();
-        if (vec == 4) tc::fwd_kernel<64, 4><<<grid, tc::THREADS, sm, s>>>(a);
-        else if (vec == 2) tc::fwd_kernel<64, 2><<<grid, tc::THREADS, sm, s>>>(a);
-        else tc::fwd_kernel<64, 1><<<grid, tc::THREADS, sm, s>>>(a);
-    } else {
-        constexpr int sm = tc::fwd_smem_bytes<128>();
-        if (vec == 4) tc::fwd_kernel<128, 4><<<grid, tc::THREADS, sm, s>>>(a);
-        else if (vec == 2) tc::fwd_kernel<128, 2><<<grid, tc::THREADS, sm, s>>>(a);
-        else tc::fwd_kernel<128, 1><<<grid, tc::THREADS, sm, s>>>(a);
-    }
+    const int pf = tc::prefetch_distance();
+#define I2P_FWD(BN_, V_, P_)                                                                              \
+    do {                                                                                                  \
+        static bool once = false;                                                                         \
+        if (!once) { tc::allow_smem(tc::fwd_kernel<BN_, V_, P_>, tc::fwd_smem_bytes<BN_>()); once = true; } \
+        tc::fwd_kernel<BN_, V_, P_><<<grid, tc::THREADS, tc::fwd_smem_bytes<BN_>(), s>>>(a);              \
+    } while (0)
+#define I2P_FWD_V(BN_, P_) do { if (vec == 4) I2P_FWD(BN_, 4, P_); else if (vec == 2) I2P_FWD(BN_, 2, P_); else I2P_FWD(BN_, 1, P_); } while (0)
+    if (g.bn_f == 64) { if (pf == 2) I2P_FWD_V(64, 2); else I2P_FWD_V(64, 1); }
+    else { if (pf == 2) I2P_FWD_V(128, 2); else I2P_FWD_V(128, 1); }
+#undef I2P_FWD_V
+#undef I2P_FWD
     return check_launch("pw_linear_fwd_tc");
 }
 
@@ -753,16 +785,18 @@ int i2p_pw_linear_bwd_dx_tc(int rows, int cin, int cout, const float *g_dense, c
     a.s12 = s12; a.wpack = wpack + g.floats_f; a.dx = dx;
     a.prev = tc::BnRef{prev_y, prev_mean, prev_rstd, prev_scale, prev_shift, prev_slope};
     a.prev_s12 = prev_s12;
-    static bool once = false;
-    if (!once) {
-        tc::allow_smem(tc::dx_kernel<64>, tc::dx_smem_bytes<64>());
-        tc::allow_smem(tc::dx_kernel<128>, tc::dx_smem_bytes<128>());
-        once = true;
-    }
     cudaStream_t s = as_stream(stream);
     dim3 grid(g.nt_x, ceil_div(rows, tc::BM));
-    if (g.bn_x == 64) tc::dx_kernel<64><<<grid, tc::THREADS, tc::dx_smem_bytes<64>(), s>>>(a);
-    else tc::dx_kernel<128><<<grid, tc::THREADS, tc::dx_smem_bytes<128>(), s>>>(a);
+    const int pf = tc::prefetch_distance();
+#define I2P_DX(BN_, P_)                                                                                \
+    do {                                                                                               \
+        static bool once = false;                                                                      \
+        if (!once) { tc::allow_smem(tc::dx_kernel<BN_, P_>, tc::dx_smem_bytes<BN_>()); once = true; }  \
+        tc::dx_kernel<BN_, P_><<<grid, tc::THREADS, tc::dx_smem_bytes<BN_>(), s>>>(a);                 \
+    } while (0)
+    if (g.bn_x == 64) { if (pf == 2) I2P_DX(64, 2); else I2P_DX(64, 1); }
+    else { if (pf == 2) I2P_DX(128, 2); else I2P_DX(128, 1); }
+#undef I2P_DX
     return check_launch("pw_linear_bwd_dx_tc");
 }
 

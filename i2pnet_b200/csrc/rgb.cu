@@ -10,18 +10,20 @@
 // Here the three ops are one pass each way over the convolution output y, parallel over
 // (chunk of a plane) x channel x sample:
 //   forward : per-chunk (count, mean, M2) -> Chan merge per channel (also updates the running
-//             statistics) -> out = maxpool(leaky(y * scale + shift)), arg-max offset kept as int8;
-//   backward: the gradient of an input position is gathered from the <= 9 pooling windows that cover
-//             it (no atomics, no zero-filled scatter target); pass 1 reduces the two batch-norm
-//             sums S1 = sum dz, S2 = sum dz * yhat, pass 2 writes dy = scale (dz - S1/n - yhat S2/n).
+//             statistics) -> out = maxpool(leaky((y - mean) * scale + beta)) from a shared-memory tile;
+//   backward: each block re-derives the arg-max of the pooling windows touching its tile and scatters
+//             their gradients in shared memory (no global atomics, no arg-max tensor, no zero-filled
+//             scatter target); pass 0 reduces the two batch-norm sums S1 = sum dz, S2 = sum dz * yhat,
+//             pass 1 writes dy = scale (dz - S1/n - yhat S2/n).
 // Neither the normalised nor the activated tensor ever exists in HBM.  Algorithmic bytes per
-// element of y: forward 4 (stats) + 4 + 5/s^2 (pool), backward 2 x (4 + 5/s^2) + 4.
+// element of y: forward 4 (stats) + 4 + 4/s^2 (pool), backward 2 x (4 + 4/s^2) + 4.
 #include <math.h>
 
 #include "common.cuh"
 
 namespace i2p {
 
+constexpr int RGB_SPREAD = 16;   // the backward sums s12 are spread over 16 slots per channel: (2 * 16, C) f64
 constexpr int RGB_CHUNK = 4096;   // elements of one (sample, channel) plane per block: 16 per thread
 constexpr int RGB_THREADS = 256;
 
@@ -77,7 +79,7 @@ __device__ __forceinline__ void chan3(float &n, float &mu, float &m2, float n2, 
     }
 }
 
-// stats (4, C) = mean, rstd, scale, shift; running statistics updated as nn.BatchNorm2d does in training
+// stats (4, C) = mean, rstd, scale = gamma * rstd, beta; running statistics updated as nn.BatchNorm2d does in training
 // (momentum, unbiased variance); s12 (2, C) f64 zeroed for the backward pass.
 __global__ void __launch_bounds__(128) rgb_bn_finalize_kernel(int C, int ntiles, const float *tile_stats,
                                                               const float *gamma, const float *beta, float eps,
@@ -104,14 +106,15 @@ __global__ void __launch_bounds__(128) rgb_bn_finalize_kernel(int C, int ntiles,
         stats[c] = mu;
         stats[C + c] = r;
         stats[2 * C + c] = g * r;
-        stats[3 * C + c] = bt - mu * g * r;
+        stats[3 * C + c] = bt;
         if (running_mean != nullptr) {
             const double unbiased = n > 1.f ? (double)m2 / ((double)n - 1.0) : var;
             running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
             running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
             if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
         }
-        if (s12 != nullptr) { s12[c] = 0.0; s12[C + c] = 0.0; }
+        if (s12 != nullptr)
+            for (int k = 0; k < 2 * RGB_SPREAD; ++k) s12[(size_t)k * C + c] = 0.0;
     }
 }
 
@@ -127,8 +130,9 @@ __global__ void rgb_bn_from_running_kernel(int C, const float *gamma, const floa
     stats[c] = mu;
     stats[C + c] = r;
     stats[2 * C + c] = g * r;
-    stats[3 * C + c] = bt - mu * g * r;
-    if (s12 != nullptr) { s12[c] = 0.0; s12[C + c] = 0.0; }
+    stats[3 * C + c] = bt;
+    if (s12 != nullptr)
+        for (int k = 0; k < 2 * RGB_SPREAD; ++k) s12[(size_t)k * C + c] = 0.0;
 }
 
 struct PoolGeom {
@@ -136,119 +140,139 @@ struct PoolGeom {
 };
 
 __device__ __forceinline__ float leaky(float z, float slope) { return z > 0.f ? z : z * slope; }
+// (y - mean) * (gamma * rstd) + beta.  Not y * scale + shift with a pre-folded shift: the raw RGB input is
+// not normalised, |mean| >> std in the first blocks, and the folded form's rounding error (relative to
+// |mean * scale|) flips several times more LeakyReLU / arg-max decisions against f64 than this one.
+__device__ __forceinline__ float norm(float y, float mean, float scale, float beta) { return __fmaf_rn(y - mean, scale, beta); }
 
-// out[b,c,ho,wo] = max over the 3x3 window of leaky(y * scale + shift); arg = kh * 3 + kw of the first maximum
-// in scan order (ATen's rule: `val > maxval || isnan(val)`).
-__global__ void __launch_bounds__(256) rgb_bn_act_pool_fwd_kernel(long long total, PoolGeom g, const float *__restrict__ y,
-                                                                  const float *__restrict__ stats, float slope,
-                                                                  float *__restrict__ out, int8_t *__restrict__ arg) {
-    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-        const int wo = (int)(e % g.Wo);
-        const long long t = e / g.Wo;
-        const int ho = (int)(t % g.Ho);
-        const long long plane = t / g.Ho;
-        const int c = (int)(plane % g.C);
-        const float sc = __ldg(stats + 2 * g.C + c), sh = __ldg(stats + 3 * g.C + c);
-        const float *p = y + (size_t)plane * g.H * g.W;
-        const int h0 = ho * g.s - 1, w0 = wo * g.s - 1;
+// ---- tiled pooling kernels ------------------------------------------------------------------------
+// One block owns a TH x TW tile of one (sample, channel) plane.  Forward: the normalised + activated
+// tile (one halo row / column) goes to shared memory once, every output takes its 3x3 maximum from
+// there.  Backward: the block rebuilds the pre-activations of its tile with a halo of two, re-derives
+// the arg-max of every pooling window that touches the tile (identical arithmetic to the forward, so
+// identical decisions: no arg-max tensor is stored) and adds that window's gradient to the arg-max
+// position in a shared-memory accumulator -- windows of neighbouring tiles that reach into this one are
+// recomputed here instead of exchanging anything between blocks.
+constexpr int RGB_TH = 16, RGB_TW = 64;
+
+// out[b,c,ho,wo] = max over the 3x3 window of leaky((y - mean) * scale + beta); first maximum in scan order wins
+// (ATen: `val > maxval || isnan(val)`), which only matters for the backward pass.
+template <int S>
+__global__ void __launch_bounds__(256) rgb_pool_fwd_kernel(PoolGeom g, const float *__restrict__ y,
+                                                          const float *__restrict__ stats, float slope,
+                                                          float *__restrict__ out) {
+    constexpr int ZH = RGB_TH + 2, ZW = RGB_TW + 2, OH = RGB_TH / S, OW = RGB_TW / S;
+    __shared__ float zt[ZH][ZW + 1];
+    const int plane = blockIdx.z, c = plane % g.C;
+    const int h0 = blockIdx.y * RGB_TH, w0 = blockIdx.x * RGB_TW;
+    const float mu = __ldg(stats + c), sc = __ldg(stats + 2 * g.C + c), bt = __ldg(stats + 3 * g.C + c);
+    const float *p = y + (size_t)plane * g.H * g.W;
+    for (int idx = threadIdx.x; idx < ZH * ZW; idx += 256) {
+        const int hh = idx / ZW, ww = idx - hh * ZW;
+        const int h = h0 - 1 + hh, w = w0 - 1 + ww;
+        zt[hh][ww] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? leaky(norm(__ldg(p + (size_t)h * g.W + w), mu, sc, bt), slope)
+                                                           : -INFINITY;
+    }
+    __syncthreads();
+    const int ho0 = h0 / S, wo0 = w0 / S;
+    float *o = out + (size_t)plane * g.Ho * g.Wo;
+    for (int idx = threadIdx.x; idx < OH * OW; idx += 256) {
+        const int oh = idx / OW, ow = idx - oh * OW;
+        if (ho0 + oh >= g.Ho || wo0 + ow >= g.Wo) continue;
         float best = -INFINITY;
-        int bi = -1;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int h = h0 + kh;
-            if (h < 0 || h >= g.H) continue;
+        for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-                const int w = w0 + kw;
-                if (w < 0 || w >= g.W) continue;
-                const float v = leaky(__fmaf_rn(__ldg(p + (size_t)h * g.W + w), sc, sh), slope);
-                if (bi < 0 || v > best || isnan(v)) { best = v; bi = kh * 3 + kw; }
+                const float v = zt[oh * S + kh][ow * S + kw];
+                if (v > best || isnan(v)) best = v;
             }
-        }
-        out[e] = best;
-        arg[e] = (int8_t)bi;
+        o[(size_t)(ho0 + oh) * g.Wo + wo0 + ow] = best;
     }
 }
 
-// Gradient w.r.t. the activated value at (h, w) of one plane: the sum of dout over the windows whose
-// arg-max is this position.
-__device__ __forceinline__ float pooled_grad(const PoolGeom &g, int h, int w, const float *__restrict__ dout,
-                                             const int8_t *__restrict__ arg) {
-    const int ho_lo = h >= 1 ? (h + g.s - 2) / g.s : 0, ho_hi = min(g.Ho - 1, (h + 1) / g.s);
-    const int wo_lo = w >= 1 ? (w + g.s - 2) / g.s : 0, wo_hi = min(g.Wo - 1, (w + 1) / g.s);
-    float acc = 0.f;
-    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
-        const int kh = h - (ho * g.s - 1);
-        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-            const int kw = w - (wo * g.s - 1);
-            const int o = ho * g.Wo + wo;
-            if (__ldg(arg + o) == kh * 3 + kw) acc += __ldg(dout + o);
-        }
-    }
-    return acc;
-}
-
-// s12[0][c] += sum dz, s12[1][c] += sum dz * yhat over one chunk of one plane (dz = pooled gradient * act')
-__global__ void __launch_bounds__(RGB_THREADS) rgb_bwd_reduce_kernel(PoolGeom g, const float *__restrict__ y,
-                                                                     const float *__restrict__ stats, float slope,
-                                                                     const float *__restrict__ dout,
-                                                                     const int8_t *__restrict__ arg, double *s12) {
+// PASS 0: s12[slot][0][c] += sum dz, s12[slot][1][c] += sum dz * yhat over the tile (dz = pooled gradient * act').
+// PASS 1: dy = scale * (dz - S1/n - yhat * S2/n) (batch statistics) or scale * dz (running statistics);
+//         the blocks of tile (0, 0) of sample 0 also emit dgamma = S2, dbeta = S1 in f32.
+template <int S, int PASS>
+__global__ void __launch_bounds__(256) rgb_pool_bwd_kernel(PoolGeom g, int batch_stats, double inv_n,
+                                                          const float *__restrict__ y, const float *__restrict__ stats,
+                                                          float slope, const float *__restrict__ dout, double *s12,
+                                                          float *__restrict__ dy, float *dgamma, float *dbeta) {
+    constexpr int ZH = RGB_TH + 4, ZW = RGB_TW + 4;
+    constexpr int NWH = RGB_TH / S + (S == 1 ? 2 : 1), NWW = RGB_TW / S + (S == 1 ? 2 : 1);   // windows touching the tile
+    __shared__ float zt[ZH][ZW + 1];          // pre-activation z, origin (h0 - 2, w0 - 2), -inf outside the plane
+    __shared__ float dzt[RGB_TH][RGB_TW];     // gradient w.r.t. the activated value
     __shared__ float red[RGB_THREADS / 32];
-    const int chunk = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
-    const int HW = g.H * g.W;
-    const int start = chunk * RGB_CHUNK, stop = min(HW, start + RGB_CHUNK);
-    const size_t plane = (size_t)b * g.C + c;
-    const float *p = y + plane * HW;
-    const float *dp = dout + plane * g.Ho * g.Wo;
-    const int8_t *ap = arg + plane * g.Ho * g.Wo;
+    __shared__ float sums[2];
+    const int plane = blockIdx.z, c = plane % g.C;
+    const int h0 = blockIdx.y * RGB_TH, w0 = blockIdx.x * RGB_TW;
     const float mu = __ldg(stats + c), rs = __ldg(stats + g.C + c), sc = __ldg(stats + 2 * g.C + c),
-                sh = __ldg(stats + 3 * g.C + c);
+                bt = __ldg(stats + 3 * g.C + c);
+    const float *p = y + (size_t)plane * g.H * g.W;
+    if (PASS == 1 && threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int k = 0; k < RGB_SPREAD; ++k) { t1 += s12[(size_t)(2 * k) * g.C + c]; t2 += s12[(size_t)(2 * k + 1) * g.C + c]; }
+        sums[0] = (float)(t1 * inv_n);
+        sums[1] = (float)(t2 * inv_n);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && plane < g.C) {
+            if (dbeta != nullptr) dbeta[c] = (float)t1;
+            if (dgamma != nullptr) dgamma[c] = (float)t2;
+        }
+    }
+    for (int idx = threadIdx.x; idx < ZH * ZW; idx += 256) {
+        const int hh = idx / ZW, ww = idx - hh * ZW;
+        const int h = h0 - 2 + hh, w = w0 - 2 + ww;
+        zt[hh][ww] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? norm(__ldg(p + (size_t)h * g.W + w), mu, sc, bt) : -INFINITY;
+    }
+    for (int idx = threadIdx.x; idx < RGB_TH * RGB_TW; idx += 256) (&dzt[0][0])[idx] = 0.f;
+    __syncthreads();
+    // every pooling window that overlaps the tile: window (i, j) is output (ho_first + i, wo_first + j) and its
+    // top-left input element sits at tile coordinates (S == 1 ? i : 2 i + 1, ...)
+    const int ho_first = S == 1 ? h0 - 1 : h0 / 2, wo_first = S == 1 ? w0 - 1 : w0 / 2;
+    const float *dp = dout + (size_t)plane * g.Ho * g.Wo;
+    for (int idx = threadIdx.x; idx < NWH * NWW; idx += 256) {
+        const int i = idx / NWW, j = idx - i * NWW;
+        const int ho = ho_first + i, wo = wo_first + j;
+        if (ho < 0 || ho >= g.Ho || wo < 0 || wo >= g.Wo) continue;
+        const int th = S == 1 ? i : 2 * i + 1, tw = S == 1 ? j : 2 * j + 1;
+        float best = -INFINITY;
+        int bh = 0, bw = 0;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float zr = zt[th + kh][tw + kw];
+                if (zr == -INFINITY) continue;          // outside the plane (padding never wins, also for slope 0)
+                const float v = leaky(zr, slope);
+                if (v > best || isnan(v)) { best = v; bh = kh; bw = kw; }
+            }
+        const int r = th + bh - 2, cc = tw + bw - 2;   // arg-max position in core-tile coordinates
+        if (r >= 0 && r < RGB_TH && cc >= 0 && cc < RGB_TW) atomicAdd(&dzt[r][cc], __ldg(dp + (size_t)ho * g.Wo + wo));
+    }
+    __syncthreads();
     float s1 = 0.f, s2 = 0.f;
-    for (int i = start + threadIdx.x; i < stop; i += RGB_THREADS) {
-        const int h = i / g.W, w = i - h * g.W;
-        const float gsum = pooled_grad(g, h, w, dp, ap);
-        const float yv = __ldg(p + i);
-        const float dz = gsum * (__fmaf_rn(yv, sc, sh) > 0.f ? 1.f : slope);
-        s1 += dz;
-        s2 += dz * ((yv - mu) * rs);
-    }
-    s1 = block_sum(s1, red);
-    s2 = block_sum(s2, red);
-    if (threadIdx.x == 0) {
-        atomicAdd(s12 + c, (double)s1);
-        atomicAdd(s12 + g.C + c, (double)s2);
-    }
-}
-
-// dy = scale * (dz - S1/n - yhat * S2/n)   (batch statistics)   or   scale * dz   (running statistics);
-// the first block also emits dgamma = S2, dbeta = S1 in f32.
-__global__ void __launch_bounds__(256) rgb_bwd_dx_kernel(long long total, PoolGeom g, int batch_stats, double inv_n,
-                                                         const float *__restrict__ y, const float *__restrict__ stats,
-                                                         float slope, const float *__restrict__ dout,
-                                                         const int8_t *__restrict__ arg, const double *__restrict__ s12,
-                                                         float *__restrict__ dy, float *dgamma, float *dbeta) {
-    if (blockIdx.x == 0) {
-        for (int c = threadIdx.x; c < g.C; c += 256) {
-            if (dbeta != nullptr) dbeta[c] = (float)s12[c];
-            if (dgamma != nullptr) dgamma[c] = (float)s12[g.C + c];
+    for (int idx = threadIdx.x; idx < RGB_TH * RGB_TW; idx += 256) {
+        const int r = idx / RGB_TW, cc = idx - r * RGB_TW;
+        const int h = h0 + r, w = w0 + cc;
+        if (h >= g.H || w >= g.W) continue;
+        const float dz = dzt[r][cc] * (zt[r + 2][cc + 2] > 0.f ? 1.f : slope);
+        const float yhat = (__ldg(p + (size_t)h * g.W + w) - mu) * rs;
+        if (PASS == 0) {
+            s1 += dz;
+            s2 += dz * yhat;
+        } else {
+            dy[(size_t)plane * g.H * g.W + (size_t)h * g.W + w] = batch_stats ? sc * (dz - sums[0] - yhat * sums[1]) : sc * dz;
         }
     }
-    const int HW = g.H * g.W;
-    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-        const int i = (int)(e % HW);
-        const long long plane = e / HW;
-        const int c = (int)(plane % g.C);
-        const int h = i / g.W, w = i - h * g.W;
-        const float gsum = pooled_grad(g, h, w, dout + (size_t)plane * g.Ho * g.Wo, arg + (size_t)plane * g.Ho * g.Wo);
-        const float yv = __ldg(y + e);
-        const float sc = __ldg(stats + 2 * g.C + c), sh = __ldg(stats + 3 * g.C + c);
-        float dz = gsum * (__fmaf_rn(yv, sc, sh) > 0.f ? 1.f : slope);
-        if (batch_stats) {
-            const float mu = __ldg(stats + c), rs = __ldg(stats + g.C + c);
-            const float s1n = (float)(s12[c] * inv_n), s2n = (float)(s12[g.C + c] * inv_n);
-            dz = dz - s1n - ((yv - mu) * rs) * s2n;
+    if (PASS == 0) {
+        s1 = block_sum(s1, red);
+        s2 = block_sum(s2, red);
+        if (threadIdx.x == 0) {
+            const int slot = (blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z) % RGB_SPREAD;
+            atomicAdd(s12 + (size_t)(2 * slot) * g.C + c, (double)s1);
+            atomicAdd(s12 + (size_t)(2 * slot + 1) * g.C + c, (double)s2);
         }
-        dy[e] = sc * dz;
     }
 }
 
@@ -258,11 +282,6 @@ static bool pool_geom(PoolGeom &g, int C, int H, int W, int stride) {
     g.C = C; g.H = H; g.W = W; g.s = stride;
     g.Ho = pool_out(H, stride); g.Wo = pool_out(W, stride);
     return C >= 1 && H >= 1 && W >= 1 && (stride == 1 || stride == 2);
-}
-
-static int grid_for(long long total) {
-    const long long g = (total + 255) / 256;
-    return (int)(g < 148 * 32 ? g : 148 * 32);
 }
 
 }  // namespace i2p
@@ -300,31 +319,36 @@ int i2p_rgb_bn_from_running(int C, const float *gamma, const float *beta, float 
     return check_launch("rgb_bn_from_running");
 }
 
+int i2p_rgb_s12_slots(void) { return 2 * i2p::RGB_SPREAD; }
+
 int i2p_rgb_bn_act_pool_fwd(int B, int C, int H, int W, int stride, const float *y, const float *stats, float slope,
-                            float *out, int8_t *arg, void *stream) {
+                            float *out, void *stream) {
     using namespace i2p;
     PoolGeom g;
-    I2P_REQUIRE(pool_geom(g, C, H, W, stride) && B >= 1, "rgb_bn_act_pool_fwd: bad sizes (stride must be 1 or 2)");
-    const long long total = (long long)B * C * g.Ho * g.Wo;
-    rgb_bn_act_pool_fwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(total, g, y, stats, slope, out, arg);
+    I2P_REQUIRE(pool_geom(g, C, H, W, stride) && B >= 1 && (long long)B * C <= 65535,
+                "rgb_bn_act_pool_fwd: bad sizes (stride must be 1 or 2, B * C <= 65535)");
+    dim3 grid(ceil_div(W, RGB_TW), ceil_div(H, RGB_TH), B * C);
+    if (stride == 1) rgb_pool_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(g, y, stats, slope, out);
+    else rgb_pool_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(g, y, stats, slope, out);
     return check_launch("rgb_bn_act_pool_fwd");
 }
 
 int i2p_rgb_bn_act_pool_bwd(int B, int C, int H, int W, int stride, int batch_stats, const float *y, const float *stats,
-                            float slope, const float *dout, const int8_t *arg, double *s12, float *dy, float *dgamma,
-                            float *dbeta, void *stream) {
+                            float slope, const float *dout, double *s12, float *dy, float *dgamma, float *dbeta,
+                            void *stream) {
     using namespace i2p;
     PoolGeom g;
-    I2P_REQUIRE(pool_geom(g, C, H, W, stride) && B >= 1 && B <= 65535 && C <= 65535,
-                "rgb_bn_act_pool_bwd: bad sizes (stride must be 1 or 2)");
-    const int HW = H * W;
-    dim3 grid(ceil_div(HW, RGB_CHUNK), C, B);
-    rgb_bwd_reduce_kernel<<<grid, RGB_THREADS, 0, as_stream(stream)>>>(g, y, stats, slope, dout, arg, s12);
-    int rc = check_launch("rgb_bwd_reduce");
+    I2P_REQUIRE(pool_geom(g, C, H, W, stride) && B >= 1 && (long long)B * C <= 65535,
+                "rgb_bn_act_pool_bwd: bad sizes (stride must be 1 or 2, B * C <= 65535)");
+    dim3 grid(ceil_div(W, RGB_TW), ceil_div(H, RGB_TH), B * C);
+    const double inv_n = 1.0 / (double)((long long)B * H * W);
+    cudaStream_t s = as_stream(stream);
+    if (stride == 1) rgb_pool_bwd_kernel<1, 0><<<grid, 256, 0, s>>>(g, batch_stats, inv_n, y, stats, slope, dout, s12, dy, dgamma, dbeta);
+    else rgb_pool_bwd_kernel<2, 0><<<grid, 256, 0, s>>>(g, batch_stats, inv_n, y, stats, slope, dout, s12, dy, dgamma, dbeta);
+    int rc = check_launch("rgb_pool_bwd(reduce)");
     if (rc != I2P_OK) return rc;
-    const long long total = (long long)B * C * HW;
-    rgb_bwd_dx_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(total, g, batch_stats, 1.0 / (double)((long long)B * HW),
-                                                                      y, stats, slope, dout, arg, s12, dy, dgamma, dbeta);
-    return check_launch("rgb_bwd_dx");
+    if (stride == 1) rgb_pool_bwd_kernel<1, 1><<<grid, 256, 0, s>>>(g, batch_stats, inv_n, y, stats, slope, dout, s12, dy, dgamma, dbeta);
+    else rgb_pool_bwd_kernel<2, 1><<<grid, 256, 0, s>>>(g, batch_stats, inv_n, y, stats, slope, dout, s12, dy, dgamma, dbeta);
+    return check_launch("rgb_pool_bwd(dx)");
 }
 }

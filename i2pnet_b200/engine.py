@@ -78,9 +78,12 @@ class FlatGradBucket:
 
 class TrainStep:
     def __init__(self, batch, n_points=20480, image_hw=(160, 512), cfg=I2PNetConfig, device="cuda:0", seed=0,
-                 use_graph=True, lr=1e-3, weight_decay=1e-4, clip=10.0, group=None, channels_last_rgb=False):
+                 use_graph=True, lr=1e-3, weight_decay=1e-4, clip=10.0, group=None, channels_last_rgb=False,
+                 cudnn_benchmark=False):
         self.device = torch.device(device)
         self.cfg, self.batch, self.clip, self.group, self.use_graph = cfg, batch, clip, group, use_graph
+        if cudnn_benchmark:   # let cuDNN time its f32 algorithms for the 15 convolutions during the eager warm-up
+            torch.backends.cudnn.benchmark = True
         torch.manual_seed(seed)
         self.model = RegNet_v2(cfg=cfg).to(self.device)
         self.model.train()

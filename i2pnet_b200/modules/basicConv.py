@@ -15,7 +15,7 @@ USE_FUSED_RGB_TAIL = True   # False: nn.BatchNorm2d -> nn.LeakyReLU -> nn.MaxPoo
 class _BlockTail(Function):
     """BatchNorm2d -> LeakyReLU -> MaxPool2d(3, stride, 1) of one pyramid block on the kernels of
     csrc/rgb.cu: one statistics pass + one pooled write forward, one reduction + one write backward,
-    nothing but the convolution output y and an int8 arg-max kept for backward."""
+    nothing but the convolution output y kept for backward (the pooling arg-max is re-derived from it)."""
 
     @staticmethod
     def forward(ctx, y, gamma, beta, bn, slope, stride):
@@ -24,7 +24,7 @@ class _BlockTail(Function):
         L = _cabi.lib()
         Ho, Wo = L.i2p_rgb_pool_out(H, stride), L.i2p_rgb_pool_out(W, stride)
         stats = torch.empty(4, C, dtype=f32, device=dev)
-        s12 = torch.empty(2, C, dtype=torch.float64, device=dev)
+        s12 = torch.empty(L.i2p_rgb_s12_slots(), C, dtype=torch.float64, device=dev)
         batch_stats = bn.training or not bn.track_running_stats
         yp = _ptr(y, f32, "conv output", dev)
         if batch_stats:
@@ -40,17 +40,15 @@ class _BlockTail(Function):
             call("i2p_rgb_bn_from_running", dev, C, _ptr(gamma, f32, "bn weight", dev), _ptr(beta, f32, "bn bias", dev),
                  float(bn.eps), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), stats.data_ptr(), s12.data_ptr())
         out = torch.empty(B, C, Ho, Wo, dtype=f32, device=dev)
-        arg = torch.empty(B, C, Ho, Wo, dtype=torch.int8, device=dev)
-        call("i2p_rgb_bn_act_pool_fwd", dev, B, C, H, W, stride, yp, stats.data_ptr(), float(slope), out.data_ptr(),
-             arg.data_ptr())
-        ctx.save_for_backward(y, stats, arg, s12)
+        call("i2p_rgb_bn_act_pool_fwd", dev, B, C, H, W, stride, yp, stats.data_ptr(), float(slope), out.data_ptr())
+        ctx.save_for_backward(y, stats, s12)
         ctx.meta = (stride, float(slope), bool(batch_stats))
         ctx.used = False
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        y, stats, arg, s12 = ctx.saved_tensors
+        y, stats, s12 = ctx.saved_tensors
         stride, slope, batch_stats = ctx.meta
         dev = y.device
         B, C, H, W = y.shape
@@ -61,7 +59,7 @@ class _BlockTail(Function):
         dy = torch.empty_like(y)
         dgb = torch.empty(2, C, dtype=f32, device=dev)
         call("i2p_rgb_bn_act_pool_bwd", dev, B, C, H, W, stride, int(batch_stats), y.data_ptr(), stats.data_ptr(), slope,
-             _ptr(dout, f32, "grad_output", dev), arg.data_ptr(), s12.data_ptr(), dy.data_ptr(), dgb[0].data_ptr(),
+             _ptr(dout, f32, "grad_output", dev), s12.data_ptr(), dy.data_ptr(), dgb[0].data_ptr(),
              dgb[1].data_ptr())
         return dy, dgb[0], dgb[1], None, None, None
 

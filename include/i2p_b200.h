@@ -203,7 +203,7 @@ int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, c
 /* ---- RGB feature-pyramid block tail: replaces BatchNorm2d -> LeakyReLU(0.1) -> MaxPool2d(3, stride, 1)
  * of src/modules/basicConv.py:11-17 on the NCHW f32 output y (B,C,H,W) of the block's convolution.
  * Neither the normalised nor the activated tensor is materialised; backward gathers through the
- * pooling windows (no atomics).  stats (4,C) = mean, rstd, scale = gamma*rstd, shift = beta - mean*scale. */
+ * pooling windows (no atomics).  stats (4,C) = mean, rstd, scale = gamma*rstd, beta; z = (y-mean)*scale+beta. */
 
 /* chunks of one (sample, channel) plane the statistics pass splits into; pooled extent (n+2-3)/stride+1 */
 int i2p_rgb_num_chunks(int hw);
@@ -211,21 +211,24 @@ int i2p_rgb_pool_out(int n, int stride);
 /* tile_stats (C, B*chunks, 3) = (count, mean, M2) per chunk */
 int i2p_rgb_bn_stats(int B, int C, int H, int W, const float *y, float *tile_stats, void *stream);
 /* Chan merge -> stats; running_mean/var (may be NULL) updated with `momentum` and the unbiased variance,
- * *num_batches_tracked += 1 (nn.BatchNorm2d in training); s12 (2,C) f64 (may be NULL) zeroed for backward. */
+ * *num_batches_tracked += 1 (nn.BatchNorm2d in training); s12 (i2p_rgb_s12_slots(),C) f64 (may be NULL) zeroed. */
 int i2p_rgb_bn_finalize(int C, int ntiles, const float *tile_stats, const float *gamma, const float *beta, float eps,
                         float momentum, float *running_mean, float *running_var, long long *num_batches_tracked,
                         float *stats, double *s12, void *stream);
 /* eval mode: stats from the running statistics */
 int i2p_rgb_bn_from_running(int C, const float *gamma, const float *beta, float eps, const float *running_mean,
                             const float *running_var, float *stats, double *s12, void *stream);
-/* out (B,C,Ho,Wo) = maxpool3x3(leaky(y*scale+shift)), arg (B,C,Ho,Wo) int8 = kh*3+kw of the first maximum */
+/* out (B,C,Ho,Wo) = maxpool3x3(leaky((y-mean)*scale+beta)); ties: first maximum in scan order, like ATen */
 int i2p_rgb_bn_act_pool_fwd(int B, int C, int H, int W, int stride, const float *y, const float *stats, float slope,
-                            float *out, int8_t *arg, void *stream);
-/* dout (B,C,Ho,Wo) -> dy (B,C,H,W), dgamma (C), dbeta (C); s12 (2,C) f64 zeroed by the forward finalize.
+                            float *out, void *stream);
+/* number of (C)-rows of the f64 s12 buffer the finalize kernels zero and the backward accumulates into */
+int i2p_rgb_s12_slots(void);
+/* dout (B,C,Ho,Wo) -> dy (B,C,H,W), dgamma (C), dbeta (C); the pooling arg-max is re-derived from y (no saved
+ * indices); s12 (i2p_rgb_s12_slots(), C) f64 zeroed by the forward finalize.
  * batch_stats = 1: full batch-norm backward; 0: running statistics (dy = scale * dz). */
 int i2p_rgb_bn_act_pool_bwd(int B, int C, int H, int W, int stride, int batch_stats, const float *y, const float *stats,
-                            float slope, const float *dout, const int8_t *arg, double *s12, float *dy, float *dgamma,
-                            float *dbeta, void *stream);
+                            float slope, const float *dout, double *s12, float *dy, float *dgamma, float *dbeta,
+                            void *stream);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,45 @@ def mlp_micro(dev):
     torch.cuda.profiler.stop()
 
 
+def marked_step(eng, out_json):
+    """One eager step with a marker kernel (torch.cuda._sleep -> `spin_kernel`) launched at every top-level module
+    boundary, forward and backward; the labels, in launch order, go to `out_json`.  tools/summarise_ncu.py zips them
+    with the spin_kernel launches of the ncu launch list to attribute device time to modules."""
+    import json
+    labels = []
+
+    def mark(label):
+        labels.append(label)
+        torch.cuda._sleep(1)
+
+    handles = []
+    for name, m in eng.model.named_children():
+        handles.append(m.register_forward_pre_hook(lambda mod, inp, n=name: mark("fwd " + n)))
+        handles.append(m.register_forward_hook(lambda mod, inp, out, n=name: mark("fwd (assembly)")))
+        handles.append(m.register_full_backward_pre_hook(lambda mod, g, n=name: mark("bwd " + n)))
+        handles.append(m.register_full_backward_hook(lambda mod, gi, go, n=name: mark("bwd (assembly)")))
+    mark("step prologue")
+    x = eng.inputs
+    eng.bucket.release()
+    out3, out4, _, _, sx, sq = eng.model(x["rgb"], x["lidar"], x["raw_point_xyz"], None, x["intrinsic"], None, None, None,
+                                         x["lidar_feats"], eng.cfg)
+    mark("loss")
+    from i2pnet_b200.compute_loss import Get_loss
+    loss, _, _ = Get_loss(out3, out4, x["q_gt"], x["t_gt"], sx, sq, eng.cfg)
+    mark("bwd (assembly)")
+    loss.backward()
+    mark("gather + clip + adam")
+    eng.bucket.gather()
+    eng.bucket.all_reduce_mean(eng.group)
+    eng.bucket.clip_(eng.clip)
+    eng.opt.step()
+    mark("end")
+    for h in handles:
+        h.remove()
+    with open(out_json, "w") as fh:
+        json.dump(labels, fh)
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "step"
     dev = torch.device("cuda:0")
@@ -57,6 +96,8 @@ def main():
     torch.cuda.profiler.start()
     if what == "step":
         eng._step_body()
+    elif what == "marked":
+        marked_step(eng, sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/markers.json")
     else:  # forward only
         with torch.no_grad():
             x = eng.inputs

@@ -14,7 +14,7 @@ import re
 import sys
 from collections import OrderedDict
 
-OWN = ("i2p::",)
+OWN = ("i2p::", "tc::")
 
 
 def _rows(path):
@@ -57,6 +57,37 @@ def launches(src, dst):
     print("wrote", dst)
 
 
+def modules(src, labels_json, dst):
+    """Per-module device time: the launch list of `profile_step.py marked` + its marker labels."""
+    import json
+    labels = json.load(open(labels_json))
+    rows = [r for r in _rows(src) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    agg, cur, k = OrderedDict(), "before first marker", 0
+    total = 0.0
+    for r in rows:
+        name = r["Kernel Name"]
+        if "spin_kernel" in name:
+            cur = labels[k] if k < len(labels) else "after last marker"
+            k += 1
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "ns")
+        us = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
+        own = any(o in name for o in OWN)
+        a = agg.setdefault(cur, [0, 0.0, 0, 0.0])
+        a[0] += 1; a[1] += us
+        if own:
+            a[2] += 1; a[3] += us
+        total += us
+    with open(dst, "w") as out:
+        out.write("# device time per top-level module (ncu launch list + module-boundary markers): %s\n\n" % src)
+        out.write("%d markers matched of %d labels; %.1f us serialised\n\n" % (k, len(labels), total))
+        out.write("| share | total us | launches | own us | own launches | segment |\n|---:|---:|---:|---:|---:|---|\n")
+        for seg, (n, us, no, uso) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            out.write("| %.1f %% | %.1f | %d | %.1f | %d | %s |\n" % (100 * us / total, us, n, uso, no, seg))
+    print("wrote", dst)
+
+
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
@@ -93,4 +124,4 @@ def raw(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "raw": raw, "modules": modules}[sys.argv[1]](*sys.argv[2:])
