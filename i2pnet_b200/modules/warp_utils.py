@@ -2,6 +2,45 @@
 :78).  Device-agnostic: the reference hard-codes `.cuda()` on its constant tensors (:5,:18-19),
 which pins everything to the current device."""
 import torch
+from torch.autograd import Function
+
+USE_FUSED_QUAT = True   # False: the reference's component-wise formulation through ATen
+
+
+class _QuatMul(Function):
+    """c = a (x) b on (B,1|N,4) f32 CUDA tensors: one launch of csrc/quat.cu; backward is the same kernel twice."""
+
+    @staticmethod
+    def _launch(a, b, conj_a, conj_b):
+        from .. import _cabi
+        B, N = a.shape[0], max(a.shape[1], b.shape[1])
+        a = a if a.data_ptr() % 16 == 0 else a.clone()      # the kernel moves quaternions as 128-bit words
+        b = b if b.data_ptr() % 16 == 0 else b.clone()
+        out = torch.empty(B, N, 4, dtype=torch.float32, device=a.device)
+        _cabi.call("i2p_quat_mul", a.device, B, N, a.shape[1], b.shape[1], int(conj_a), int(conj_b),
+                   _cabi._ptr(a, torch.float32, "q_a"), _cabi._ptr(b, torch.float32, "q_b", a.device), out.data_ptr())
+        return out
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        ctx.save_for_backward(a, b)
+        return _QuatMul._launch(a, b, False, False)
+
+    @staticmethod
+    def backward(ctx, dc):
+        a, b = ctx.saved_tensors
+        dc = dc.contiguous()
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = _QuatMul._launch(dc, b, False, True)           # dc (x) conj(b)
+            if a.shape[1] == 1 and da.shape[1] != 1:
+                da = da.sum(dim=1, keepdim=True)
+        if ctx.needs_input_grad[1]:
+            db = _QuatMul._launch(a, dc, True, False)           # conj(a) (x) dc
+            if b.shape[1] == 1 and db.shape[1] != 1:
+                db = db.sum(dim=1, keepdim=True)
+        return da, db
 
 
 def inv_q(q):
@@ -17,6 +56,10 @@ def mul_q(q_a, q_b):
         q_a = q_a.unsqueeze(1)
     if q_b.ndim == 2:
         q_b = q_b.unsqueeze(1)
+    if (USE_FUSED_QUAT and q_a.is_cuda and q_a.dtype == torch.float32 and q_b.dtype == torch.float32
+            and q_a.ndim == 3 and q_b.ndim == 3 and q_a.shape[0] == q_b.shape[0]
+            and (q_a.shape[1] == q_b.shape[1] or 1 in (q_a.shape[1], q_b.shape[1]))):
+        return _QuatMul.apply(q_a, q_b)
     a0, a1, a2, a3 = q_a.unbind(-1)
     b0, b1, b2, b3 = q_b.unbind(-1)
     return torch.stack([a0 * b0 - a1 * b1 - a2 * b2 - a3 * b3,

@@ -230,6 +230,12 @@ int i2p_rgb_bn_act_pool_bwd(int B, int C, int H, int W, int stride, int batch_st
                             float slope, const float *dout, double *s12, float *dy, float *dgamma, float *dbeta,
                             void *stream);
 
+/* ---- quaternion product: replaces mul_q of src/modules/warp_utils.py:25-60 (one launch instead of ~30) ----
+ * out (B,N,4) = A (x) B with A = a (B,na,4), B = b (B,nb,4), na / nb in {1, N} (broadcast over points),
+ * either operand optionally conjugated (the backward pass is da = dc (x) conj(b), db = conj(a) (x) dc). */
+int i2p_quat_mul(int B, int N, int na, int nb, int conj_a, int conj_b, const float *a, const float *b, float *out,
+                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif
