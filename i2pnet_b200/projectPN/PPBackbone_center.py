@@ -247,6 +247,97 @@ class ProjSetUpconvModule(nn.Module):
             conv.set_bn()
 
 
+USE_FUSED_CV = True   # False: the reference's broadcast / mask / concatenate / softmax formulation through ATen
+
+
+class _CvBuild(torch.autograd.Function):
+    """First-layer operand of the cost volume (csrc/cv.cu cv_build): X (B,N,K,6+C[+C]) and the 6 coordinate
+    channels alone, from xyz1 (B,N,3), xyz2 (B,N2,3), pi (B,N,C), qi (B,N2,C), maxc (B,N2,C) | None,
+    idx (B,N,K) int32 | None (None: K == N2, every point sees every pixel)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, pi, qi, maxc, idx):
+        from .. import _cabi
+        f32, dev = torch.float32, pi.device
+        xyz1, xyz2, pi, qi = xyz1.contiguous(), xyz2.contiguous(), pi.contiguous(), qi.contiguous()
+        maxc = maxc.contiguous() if maxc is not None else None
+        B, N, C = pi.shape
+        N2 = qi.shape[1]
+        K = idx.shape[2] if idx is not None else N2
+        Cx = 6 + C + (C if maxc is not None else 0)
+        X = torch.empty(B, N, K, Cx, dtype=f32, device=dev)
+        xyz6 = torch.empty(B, N, K, 6, dtype=f32, device=dev)
+        _cabi.call("i2p_cv_build", dev, B, N, K, N2, C, _cabi._ptr(xyz1, f32, "xyz1", dev), _cabi._ptr(xyz2, f32, "xyz2", dev),
+                   _cabi._ptr(pi, f32, "pi", dev), _cabi._ptr(qi, f32, "qi", dev),
+                   _cabi._ptr(maxc, f32, "maxc", dev) if maxc is not None else None,
+                   _cabi._ptr(idx, torch.int32, "idx", dev) if idx is not None else None, X.data_ptr(), xyz6.data_ptr())
+        ctx.save_for_backward(pi, qi, idx if idx is not None else torch.empty(0, device=dev))
+        ctx.meta = (B, N, K, N2, C, maxc is not None, idx is not None)
+        return X, xyz6
+
+    @staticmethod
+    def backward(ctx, dX, dxyz6):
+        from .. import _cabi
+        pi, qi, idx = ctx.saved_tensors
+        B, N, K, N2, C, has_max, has_idx = ctx.meta
+        f32, dev = torch.float32, pi.device
+        dX = dX.contiguous()
+        dxyz6 = dxyz6.contiguous() if dxyz6 is not None else None
+        dxyz1 = torch.empty(B, N, 3, dtype=f32, device=dev)
+        dpi = torch.empty(B, N, C, dtype=f32, device=dev)
+        acc = torch.zeros(B, N2, 3 + C + (C if has_max else 0), dtype=f32, device=dev)   # one fill for the three atomics targets
+        # the kernel addresses the three accumulators as separate dense tensors: carve them out of one zeroed buffer
+        flat = acc.view(-1)
+        dxyz2 = flat[:B * N2 * 3].view(B, N2, 3)
+        dqi = flat[B * N2 * 3:B * N2 * (3 + C)].view(B, N2, C)
+        dmaxc = flat[B * N2 * (3 + C):].view(B, N2, C) if has_max else None
+        _cabi.call("i2p_cv_build_bwd", dev, B, N, K, N2, C, int(has_max), _cabi._ptr(dX, f32, "dX", dev),
+                   _cabi._ptr(dxyz6, f32, "dxyz6", dev) if dxyz6 is not None else None, pi.data_ptr(), qi.data_ptr(),
+                   idx.data_ptr() if has_idx else None, dxyz1.data_ptr(), dxyz2.data_ptr(), dpi.data_ptr(), dqi.data_ptr(),
+                   dmaxc.data_ptr() if has_max else None)
+        return dxyz1, dxyz2, dpi, dqi, dmaxc, None
+
+
+class _SoftmaxWSum(torch.autograd.Function):
+    """sum_k softmax_k(logit [masked]) * value over axis 2 of (B,N,K,C) tensors -> (B,N,C)  (csrc/cv.cu)."""
+
+    @staticmethod
+    def forward(ctx, logit, value, mask):
+        from .. import _cabi
+        f32, dev = torch.float32, logit.device
+        logit, value = logit.contiguous(), value.contiguous()
+        mask = mask.contiguous() if mask is not None else None
+        B, N, K, C = logit.shape
+        out = torch.empty(B, N, C, dtype=f32, device=dev)
+        _cabi.call("i2p_softmax_wsum", dev, B * N, K, C, _cabi._ptr(logit, f32, "logit", dev), _cabi._ptr(value, f32, "value", dev),
+                   _cabi._ptr(mask, f32, "mask", dev) if mask is not None else None, out.data_ptr())
+        ctx.save_for_backward(logit, value, out, mask if mask is not None else torch.empty(0, device=dev))
+        ctx.has_mask = mask is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        from .. import _cabi
+        logit, value, out, mask = ctx.saved_tensors
+        f32, dev = torch.float32, logit.device
+        B, N, K, C = logit.shape
+        gout = gout.contiguous()
+        dlogit, dvalue = torch.empty_like(logit), torch.empty_like(value)
+        _cabi.call("i2p_softmax_wsum_bwd", dev, B * N, K, C, logit.data_ptr(), value.data_ptr(),
+                   mask.data_ptr() if ctx.has_mask else None, out.data_ptr(), _cabi._ptr(gout, f32, "grad", dev),
+                   dlogit.data_ptr(), dvalue.data_ptr())
+        return dlogit, dvalue, None
+
+
+def _softmax_wsum(logit, value, mask=None):
+    """(B,N,K,C) logits / values [+ (B,N,K,1) validity mask] -> (B,N,C)"""
+    if USE_FUSED_CV and logit.is_cuda:
+        return _SoftmaxWSum.apply(logit, value, mask.reshape(mask.shape[:3]) if mask is not None else None)
+    if mask is not None:
+        logit = logit * mask + -1e10 * (1 - mask)
+    return torch.sum(F.softmax(logit, dim=2) * value, dim=2)
+
+
 def _standardise(x):
     """(x - mean) / max(std, 1e-12) over the channel axis, unbiased std (:384-389)."""
     return (x - x.mean(-1, keepdim=True)) / torch.clip(x.std(-1, keepdim=True), min=1e-12)
@@ -283,30 +374,16 @@ class CostVolume(nn.Module):
         """warped_xyz (B,HW,3) on the normalised plane, warped_points (B,HW,C), idx_n2 (B,HW,2),
         f2_xyz (B,N2,3), f2_points (B,N2,C), lidar_z (B,HW,1) -> (B,H,W,mlp2[-1])"""
         B, N, C = warped_points.shape
-        if self.nsample_q > 0:
-            idx = knn_point(self.nsample_q, f2_xyz.contiguous(), warped_xyz.contiguous()).to(torch.int32)
-            qi_xyz = gather_rows(f2_xyz, idx)                       # B,N,K,3
-            qi_points = gather_rows(f2_points, idx)                 # B,N,K,C
+        if USE_FUSED_CV and warped_points.is_cuda:
+            pi_feat1_new, pi_xyz_diff_concat, warped_xyz = self._first_layer_operand_fused(warped_xyz, warped_points, f2_xyz,
+                                                                                       f2_points, lidar_z)
         else:
-            qi_xyz = f2_xyz.unsqueeze(1).expand(-1, N, -1, -1)      # B,N,N2,3
-            qi_points = f2_points.unsqueeze(1)                      # B,1,N2,C (broadcast over points)
-        K = qi_xyz.shape[2]
-        warped_xyz = warped_xyz.mul(lidar_z)                        # restore depth (:379)
-        pi_xyz_diff_concat = torch.cat([warped_xyz[:, :, None, :].expand(-1, -1, K, -1), qi_xyz], dim=3)
-
-        pi_n = _standardise(warped_points)[:, :, None, :]           # B,N,1,C
-        qi_n = _standardise(qi_points)                              # B,(1|N),K,C
-        corr = pi_n * qi_n                                          # B,N,K,C
-        parts = [pi_xyz_diff_concat, corr]
-        if self.backward_validation:
-            valid = check_valid(warped_xyz).unsqueeze(-1)           # B,N,1,1
-            masked = corr * valid + -1e10 * (1 - valid)
-            parts.append(torch.max(masked, 1, keepdim=True)[0].expand(-1, N, -1, -1))
-        pi_feat1_new = torch.cat(parts, dim=3)
+            pi_feat1_new, pi_xyz_diff_concat, warped_xyz = self._first_layer_operand(warped_xyz, warped_points, f2_xyz,
+                                                                                 f2_points, lidar_z)
         pi_feat1_new = run_mlp(self.mlp1_convs, pi_feat1_new)
         pi_concat = torch.cat([self.pi_encoding(pi_xyz_diff_concat), pi_feat1_new], dim=3)
         pi_concat = run_mlp(self.mlp2_convs, pi_concat)
-        pi_feat1_new = torch.sum(F.softmax(pi_concat, dim=2) * pi_feat1_new, dim=2)   # B,N,mlp1[-1]
+        pi_feat1_new = _softmax_wsum(pi_concat, pi_feat1_new)        # B,N,mlp1[-1]
 
         # second stage: re-weight over the nsample 3-D neighbours of every point
         warped_xyz_bhw = warped_xyz.view(B, self.H, self.W, 3)
@@ -322,9 +399,57 @@ class CostVolume(nn.Module):
         pc_xyz_encoding = self.pc_encoding(torch.cat([pc_xyz_new, pc_xyz_grouped, pc_xyz_diff, pc_euc_diff], dim=3))
         pc_concat = torch.cat([pc_xyz_encoding, pc_points_new, pc_points_grouped], dim=-1)
         pc_concat = run_mlp(self.mlp2_convs_2, pc_concat)
-        pc_concat = pc_concat * valid_mask + -1e10 * (1 - valid_mask)
-        pc_feat1_new = torch.sum(F.softmax(pc_concat, dim=2) * pc_points_grouped, dim=2)
+        pc_feat1_new = _softmax_wsum(pc_concat, pc_points_grouped, valid_mask)
         return pc_feat1_new.view(B, self.H, self.W, -1)
+
+    def _first_layer_operand(self, warped_xyz, warped_points, f2_xyz, f2_points, lidar_z):
+        """The reference's formulation (:366-400): broadcast operands, mask, max, concatenate.
+        -> (B,N,K,6+C[+C]) operand of mlp1, (B,N,K,6) coordinate pairs, depth-restored xyz (B,N,3)"""
+        B, N, C = warped_points.shape
+        if self.nsample_q > 0:
+            idx = knn_point(self.nsample_q, f2_xyz.contiguous(), warped_xyz.contiguous()).to(torch.int32)
+            qi_xyz = gather_rows(f2_xyz, idx)                       # B,N,K,3
+            qi_points = gather_rows(f2_points, idx)                 # B,N,K,C
+        else:
+            qi_xyz = f2_xyz.unsqueeze(1).expand(-1, N, -1, -1)      # B,N,N2,3
+            qi_points = f2_points.unsqueeze(1)                      # B,1,N2,C (broadcast over points)
+        K = qi_xyz.shape[2]
+        warped_xyz = warped_xyz.mul(lidar_z)                        # restore depth (:379)
+        pi_xyz_diff_concat = torch.cat([warped_xyz[:, :, None, :].expand(-1, -1, K, -1), qi_xyz], dim=3)
+        pi_n = _standardise(warped_points)[:, :, None, :]           # B,N,1,C
+        qi_n = _standardise(qi_points)                              # B,(1|N),K,C
+        corr = pi_n * qi_n                                          # B,N,K,C
+        parts = [pi_xyz_diff_concat, corr]
+        if self.backward_validation:
+            valid = check_valid(warped_xyz).unsqueeze(-1)           # B,N,1,1
+            masked = corr * valid + -1e10 * (1 - valid)
+            parts.append(torch.max(masked, 1, keepdim=True)[0].expand(-1, N, -1, -1))
+        return torch.cat(parts, dim=3), pi_xyz_diff_concat, warped_xyz
+
+    def _first_layer_operand_fused(self, warped_xyz, warped_points, f2_xyz, f2_points, lidar_z):
+        """Same values from one build kernel.  The per-row standardisation commutes with the pixel gather, so the
+        pixels are standardised once (B,N2,C) instead of per (point, neighbour); the backward-validation maximum
+        over the points, max_n(valid_n ? pi[n,c] * qi[k,c] : -1e10), is qi[k,c] times the largest (qi > 0) or
+        smallest (qi < 0) valid pi[:,c] -- multiplication by a constant is monotonic also after rounding -- so
+        it needs two (B,C) reductions instead of passes over the (B,N,K,C) product."""
+        B, N, C = warped_points.shape
+        idx = None
+        if self.nsample_q > 0:
+            idx = knn_point(self.nsample_q, f2_xyz.contiguous(), warped_xyz.contiguous()).to(torch.int32)
+        warped_xyz = warped_xyz.mul(lidar_z)                        # restore depth (:379)
+        pi_n = _standardise(warped_points)                          # B,N,C
+        qi_n = _standardise(f2_points)                              # B,N2,C
+        maxc = None
+        if self.backward_validation:
+            valid = check_valid(warped_xyz) > 0                     # B,N,1
+            any_valid = valid.any(dim=1, keepdim=True)              # B,1,1
+            hi = torch.where(valid, pi_n, float("-inf")).max(dim=1, keepdim=True)[0]   # B,1,C
+            lo = torch.where(valid, pi_n, float("inf")).min(dim=1, keepdim=True)[0]
+            hi, lo = torch.where(any_valid, hi, 0.0), torch.where(any_valid, lo, 0.0)
+            maxc = torch.where(qi_n > 0, qi_n * hi, qi_n * lo)      # B,N2,C
+            maxc = torch.where(any_valid, maxc, -1e10)
+        X, xyz6 = _CvBuild.apply(warped_xyz, f2_xyz, pi_n, qi_n, maxc, idx)
+        return X, xyz6, warped_xyz
 
     def set_bn(self):
         for conv in list(self.mlp2_convs) + list(self.mlp1_convs) + list(self.mlp2_convs_2):

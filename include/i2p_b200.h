@@ -230,6 +230,25 @@ int i2p_rgb_bn_act_pool_bwd(int B, int C, int H, int W, int stride, int batch_st
                             float slope, const float *dout, double *s12, float *dy, float *dgamma, float *dbeta,
                             void *stream);
 
+/* ---- cost-volume glue: replaces the repeat / multiply / mask / max / concatenate and the softmax-weighted
+ * sums of CostVolume.forward (src/projectPN/PPBackbone_center.py:366-420, 470-488) ------------------------
+ * cv_build: X (B,N,K,Cx) = [xyz1[b,n] (3) | xyz2[b,j] (3) | pi[b,n,:]*qi[b,j,:] (C) | maxc[b,j,:] (C, if maxc)],
+ * j = k when idx == NULL (then K == N2) else idx[b,n,k]; xyz6 (B,N,K,6) = the coordinate channels alone.
+ * xyz1 (B,N,3), xyz2 (B,N2,3), pi (B,N,C), qi (B,N2,C), maxc (B,N2,C) or NULL, idx (B,N,K) int32 or NULL. */
+int i2p_cv_build(int B, int N, int K, int N2, int C, const float *xyz1, const float *xyz2, const float *pi, const float *qi,
+                 const float *maxc, const int32_t *idx, float *X, float *xyz6, void *stream);
+/* dX (B,N,K,Cx), dxyz6 (B,N,K,6) or NULL -> dxyz1 (B,N,3), dpi (B,N,C) written; dxyz2 (B,N2,3), dqi (B,N2,C),
+ * dmaxc (B,N2,C) accumulated (zero them first). */
+int i2p_cv_build_bwd(int B, int N, int K, int N2, int C, int has_max, const float *dX, const float *dxyz6, const float *pi,
+                     const float *qi, const int32_t *idx, float *dxyz1, float *dxyz2, float *dpi, float *dqi, float *dmaxc,
+                     void *stream);
+/* out (G,C) = sum_k softmax_k(l) v, l = logit (G,K,C) [* mask + -1e10 (1 - mask), mask (G,K) or NULL], v = value (G,K,C) */
+int i2p_softmax_wsum(long long groups, int K, int C, const float *logit, const float *value, const float *mask, float *out,
+                     void *stream);
+/* gout (G,C) -> dlogit, dvalue (G,K,C); the softmax is recomputed from logit */
+int i2p_softmax_wsum_bwd(long long groups, int K, int C, const float *logit, const float *value, const float *mask,
+                         const float *out, const float *gout, float *dlogit, float *dvalue, void *stream);
+
 /* ---- quaternion product: replaces mul_q of src/modules/warp_utils.py:25-60 (one launch instead of ~30) ----
  * out (B,N,4) = A (x) B with A = a (B,na,4), B = b (B,nb,4), na / nb in {1, N} (broadcast over points),
  * either operand optionally conjugated (the backward pass is da = dc (x) conj(b), db = conj(a) (x) dc). */
