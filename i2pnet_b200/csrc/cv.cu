@@ -7,8 +7,8 @@
 //    broadcast operands with `repeat`, multiplies, masks (3 more passes), max-reduces, expands and
 //    concatenates: ~750 MB of traffic per step for cost volume 1 at batch 8, against 153 MB written here.
 //    A second output holds the 6 coordinate channels alone (input of the position encoding).
-// 2. cv_build_bwd: dX read once; d pi by a register reduction over the pixels, d qi / d maxc / d xyz2 by
-//    a block-level partial sum over 8 points followed by one vector red.add per (pixel, channel).
+// 2. cv_build_bwd: dX read once by blocks of 8 points x 16 pixels; every block adds its partial sums (over its
+//    pixels for d pi / d xyz1, over its points for d qi / d maxc / d xyz2) with one red.add per element.
 // 3. softmax_wsum: out[b,n,c] = sum_k softmax_k(l[b,n,k,c]) v[b,n,k,c] with an optional validity mask
 //    (l * m - 1e10 (1 - m), as the reference spells it), replacing softmax + multiply + sum (+ 4 mask ops);
 // 4. its backward, which recomputes the softmax from the saved logits:
@@ -20,7 +20,7 @@
 
 namespace i2p {
 
-constexpr int CVB_NT = 8;   // points per block in cv_build_bwd
+constexpr int CVB_NT = 8, CVB_KT = 16;   // points x pixels per block in cv_build_bwd
 
 struct CvGeom {
     int B, N, K, N2, C, has_max, Cx;   // Cx = 6 + C + (has_max ? C : 0)
@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) cv_build_kernel(CvGeom g, const float *__
     const float xv = t < 3 ? __ldg(xyz1 + ((size_t)b * g.N + n) * 3 + t) : 0.f;
     float *row = X + ((size_t)b * g.N + n) * g.K * g.Cx;
     float *row6 = xyz6 + ((size_t)b * g.N + n) * g.K * 6;
+#pragma unroll 4
     for (int k = 0; k < g.K; ++k) {
         const int j = idx != nullptr ? __ldg(idx + ((size_t)b * g.N + n) * g.K + k) : k;
         const float v = is_max ? __ldg(maxc + ((size_t)b * g.N2 + j) * g.C + c) : __fmul_rn(pv, __ldg(qi + ((size_t)b * g.N2 + j) * g.C + c));
@@ -50,14 +51,16 @@ __global__ void __launch_bounds__(256) cv_build_kernel(CvGeom g, const float *__
     }
 }
 
-// grid (ceil(N / 8), B), block Cx - 6 threads.  dxyz6 (B,N,K,6) is the gradient of the separate coordinate output
-// (may be NULL).  dqi, dmaxc, dxyz2 are accumulated with atomics and must be zero on entry; dpi, dxyz1 are written.
+// grid (ceil(N / 8), ceil(K / 16), B), block Cx - 6 threads: 8 points x 16 pixels per block.  dxyz6 (B,N,K,6) is the
+// gradient of the separate coordinate output (may be NULL).  Every output is accumulated with atomics (a block
+// holds a partial sum over its pixels for d pi / d xyz1 and over its points for d qi / d maxc / d xyz2) and must
+// be zero on entry.
 __global__ void __launch_bounds__(256) cv_build_bwd_kernel(CvGeom g, const float *__restrict__ dX, const float *__restrict__ dxyz6,
                                                           const float *__restrict__ pi, const float *__restrict__ qi,
-                                                          const int32_t *__restrict__ idx, float *__restrict__ dxyz1,
-                                                          float *dxyz2, float *__restrict__ dpi, float *dqi, float *dmaxc) {
-    const int n0 = blockIdx.x * CVB_NT, b = blockIdx.y, t = threadIdx.x;
-    const int nn = min(CVB_NT, g.N - n0);
+                                                          const int32_t *__restrict__ idx, float *dxyz1, float *dxyz2,
+                                                          float *dpi, float *dqi, float *dmaxc) {
+    const int n0 = blockIdx.x * CVB_NT, k0 = blockIdx.y * CVB_KT, b = blockIdx.z, t = threadIdx.x;
+    const int nn = min(CVB_NT, g.N - n0), k1 = min(g.K, k0 + CVB_KT);
     const bool is_max = t >= g.C;
     const int c = is_max ? t - g.C : t;
     float pv[CVB_NT], accp[CVB_NT], acc1[CVB_NT];
@@ -67,21 +70,24 @@ __global__ void __launch_bounds__(256) cv_build_bwd_kernel(CvGeom g, const float
         accp[i] = 0.f;
         acc1[i] = 0.f;
     }
-    for (int k = 0; k < g.K; ++k) {
+    for (int k = k0; k < k1; ++k) {
         float aq = 0.f, a2 = 0.f;   // partial sums over the block's points for (pixel k, this channel), every-pixel form
+        float v[CVB_NT];
+#pragma unroll
+        for (int i = 0; i < CVB_NT; ++i)   // the block's eight rows of this pixel: independent loads, all in flight
+            v[i] = i < nn ? __ldg(dX + (((size_t)b * g.N + n0 + i) * g.K + k) * g.Cx + 6 + t) : 0.f;
 #pragma unroll
         for (int i = 0; i < CVB_NT; ++i) {
             if (i >= nn) break;
             const size_t r = ((size_t)b * g.N + n0 + i) * g.K + k;
             const int j = idx != nullptr ? __ldg(idx + r) : k;
-            const float v = __ldg(dX + r * g.Cx + 6 + t);
             if (is_max) {
-                if (idx != nullptr) atomicAdd(dmaxc + ((size_t)b * g.N2 + j) * g.C + c, v);
-                else aq += v;
+                if (idx != nullptr) atomicAdd(dmaxc + ((size_t)b * g.N2 + j) * g.C + c, v[i]);
+                else aq += v[i];
             } else {
-                accp[i] = __fmaf_rn(v, __ldg(qi + ((size_t)b * g.N2 + j) * g.C + c), accp[i]);
-                if (idx != nullptr) atomicAdd(dqi + ((size_t)b * g.N2 + j) * g.C + c, v * pv[i]);
-                else aq = __fmaf_rn(v, pv[i], aq);
+                accp[i] = __fmaf_rn(v[i], __ldg(qi + ((size_t)b * g.N2 + j) * g.C + c), accp[i]);
+                if (idx != nullptr) atomicAdd(dqi + ((size_t)b * g.N2 + j) * g.C + c, v[i] * pv[i]);
+                else aq = __fmaf_rn(v[i], pv[i], aq);
             }
             if (t < 6) {   // coordinate channels: both the copy inside X and the separate 6-channel output
                 float w = __ldg(dX + r * g.Cx + t);
@@ -99,8 +105,8 @@ __global__ void __launch_bounds__(256) cv_build_bwd_kernel(CvGeom g, const float
 #pragma unroll
     for (int i = 0; i < CVB_NT; ++i) {
         if (i >= nn) break;
-        if (!is_max) dpi[((size_t)b * g.N + n0 + i) * g.C + c] = accp[i];
-        if (t < 3) dxyz1[((size_t)b * g.N + n0 + i) * 3 + t] = acc1[i];
+        if (!is_max) atomicAdd(dpi + ((size_t)b * g.N + n0 + i) * g.C + c, accp[i]);
+        if (t < 3) atomicAdd(dxyz1 + ((size_t)b * g.N + n0 + i) * 3 + t, acc1[i]);
     }
 }
 
@@ -196,7 +202,7 @@ int i2p_cv_build_bwd(int B, int N, int K, int N2, int C, int has_max, const floa
     I2P_REQUIRE(cv_geom(g, B, N, K, N2, C, has_max), "cv_build_bwd: bad sizes");
     I2P_REQUIRE(idx != nullptr || K == N2, "cv_build_bwd: K must equal N2 without an index");
     I2P_REQUIRE(!has_max || dmaxc != nullptr, "cv_build_bwd: dmaxc missing");
-    cv_build_bwd_kernel<<<dim3(ceil_div(N, CVB_NT), B), g.Cx - 6, 0, as_stream(stream)>>>(g, dX, dxyz6, pi, qi, idx, dxyz1, dxyz2,
+    cv_build_bwd_kernel<<<dim3(ceil_div(N, CVB_NT), ceil_div(K, CVB_KT), B), g.Cx - 6, 0, as_stream(stream)>>>(g, dX, dxyz6, pi, qi, idx, dxyz1, dxyz2,
                                                                                           dpi, dqi, dmaxc);
     return check_launch("cv_build_bwd");
 }

@@ -153,7 +153,7 @@ __device__ __forceinline__ float norm(float y, float mean, float scale, float be
 // identical decisions: no arg-max tensor is stored) and adds that window's gradient to the arg-max
 // position in a shared-memory accumulator -- windows of neighbouring tiles that reach into this one are
 // recomputed here instead of exchanging anything between blocks.
-constexpr int RGB_TH = 16, RGB_TW = 64;
+constexpr int RGB_TH = 32, RGB_TW = 128;   // 4096 elements per block: 16 per thread amortise the block launch
 
 // out[b,c,ho,wo] = max over the 3x3 window of leaky((y - mean) * scale + beta); first maximum in scan order wins
 // (ATen: `val > maxval || isnan(val)`), which only matters for the backward pass.

@@ -283,14 +283,17 @@ class _CvBuild(torch.autograd.Function):
         f32, dev = torch.float32, pi.device
         dX = dX.contiguous()
         dxyz6 = dxyz6.contiguous() if dxyz6 is not None else None
-        dxyz1 = torch.empty(B, N, 3, dtype=f32, device=dev)
-        dpi = torch.empty(B, N, C, dtype=f32, device=dev)
-        acc = torch.zeros(B, N2, 3 + C + (C if has_max else 0), dtype=f32, device=dev)   # one fill for the three atomics targets
-        # the kernel addresses the three accumulators as separate dense tensors: carve them out of one zeroed buffer
-        flat = acc.view(-1)
-        dxyz2 = flat[:B * N2 * 3].view(B, N2, 3)
-        dqi = flat[B * N2 * 3:B * N2 * (3 + C)].view(B, N2, C)
-        dmaxc = flat[B * N2 * (3 + C):].view(B, N2, C) if has_max else None
+        # five accumulators carved out of one zero-filled buffer (a single fill launch)
+        sizes = [B * N * 3, B * N * C, B * N2 * 3, B * N2 * C, B * N2 * C if has_max else 0]
+        flat = torch.zeros(sum(sizes), dtype=f32, device=dev)
+        offs = [0]
+        for n_ in sizes:
+            offs.append(offs[-1] + n_)
+        dxyz1 = flat[offs[0]:offs[1]].view(B, N, 3)
+        dpi = flat[offs[1]:offs[2]].view(B, N, C)
+        dxyz2 = flat[offs[2]:offs[3]].view(B, N2, 3)
+        dqi = flat[offs[3]:offs[4]].view(B, N2, C)
+        dmaxc = flat[offs[4]:offs[5]].view(B, N2, C) if has_max else None
         _cabi.call("i2p_cv_build_bwd", dev, B, N, K, N2, C, int(has_max), _cabi._ptr(dX, f32, "dX", dev),
                    _cabi._ptr(dxyz6, f32, "dxyz6", dev) if dxyz6 is not None else None, pi.data_ptr(), qi.data_ptr(),
                    idx.data_ptr() if has_idx else None, dxyz1.data_ptr(), dxyz2.data_ptr(), dpi.data_ptr(), dqi.data_ptr(),

@@ -237,8 +237,8 @@ int i2p_rgb_bn_act_pool_bwd(int B, int C, int H, int W, int stride, int batch_st
  * xyz1 (B,N,3), xyz2 (B,N2,3), pi (B,N,C), qi (B,N2,C), maxc (B,N2,C) or NULL, idx (B,N,K) int32 or NULL. */
 int i2p_cv_build(int B, int N, int K, int N2, int C, const float *xyz1, const float *xyz2, const float *pi, const float *qi,
                  const float *maxc, const int32_t *idx, float *X, float *xyz6, void *stream);
-/* dX (B,N,K,Cx), dxyz6 (B,N,K,6) or NULL -> dxyz1 (B,N,3), dpi (B,N,C) written; dxyz2 (B,N2,3), dqi (B,N2,C),
- * dmaxc (B,N2,C) accumulated (zero them first). */
+/* dX (B,N,K,Cx), dxyz6 (B,N,K,6) or NULL -> dxyz1 (B,N,3), dpi (B,N,C), dxyz2 (B,N2,3), dqi (B,N2,C), dmaxc (B,N2,C),
+ * all ACCUMULATED with atomics: zero them first. */
 int i2p_cv_build_bwd(int B, int N, int K, int N2, int C, int has_max, const float *dX, const float *dxyz6, const float *pi,
                      const float *qi, const int32_t *idx, float *dxyz1, float *dxyz2, float *dpi, float *dqi, float *dmaxc,
                      void *stream);

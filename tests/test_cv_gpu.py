@@ -84,7 +84,7 @@ def test_softmax_wsum_matches_torch():
             mask[:, 0] = 0                                        # a point with no valid neighbour at all
         outs = []
         for dt, fused in ((torch.float32, True), (torch.float64, False)):
-            l, v = l0.to(dt).requires_grad_(True), v0.to(dt).requires_grad_(True)
+            l, v = l0.detach().to(dt).clone().requires_grad_(True), v0.detach().to(dt).clone().requires_grad_(True)
             m = mask.to(dt) if masked else None
             if fused:
                 o = _softmax_wsum(l, v, m)

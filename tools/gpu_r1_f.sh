@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 900 python -m pytest tests/test_cv_gpu.py tests/test_quat_gpu.py tests/test_rgb_gpu.py tests/test_model_gpu.py -m gpu -q --no-header -p no:cacheprovider -x > $O/pytest_new.log 2>&1
+timeout 900 python -m pytest tests/test_cv_gpu.py tests/test_quat_gpu.py tests/test_rgb_gpu.py tests/test_model_gpu.py -m gpu -q --no-header -p no:cacheprovider > $O/pytest_new.log 2>&1
 echo "pytest exit $?" >> $O/pytest_new.log
 timeout 900 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider --deselect tests/test_cv_gpu.py --deselect tests/test_quat_gpu.py --deselect tests/test_rgb_gpu.py --deselect tests/test_model_gpu.py > $O/pytest_rest.log 2>&1
 echo "pytest exit $?" >> $O/pytest_rest.log
