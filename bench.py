@@ -297,7 +297,16 @@ def run_ours(args):
             "clocks": clocks, "roofline": roof, "roofline_others": roof_others, "cpu_baseline": cpu,
         }))
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: the captured graph holds NCCL kernels, and destroying the communicator underneath it was
+        # observed to hang (N = 2, after the JSON line was already printed).  All ranks meet at a barrier, the
+        # graph is released first, and the processes leave without the communicator destructor.
+        sys.stdout.flush()
+        dist.barrier()
+        torch.cuda.synchronize(device)
+        eng.graph = None
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -96,6 +96,24 @@ def main():
     torch.cuda.profiler.start()
     if what == "step":
         eng._step_body()
+    elif what == "kineto":
+        # real (warm, unserialised) kernel durations through CUPTI: sum per kernel name over 3 eager steps
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                eng._step_body()
+            torch.cuda.synchronize()
+        rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
+        rows.sort(key=lambda r: -r[2])
+        total = sum(r[2] for r in rows)
+        out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/kineto_step.md"
+        with open(out, "w") as fh:
+            fh.write("# CUPTI kernel durations, eager training step (3 steps; per-step figures below)\n\n")
+            fh.write("%.1f us of kernel time per step, %d launches per step\n\n" % (total / 3, sum(r[1] for r in rows) / 3))
+            fh.write("| share | us / step | launches / step | kernel |\n|---:|---:|---:|---|\n")
+            for k, n, t in rows[:80]:
+                fh.write("| %.1f %% | %.1f | %.1f | `%s` |\n" % (100 * t / total, t / 3, n / 3, k[:120]))
+        print("wrote", out)
     elif what == "marked":
         marked_step(eng, sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/markers.json")
     else:  # forward only
