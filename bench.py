@@ -85,8 +85,14 @@ def cpu_reference_steps(steps, warmup, batch, threads=None, seed=0):
     import torch
     from i2pnet_b200.synthetic import make_pairs
     from oracle import model_cpu
-    if threads:
-        torch.set_num_threads(threads)
+    # every host thread this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently turn the reference arm into a single-thread run
+    if not threads:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     cores = torch.get_num_threads()
     sd = {k: v.requires_grad_(True) for k, v in model_cpu.random_state(seed).items()}
     opt = torch.optim.Adam(list(sd.values()), lr=1e-3, weight_decay=1e-4)
