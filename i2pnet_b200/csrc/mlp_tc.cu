@@ -27,6 +27,8 @@
 #include "common.cuh"
 #include "umma.cuh"
 
+extern "C" int i2p_get_mlp_tensor_cores(void);
+
 namespace i2p {
 namespace tc {
 
@@ -96,7 +98,9 @@ __host__ __device__ inline PackGeom pack_geom(int cin, int cout) {
     return g;
 }
 
-__global__ void __launch_bounds__(256) pack_weights_kernel(int cin, int cout, const float *__restrict__ w,
+// layout 0: no-swizzle canonical order ((k / 4) * bn + n) * 4 + k % 4; layout 1: SWIZZLE_128B atoms of 8 rows x 128 B
+// (row n of the tile holds its 32 k contiguously, the 16-byte chunk index XORed with n % 8)
+__global__ void __launch_bounds__(256) pack_weights_kernel(int cin, int cout, int layout, const float *__restrict__ w,
                                                            float *__restrict__ pack) {
     const PackGeom g = pack_geom(cin, cout);
     const long long half_f = g.floats_f / 2, half_x = g.floats_x / 2;
@@ -108,8 +112,15 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(int cin, int cout, co
         const long long blk = q / per;
         const int r = (int)(q - blk * per);
         const int nt = (int)(blk / nc), c = (int)(blk - (long long)nt * nc);
-        // canonical order inside the half-block: ((k / 4) * bn + n) * 4 + k % 4
-        const int k4 = r / (bn * 4), rem = r - k4 * bn * 4, nl = rem >> 2, kl = k4 * 4 + (rem & 3);
+        int nl, kl;   // (row, k) of the element stored at float offset r of the half-block
+        if (layout == 0) {
+            const int k4 = r / (bn * 4), rem = r - k4 * bn * 4;
+            nl = rem >> 2;
+            kl = k4 * 4 + (rem & 3);
+        } else {
+            nl = r >> 5;                                    // 32 floats per row
+            kl = ((((r >> 2) & 7) ^ (nl & 7)) << 2) + (r & 3);
+        }
         const int n = nt * bn + nl, k = c * BK + kl;
         float v = 0.f;
         if (fwd) { if (n < cout && k < cin) v = __ldg(w + (size_t)n * cin + k); }
@@ -143,9 +154,19 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_hi, uint
     }
 }
 
-struct Prologue {
-    uint32_t tmem_d;
-};
+// The same for SWIZZLE_128B K-major tiles (8-row atoms of 1024 B; a k-step of 8 tf32 is 32 bytes further inside
+// the atom; layout type 2, SBO = 1024, LBO = 16 as CUTLASS encodes the swizzled K-major canonical layout).
+__device__ __forceinline__ void issue_chunk_sw(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                               uint32_t idesc, bool first_chunk) {
+#pragma unroll
+    for (int j = 0; j < BK / 8; ++j) {
+        const uint64_t ah = umma::smem_desc(a_hi + j * 32, 16, 1024, 2), al = umma::smem_desc(a_lo + j * 32, 16, 1024, 2);
+        const uint64_t bh = umma::smem_desc(b_hi + j * 32, 16, 1024, 2), bl = umma::smem_desc(b_lo + j * 32, 16, 1024, 2);
+        umma::mma_tf32(tmem_d, ah, bh, idesc, !(first_chunk && j == 0));
+        umma::mma_tf32(tmem_d, al, bh, idesc, true);
+        umma::mma_tf32(tmem_d, ah, bl, idesc, true);
+    }
+}
 
 // TMEM allocation + mbarrier set-up shared by the three kernels
 template <int COLS>
@@ -231,61 +252,96 @@ struct KMajorCoords {
     }
 };
 
-template <int BN>
+// SW variant: the tile is SWIZZLE_128B K-major -- row r holds its 32 k (128 B) contiguously at (r / 8) * 1024 +
+// (r % 8) * 128 with the 16-byte chunk index XORed with r % 8.  Lanes 0-7 are the eight k-groups of one row (one
+// full 128-byte line of global memory, stored to 128 contiguous bytes of shared memory), a warp pass covers 4 rows,
+// warp w owns rows 4 w + (lane >> 3) + 32 p.  Half as many L1 wavefronts per load as the no-swizzle mapping, whose
+// 8-lane phases had to span 8 rows: the load/store unit, not HBM or the tensor pipe, bounded that version.
+struct SwizzledCoords {
+    int kg, rbase;
+    uint32_t soff;   // byte offset of pass 0 inside a tile; pass p adds p * 4096
+    __device__ SwizzledCoords() {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        kg = lane & 7;
+        rbase = warp * 4 + (lane >> 3);          // row of pass p: rbase + 32 p
+        soff = (uint32_t)(rbase >> 3) * 1024u + (uint32_t)(rbase & 7) * 128u + ((uint32_t)(kg ^ (rbase & 7)) << 4);
+    }
+};
+
+// A hi | A lo | B hi | B lo, or the epilogue tile that overlays them, whichever is larger; SW: + 1 KB so that the
+// kernel can align the operand tiles to the 1024-byte swizzle atom itself
+template <int BN, int SW = 0>
 __host__ __device__ constexpr int fwd_smem_bytes() {
-    return (2 * BM * BK * 4 + 2 * BN * BK * 4) > (BM * (BN + 4) * 4) ? (2 * BM * BK * 4 + 2 * BN * BK * 4) : (BM * (BN + 4) * 4);
+    return ((2 * BM * BK * 4 + 2 * BN * BK * 4) > (BM * (BN + 4) * 4) ? (2 * BM * BK * 4 + 2 * BN * BK * 4) : (BM * (BN + 4) * 4)) +
+           (SW ? 1024 : 0);
 }
 
-template <int BN, int VEC, int PF>   // PF: prefetch distance in chunks (1 or 2 register sets)
+// SW = 0: no-swizzle operand tiles, weights by cp.async.  SW = 1: SWIZZLE_128B tiles with line-coalesced operand
+// loads (SwizzledCoords) and the weights of a chunk delivered by ONE bulk copy (TMA engine) that thread 0 issues
+// as soon as the previous chunk's MMAs have released the buffer -- no LSU work for the weight operand at all.
+template <int BN, int VEC, int SW>
 __global__ void __launch_bounds__(THREADS, BN == 128 ? 3 : 4) fwd_kernel(const FwdArgs a) {
     constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
     constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, SBO = 128;
-    extern __shared__ __align__(1024) unsigned char smem[];   // A hi | A lo | B hi | B lo ; epilogue tile overlays
-    __shared__ uint64_t mma_bar;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];   // A hi | A lo | B hi | B lo ; epilogue tile overlays
+    __shared__ uint64_t mma_bar, b_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ float part_n[THREADS / BN][BN], part_mu[THREADS / BN][BN], part_m2[THREADS / BN][BN];
 
     const int tid = threadIdx.x;
     const int nt = blockIdx.x, n0 = nt * BN, r0 = blockIdx.y * BM;
+    if (SW && tid == 0) umma::mbar_init(&b_bar, 1);
     const uint32_t tmem_d = tc_prologue<BN>(&mma_bar, &tmem_slot);
+    unsigned char *smem = SW ? smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
     const uint32_t sbase = umma::smem_u32(smem);
     constexpr uint32_t idesc = idesc_tf32(BN, false, false);
     const KMajorCoords co;
+    const SwizzledCoords cs;
+    const int kg = SW ? cs.kg : co.kg, rbase = SW ? cs.rbase : co.rbase;
+    const uint32_t soff = SW ? cs.soff : co.soff, pstep = SW ? 4096u : 512u;
     const int nchunks = (a.cin + BK - 1) / BK;
     const bool has_tf = a.in_scale != nullptr;
     const float *wblk = a.wpack + (size_t)nt * nchunks * 2 * BN * BK;
 
-    // Two register sets: the global loads of chunk c + 2 are issued as soon as chunk c has been staged, so a load
-    // has two chunk periods (staging + MMA of two chunks) to land -- one period is shorter than the DRAM latency
-    // under load (ncu: 44 % of warp time in long-scoreboard stalls with a single set).
-    float4 ra[PF][4];
-    auto fetch = [&](int c, float4 (&dst)[4]) {
-        const int k = c * BK + co.kg * 4;
+    float4 ra[4];
+    auto fetch = [&](int c) {   // issue the global loads of chunk c; nothing depends on them until it is staged
+        const int k = c * BK + kg * 4;
         const int kvalid = a.cin - k;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const int r = r0 + co.rbase + 32 * p;
-            dst[p] = load4<VEC>(a.x + (size_t)r * a.cin + k, r < a.rows ? kvalid : 0);
+            const int r = r0 + rbase + 32 * p;
+            ra[p] = load4<VEC>(a.x + (size_t)r * a.cin + k, r < a.rows ? kvalid : 0);
         }
     };
-    auto stage_and_issue = [&](int c, float4 (&src)[4]) {
-        float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_tf) {   // per-channel constants of the fused input transform (L1-resident)
-            const int k = c * BK + co.kg * 4;
-            sc4 = load4<1>(a.in_scale + k, a.cin - k);
-            sh4 = load4<1>(a.in_shift + k, a.cin - k);
-        }
-        if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);   // the tensor core is done with the stage
-        {   // weights of this chunk: straight 16-byte copies of the packed (hi | lo) block
-            const float *wsrc = wblk + (size_t)c * 2 * BN * BK;
+    auto copy_b = [&](int c) {   // weights of chunk c: the packed (hi | lo) block, byte for byte
+        const float *wsrc = wblk + (size_t)c * 2 * BN * BK;
+        if (SW) {
+            if (tid == 0) {
+                umma::mbar_expect_tx(&b_bar, 2 * B_BYTES);
+                umma::bulk_g2s(sbase + 2 * A_BYTES, wsrc, B_BYTES, &b_bar);
+                umma::bulk_g2s(sbase + 2 * A_BYTES + B_BYTES, wsrc + BN * BK, B_BYTES, &b_bar);
+            }
+        } else {
             constexpr int N16 = 2 * B_BYTES / 16;
 #pragma unroll
             for (int i = 0; i < N16 / THREADS; ++i)
                 cp_async16(sbase + 2 * A_BYTES + (uint32_t)(tid + i * THREADS) * 16, wsrc + (size_t)(tid + i * THREADS) * 4);
         }
+    };
+
+    fetch(0);
+    for (int c = 0; c < nchunks; ++c) {
+        float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_tf) {   // per-channel constants of the fused input transform (L1-resident)
+            const int k = c * BK + kg * 4;
+            sc4 = load4<1>(a.in_scale + k, a.cin - k);
+            sh4 = load4<1>(a.in_shift + k, a.cin - k);
+        }
+        if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);   // the tensor core is done with the stage
+        copy_b(c);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            float4 v = src[p];
+            float4 v = ra[p];
             if (has_tf) {   // previous layer's normalise + activation; max(z, slope z) is act for 0 <= slope <= 1
                 float z;
                 z = __fmaf_rn(v.x, sc4.x, sh4.x); v.x = fmaxf(z, z * a.in_slope);
@@ -293,35 +349,23 @@ __global__ void __launch_bounds__(THREADS, BN == 128 ? 3 : 4) fwd_kernel(const F
                 z = __fmaf_rn(v.z, sc4.z, sh4.z); v.z = fmaxf(z, z * a.in_slope);
                 z = __fmaf_rn(v.w, sc4.w, sh4.w); v.w = fmaxf(z, z * a.in_slope);
             }
-            split_store4(smem, smem + A_BYTES, co.soff + (uint32_t)p * 512u, v.x, v.y, v.z, v.w);
+            split_store4(smem, smem + A_BYTES, soff + (uint32_t)p * pstep, v.x, v.y, v.z, v.w);
         }
-        cp_async_wait_all();
+        if (!SW) cp_async_wait_all();
         umma::fence_smem_to_async();
         __syncthreads();
         if (tid == 0) {
             umma::fence_after_sync();
-            issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, 2 * A_LBO, sbase + 2 * A_BYTES, sbase + 2 * A_BYTES + B_BYTES,
-                        B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
+            const uint32_t sb = sbase + 2 * A_BYTES;
+            if (SW) {
+                umma::mbar_wait(&b_bar, (uint32_t)c & 1u);   // the bulk copy of this chunk's weights has landed
+                issue_chunk_sw(tmem_d, sbase, sbase + A_BYTES, sb, sb + B_BYTES, idesc, c == 0);
+            } else {
+                issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, 2 * A_LBO, sb, sb + B_BYTES, B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
+            }
             umma::commit(&mma_bar);
         }
-    };
-
-    fetch(0, ra[0]);
-    if (PF == 2) {
-        if (nchunks > 1) fetch(1, ra[PF - 1]);
-        for (int c = 0; c < nchunks; c += 2) {
-            stage_and_issue(c, ra[0]);
-            if (c + 2 < nchunks) fetch(c + 2, ra[0]);
-            if (c + 1 < nchunks) {
-                stage_and_issue(c + 1, ra[PF - 1]);
-                if (c + 3 < nchunks) fetch(c + 3, ra[PF - 1]);
-            }
-        }
-    } else {
-        for (int c = 0; c < nchunks; ++c) {
-            stage_and_issue(c, ra[0]);
-            if (c + 1 < nchunks) fetch(c + 1, ra[0]);
-        }
+        if (c + 1 < nchunks) fetch(c + 1);   // global loads in flight while the tensor core runs
     }
     umma::mbar_wait(&mma_bar, (uint32_t)(nchunks - 1) & 1u);
     umma::fence_after_sync();
@@ -418,83 +462,87 @@ struct DxArgs {
     double *prev_s12;
 };
 
-template <int BN>
-__host__ __device__ constexpr int dx_smem_bytes() { return fwd_smem_bytes<BN>() + (int)sizeof(DyTab); }
+template <int BN, int SW = 0>
+__host__ __device__ constexpr int dx_smem_bytes() { return fwd_smem_bytes<BN, SW>() + (int)sizeof(DyTab); }
 
-template <int BN, int PF>
-__global__ void __launch_bounds__(THREADS, PF == 2 ? 2 : 3) dx_kernel(const DxArgs a) {
+template <int BN, int SW>
+__global__ void __launch_bounds__(THREADS, 3) dx_kernel(const DxArgs a) {
     constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
     constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, SBO = 128;
-    constexpr int OPER = fwd_smem_bytes<BN>();
-    extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t mma_bar;
+    constexpr int OPER = fwd_smem_bytes<BN, 0>();
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t mma_bar, b_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ float part1[THREADS / BN][BN], part2[THREADS / BN][BN];
+    unsigned char *smem = SW ? smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
     DyTab &tab = *reinterpret_cast<DyTab *>(smem + OPER);
 
     const int tid = threadIdx.x;
     const int nt = blockIdx.x, n0 = nt * BN, r0 = blockIdx.y * BM;
     load_dytab(tab, a.bn, a.s12, a.cout, a.rows);
+    if (SW && tid == 0) umma::mbar_init(&b_bar, 1);
     const uint32_t tmem_d = tc_prologue<BN>(&mma_bar, &tmem_slot);   // (its barrier also publishes the tables)
     const uint32_t sbase = umma::smem_u32(smem);
     constexpr uint32_t idesc = idesc_tf32(BN, false, false);
     const KMajorCoords co;
+    const SwizzledCoords cs;
+    const int kg = SW ? cs.kg : co.kg, rbase = SW ? cs.rbase : co.rbase;
+    const uint32_t soff = SW ? cs.soff : co.soff, pstep = SW ? 4096u : 512u;
     const int nchunks = a.cout / BK;
     const float *wblk = a.wpack + (size_t)nt * nchunks * 2 * BN * BK;
 
-    float4 rg[PF][4], ry[PF][4];   // PF = 2: two register sets, loads issued two chunks ahead (see the forward kernel)
-    auto fetch = [&](int c, float4 (&dg)[4], float4 (&dyv)[4]) {
-        const int k = c * BK + co.kg * 4;
+    float4 rg[4], ry[4];
+    auto fetch = [&](int c) {
+        const int k = c * BK + kg * 4;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const int r = r0 + co.rbase + 32 * p;
+            const int r = r0 + rbase + 32 * p;
             const int valid = r < a.rows ? 4 : 0;
-            dg[p] = load4<4>(a.g + (size_t)r * a.cout + k, valid);
-            dyv[p] = load4<4>(a.bn.y + (size_t)r * a.cout + k, valid);
+            rg[p] = load4<4>(a.g + (size_t)r * a.cout + k, valid);
+            ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + k, valid);
         }
     };
-    auto stage_and_issue = [&](int c, float4 (&sg)[4], float4 (&sy)[4]) {
-        if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);
-        {
-            const float *wsrc = wblk + (size_t)c * 2 * BN * BK;
+    auto copy_b = [&](int c) {
+        const float *wsrc = wblk + (size_t)c * 2 * BN * BK;
+        if (SW) {
+            if (tid == 0) {
+                umma::mbar_expect_tx(&b_bar, 2 * B_BYTES);
+                umma::bulk_g2s(sbase + 2 * A_BYTES, wsrc, B_BYTES, &b_bar);
+                umma::bulk_g2s(sbase + 2 * A_BYTES + B_BYTES, wsrc + BN * BK, B_BYTES, &b_bar);
+            }
+        } else {
             constexpr int N16 = 2 * B_BYTES / 16;
 #pragma unroll
             for (int i = 0; i < N16 / THREADS; ++i)
                 cp_async16(sbase + 2 * A_BYTES + (uint32_t)(tid + i * THREADS) * 16, wsrc + (size_t)(tid + i * THREADS) * 4);
         }
-        const int ch = c * BK + co.kg * 4;
+    };
+
+    fetch(0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);
+        copy_b(c);
+        const int ch = c * BK + kg * 4;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const float4 v = dy4(tab, ch, sg[p], sy[p], a.bn.slope);   // rows beyond `rows` give finite garbage: never stored
-            split_store4(smem, smem + A_BYTES, co.soff + (uint32_t)p * 512u, v.x, v.y, v.z, v.w);
+            const float4 v = dy4(tab, ch, rg[p], ry[p], a.bn.slope);   // rows beyond `rows` give finite garbage: never stored
+            split_store4(smem, smem + A_BYTES, soff + (uint32_t)p * pstep, v.x, v.y, v.z, v.w);
         }
-        cp_async_wait_all();
+        if (!SW) cp_async_wait_all();
         umma::fence_smem_to_async();
         __syncthreads();
         if (tid == 0) {
             umma::fence_after_sync();
-            issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, 2 * A_LBO, sbase + 2 * A_BYTES, sbase + 2 * A_BYTES + B_BYTES,
-                        B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
+            const uint32_t sb = sbase + 2 * A_BYTES;
+            if (SW) {
+                umma::mbar_wait(&b_bar, (uint32_t)c & 1u);
+                issue_chunk_sw(tmem_d, sbase, sbase + A_BYTES, sb, sb + B_BYTES, idesc, c == 0);
+            } else {
+                issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, 2 * A_LBO, sb, sb + B_BYTES, B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
+            }
             umma::commit(&mma_bar);
         }
-    };
-
-    fetch(0, rg[0], ry[0]);
-    if (PF == 2) {
-        if (nchunks > 1) fetch(1, rg[PF - 1], ry[PF - 1]);
-        for (int c = 0; c < nchunks; c += 2) {
-            stage_and_issue(c, rg[0], ry[0]);
-            if (c + 2 < nchunks) fetch(c + 2, rg[0], ry[0]);
-            if (c + 1 < nchunks) {
-                stage_and_issue(c + 1, rg[PF - 1], ry[PF - 1]);
-                if (c + 3 < nchunks) fetch(c + 3, rg[PF - 1], ry[PF - 1]);
-            }
-        }
-    } else {
-        for (int c = 0; c < nchunks; ++c) {
-            stage_and_issue(c, rg[0], ry[0]);
-            if (c + 1 < nchunks) fetch(c + 1, rg[0], ry[0]);
-        }
+        if (c + 1 < nchunks) fetch(c + 1);
     }
     umma::mbar_wait(&mma_bar, (uint32_t)(nchunks - 1) & 1u);
     umma::fence_after_sync();
@@ -703,18 +751,11 @@ static int vec_of(int ld, const void *p) {
 }
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// Register prefetch distance of the forward / dX kernels: environment variable I2P_TC_PREFETCH (1 or 2), default 1.
-// Measured on B200 (cost-volume layer shapes): a second register set does not shorten the forward kernel
-// (118.8 -> 120.9 us) and costs dX a third resident CTA per SM (86 -> 96 us): the kernels are not waiting
-// on the depth of the load pipeline.
-static int prefetch_distance() {
-    static int pf = 0;
-    if (pf == 0) {
-        const char *e = getenv("I2P_TC_PREFETCH");
-        pf = (e != nullptr && atoi(e) == 2) ? 2 : 1;
-    }
-    return pf;
-}
+// Operand layout of the forward / dX kernels: bit 16 of the tensor-core mask (i2p_set_mlp_tensor_cores) selects the
+// SWIZZLE_128B + bulk-copy variant.  Measured and dropped on the way here: a second register set for the activation
+// operand (prefetch distance 2: 118.8 -> 120.9 us forward) and double-buffered cp.async weights (116.7 vs 120.8 us):
+// the kernels were bound by load/store-unit wavefronts, not by the depth of either pipeline.
+static bool swizzled() { return (i2p_get_mlp_tensor_cores() & 16) != 0; }
 
 }  // namespace tc
 }  // namespace i2p
@@ -741,7 +782,7 @@ int i2p_pw_pack_weights(int cin, int cout, const float *w, float *pack, void *st
     const tc::PackGeom g = tc::pack_geom(cin, cout);
     const long long total = (g.floats_f + g.floats_x) / 2;
     const long long blocks = (total + 255) / 256;
-    tc::pack_weights_kernel<<<(int)(blocks < 592 ? blocks : 592), 256, 0, as_stream(stream)>>>(cin, cout, w, pack);
+    tc::pack_weights_kernel<<<(int)(blocks < 592 ? blocks : 592), 256, 0, as_stream(stream)>>>(cin, cout, tc::swizzled() ? 1 : 0, w, pack);
     return check_launch("pw_pack_weights");
 }
 
@@ -757,16 +798,16 @@ int i2p_pw_linear_fwd_tc(int rows, int cin, int cout, const float *x, const floa
     cudaStream_t s = as_stream(stream);
     dim3 grid(g.nt_f, ceil_div(rows, tc::BM));
     const int vec = tc::vec_of(cin, x);
-    const int pf = tc::prefetch_distance();
-#define I2P_FWD(BN_, V_, P_)                                                                              \
-    do {                                                                                                  \
-        static bool once = false;                                                                         \
-        if (!once) { tc::allow_smem(tc::fwd_kernel<BN_, V_, P_>, tc::fwd_smem_bytes<BN_>()); once = true; } \
-        tc::fwd_kernel<BN_, V_, P_><<<grid, tc::THREADS, tc::fwd_smem_bytes<BN_>(), s>>>(a);              \
+    const int bdb = tc::swizzled();
+#define I2P_FWD(BN_, V_, P_)                                                                                    \
+    do {                                                                                                        \
+        static bool once = false;                                                                               \
+        if (!once) { tc::allow_smem(tc::fwd_kernel<BN_, V_, P_>, tc::fwd_smem_bytes<BN_, P_>()); once = true; } \
+        tc::fwd_kernel<BN_, V_, P_><<<grid, tc::THREADS, tc::fwd_smem_bytes<BN_, P_>(), s>>>(a);                \
     } while (0)
 #define I2P_FWD_V(BN_, P_) do { if (vec == 4) I2P_FWD(BN_, 4, P_); else if (vec == 2) I2P_FWD(BN_, 2, P_); else I2P_FWD(BN_, 1, P_); } while (0)
-    if (g.bn_f == 64) { if (pf == 2) I2P_FWD_V(64, 2); else I2P_FWD_V(64, 1); }
-    else { if (pf == 2) I2P_FWD_V(128, 2); else I2P_FWD_V(128, 1); }
+    if (g.bn_f == 64) { if (bdb) I2P_FWD_V(64, 1); else I2P_FWD_V(64, 0); }
+    else { if (bdb) I2P_FWD_V(128, 1); else I2P_FWD_V(128, 0); }
 #undef I2P_FWD_V
 #undef I2P_FWD
     return check_launch("pw_linear_fwd_tc");
@@ -790,15 +831,15 @@ int i2p_pw_linear_bwd_dx_tc(int rows, int cin, int cout, const float *g_dense, c
     a.prev_s12 = prev_s12;
     cudaStream_t s = as_stream(stream);
     dim3 grid(g.nt_x, ceil_div(rows, tc::BM));
-    const int pf = tc::prefetch_distance();
-#define I2P_DX(BN_, P_)                                                                                \
-    do {                                                                                               \
-        static bool once = false;                                                                      \
-        if (!once) { tc::allow_smem(tc::dx_kernel<BN_, P_>, tc::dx_smem_bytes<BN_>()); once = true; }  \
-        tc::dx_kernel<BN_, P_><<<grid, tc::THREADS, tc::dx_smem_bytes<BN_>(), s>>>(a);                 \
+    const int bdb = tc::swizzled();
+#define I2P_DX(BN_, P_)                                                                                    \
+    do {                                                                                                   \
+        static bool once = false;                                                                          \
+        if (!once) { tc::allow_smem(tc::dx_kernel<BN_, P_>, tc::dx_smem_bytes<BN_, P_>()); once = true; }  \
+        tc::dx_kernel<BN_, P_><<<grid, tc::THREADS, tc::dx_smem_bytes<BN_, P_>(), s>>>(a);                 \
     } while (0)
-    if (g.bn_x == 64) { if (pf == 2) I2P_DX(64, 2); else I2P_DX(64, 1); }
-    else { if (pf == 2) I2P_DX(128, 2); else I2P_DX(128, 1); }
+    if (g.bn_x == 64) { if (bdb) I2P_DX(64, 1); else I2P_DX(64, 0); }
+    else { if (bdb) I2P_DX(128, 1); else I2P_DX(128, 0); }
 #undef I2P_DX
     return check_launch("pw_linear_bwd_dx_tc");
 }

@@ -22,6 +22,17 @@ SHAPES = [
 ]
 
 
+@pytest.fixture(autouse=True, params=[7, 23], ids=["noswizzle", "sw128"])
+def operand_layout(request):
+    """Every kernel-level test runs with both operand layouts of the forward / dX kernels."""
+    from i2pnet_b200 import _cabi
+    L = _cabi.lib()
+    before = L.i2p_get_mlp_tensor_cores()
+    L.i2p_set_mlp_tensor_cores(request.param)
+    yield request.param
+    L.i2p_set_mlp_tensor_cores(before)
+
+
 def _ids(s):
     return "r%d_%dto%d%s" % (s[0], s[1], s[2], "_bn" if s[3] else "")
 
@@ -108,7 +119,7 @@ def test_forward_tc_matches_f64(shape):
                  lay.b.data_ptr(), y.data_ptr(), tiles.data_ptr())
         else:
             before = L.i2p_get_mlp_tensor_cores()
-            L.i2p_set_mlp_tensor_cores(0)
+            L.i2p_set_mlp_tensor_cores(0)        # (the FMA kernel inside i2p_pw_linear_fwd; mask bit 8 would pick tcgen05 v1)
             call("i2p_pw_linear_fwd", dev, rows, cin, cout, lay.x.data_ptr(), sc, sh, lay.in_slope, lay.w.data_ptr(),
                  lay.b.data_ptr(), y.data_ptr(), tiles.data_ptr())
             L.i2p_set_mlp_tensor_cores(before)
@@ -168,11 +179,12 @@ def test_backward_tc_matches_f64(shape):
     assert ok, "\n" + "\n".join(rep)
 
 
-def test_pack_layout_round_trips():
-    """The pack kernel against a host restatement of the UMMA canonical K-major layout."""
+def test_pack_layout_round_trips(operand_layout):
+    """The pack kernel against a host restatement of the UMMA canonical K-major layouts (no swizzle / SWIZZLE_128B)."""
     from i2pnet_b200 import _cabi
     from i2pnet_b200._cabi import call
     L = _cabi.lib()
+    swz = bool(operand_layout & 16)
     dev = torch.device("cuda:0")
     cin, cout = 70, 96
     w = torch.randn(cout, cin, device=dev)
@@ -185,7 +197,8 @@ def test_pack_layout_round_trips():
     bn, nc = 128, 3            # forward section: cout 96 -> one 128-wide tile, cin 70 -> 3 chunks of 32
     for (nn, k) in [(0, 0), (5, 3), (95, 69), (17, 33), (96, 0), (0, 70)]:
         c, kl = divmod(k, 32)
-        off = (0 * nc + c) * 2 * bn * 32 + (kl // 4) * bn * 4 + nn * 4 + kl % 4
+        inner = nn * 32 + (((kl // 4) ^ (nn % 8)) * 4) + kl % 4 if swz else (kl // 4) * bn * 4 + nn * 4 + kl % 4
+        off = (0 * nc + c) * 2 * bn * 32 + inner
         want = float(wc[nn, k]) if nn < cout and k < cin else 0.0
         hi, lo = float(p[off]), float(p[off + bn * 32])
         assert abs(hi + lo - want) <= 5e-7 * abs(want) + 1e-12, (nn, k, hi, lo, want)

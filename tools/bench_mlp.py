@@ -59,20 +59,24 @@ def main():
         pp = ps12.data_ptr() if has_tf else None
         t_pack = timeit(lambda: call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr()))
 
-        def fwd(mask):
+        def fwd_mask(mask):
             L.i2p_set_mlp_tensor_cores(mask)
-            if mask == 1:
+            if mask & 1:
                 return lambda: call("i2p_pw_linear_fwd_tc", dev, rows, cin, cout, x.data_ptr(), psc, psh, 0.1, pack.data_ptr(),
                                     b.data_ptr(), y.data_ptr(), tiles.data_ptr())
             return lambda: call("i2p_pw_linear_fwd", dev, rows, cin, cout, x.data_ptr(), psc, psh, 0.1, w.data_ptr(),
                                 b.data_ptr(), y.data_ptr(), tiles.data_ptr())
         res = {}
-        for name, mask in (("fma", 0), ("tc_v1", 8), ("tc", 1)):
-            res["fwd_" + name] = timeit(fwd(mask))
+        for name, mask in (("fma", 0), ("tc", 1), ("tc_sw", 17)):
+            if mask & 16:   # the pack layout follows the mask
+                L.i2p_set_mlp_tensor_cores(mask)
+                call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr())
+            res["fwd_" + name] = timeit(fwd_mask(mask))
             if name == "fma":
                 y0 = y.clone()
         err = float((y - y0).abs().max() / y0.abs().max())
         L.i2p_set_mlp_tensor_cores(7)
+        call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr())
         call("i2p_bn_finalize", dev, rows, cout, tiles.data_ptr(), sc[:1].expand(cout).contiguous().data_ptr(), b.data_ptr(), 1e-5,
              st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr())
         bn = (y.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), 0.1)
@@ -83,16 +87,21 @@ def main():
         if L.i2p_pw_tc_supported(1, rows, cin, cout):
             res["dx_tc"] = timeit(lambda: call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, g.data_ptr(), *bn, s12.data_ptr(),
                                                pack.data_ptr(), dx.data_ptr(), *prev, pp))
+            L.i2p_set_mlp_tensor_cores(23)
+            call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr())
+            res["dx_tc_sw"] = timeit(lambda: call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, g.data_ptr(), *bn, s12.data_ptr(),
+                                                  pack.data_ptr(), dx.data_ptr(), *prev, pp))
+            L.i2p_set_mlp_tensor_cores(7)
             res["dw_tc"] = timeit(lambda: call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, g.data_ptr(), *bn, s12.data_ptr(),
                                                x.data_ptr(), psc, psh, 0.1 if has_tf else 1.0, dw.data_ptr()))
         t_mm = timeit(lambda: torch.addmm(b, x, w.t(), out=y))
         fb, bb = 4.0 * rows * (cin + cout), 4.0 * rows * (2 * cout + cin)
         line = "rows=%7d %3d->%3d pack %5.1f us | fwd" % (rows, cin, cout, t_pack)
-        for k in ("fma", "tc_v1", "tc"):
+        for k in ("fma", "tc", "tc_sw"):
             t = res["fwd_" + k]
             line += "  %s %6.1f us (%4.0f GB/s %.2f)" % (k, t, fb / t / 1e3, fb / t / 1e3 / PEAK)
         line += "  cublas %6.1f us  maxrel %.1e |" % (t_mm, err)
-        for k in ("dx_fma", "dx_tc", "dw_fma", "dw_tc"):
+        for k in ("dx_fma", "dx_tc", "dx_tc_sw", "dw_fma", "dw_tc"):
             if k in res:
                 line += "  %s %6.1f us (%4.0f GB/s %.2f)" % (k, res[k], bb / res[k] / 1e3, bb / res[k] / 1e3 / PEAK)
         print(line, flush=True)
