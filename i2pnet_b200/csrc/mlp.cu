@@ -813,12 +813,13 @@ static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : 64); }
 
 // Which shared-MLP GEMMs run on the tensor cores (tcgen05, 3xTF32; kernels in mlp_tc.cu), as a bit mask:
 // 1 forward, 2 dX, 4 dW, 8 the first-generation forward kernel of this file (kept for A/B measurements).
-// Default 7; environment variable I2P_MLP_TC overrides; 0 = f32 FMA kernels everywhere.
+// 16 = SWIZZLE_128B operand tiles + bulk-copied weights in the forward / dX kernels.  Default 23 (= 7 | 16);
+// environment variable I2P_MLP_TC overrides; 0 = f32 FMA kernels everywhere.
 static int g_mlp_tc = -1;
 static int mlp_tc_mask() {
     if (g_mlp_tc < 0) {
         const char *e = getenv("I2P_MLP_TC");
-        g_mlp_tc = (e == nullptr) ? 7 : atoi(e);
+        g_mlp_tc = (e == nullptr) ? 23 : atoi(e);
     }
     return g_mlp_tc;
 }

@@ -13,10 +13,10 @@
 //             statistics) -> out = maxpool(leaky((y - mean) * scale + beta)) from a shared-memory tile;
 //   backward: each block re-derives the arg-max of the pooling windows touching its tile and scatters
 //             their gradients in shared memory (no global atomics, no arg-max tensor, no zero-filled
-//             scatter target); pass 0 reduces the two batch-norm sums S1 = sum dz, S2 = sum dz * yhat,
-//             pass 1 writes dy = scale (dz - S1/n - yhat S2/n).
+//             scatter target); pass 0 writes dz = pooled gradient * act' and reduces the two batch-norm
+//             sums S1 = sum dz, S2 = sum dz * yhat, pass 1 streams dy = scale (dz - S1/n - yhat S2/n) in place.
 // Neither the normalised nor the activated tensor ever exists in HBM.  Algorithmic bytes per
-// element of y: forward 4 (stats) + 4 + 4/s^2 (pool), backward 2 x (4 + 4/s^2) + 4.
+// element of y: forward 4 (stats) + 4 + 4/s^2 (pool), backward (4 + 4/s^2 + 4) + (4 + 4 + 4).
 #include <math.h>
 
 #include "common.cuh"
@@ -191,35 +191,22 @@ __global__ void __launch_bounds__(256) rgb_pool_fwd_kernel(PoolGeom g, const flo
     }
 }
 
-// PASS 0: s12[slot][0][c] += sum dz, s12[slot][1][c] += sum dz * yhat over the tile (dz = pooled gradient * act').
-// PASS 1: dy = scale * (dz - S1/n - yhat * S2/n) (batch statistics) or scale * dz (running statistics);
-//         the blocks of tile (0, 0) of sample 0 also emit dgamma = S2, dbeta = S1 in f32.
-template <int S, int PASS>
-__global__ void __launch_bounds__(256) rgb_pool_bwd_kernel(PoolGeom g, int batch_stats, double inv_n,
-                                                          const float *__restrict__ y, const float *__restrict__ stats,
+// Pass 0: dz = pooled gradient * act' for every element of the tile, written to dy; s12[slot][0][c] += sum dz,
+// s12[slot][1][c] += sum dz * yhat.  Pass 1 (rgb_bn_bwd_apply_kernel) then streams dy <- scale * (dz - S1/n - yhat S2/n).
+template <int S>
+__global__ void __launch_bounds__(256) rgb_pool_bwd_kernel(PoolGeom g, const float *__restrict__ y, const float *__restrict__ stats,
                                                           float slope, const float *__restrict__ dout, double *s12,
-                                                          float *__restrict__ dy, float *dgamma, float *dbeta) {
+                                                          float *__restrict__ dy) {
     constexpr int ZH = RGB_TH + 4, ZW = RGB_TW + 4;
     constexpr int NWH = RGB_TH / S + (S == 1 ? 2 : 1), NWW = RGB_TW / S + (S == 1 ? 2 : 1);   // windows touching the tile
     __shared__ float zt[ZH][ZW + 1];          // pre-activation z, origin (h0 - 2, w0 - 2), -inf outside the plane
     __shared__ float dzt[RGB_TH][RGB_TW];     // gradient w.r.t. the activated value
     __shared__ float red[RGB_THREADS / 32];
-    __shared__ float sums[2];
     const int plane = blockIdx.z, c = plane % g.C;
     const int h0 = blockIdx.y * RGB_TH, w0 = blockIdx.x * RGB_TW;
     const float mu = __ldg(stats + c), rs = __ldg(stats + g.C + c), sc = __ldg(stats + 2 * g.C + c),
                 bt = __ldg(stats + 3 * g.C + c);
     const float *p = y + (size_t)plane * g.H * g.W;
-    if (PASS == 1 && threadIdx.x == 0) {
-        double t1 = 0.0, t2 = 0.0;
-        for (int k = 0; k < RGB_SPREAD; ++k) { t1 += s12[(size_t)(2 * k) * g.C + c]; t2 += s12[(size_t)(2 * k + 1) * g.C + c]; }
-        sums[0] = (float)(t1 * inv_n);
-        sums[1] = (float)(t2 * inv_n);
-        if (blockIdx.x == 0 && blockIdx.y == 0 && plane < g.C) {
-            if (dbeta != nullptr) dbeta[c] = (float)t1;
-            if (dgamma != nullptr) dgamma[c] = (float)t2;
-        }
-    }
     for (int idx = threadIdx.x; idx < ZH * ZW; idx += 256) {
         const int hh = idx / ZW, ww = idx - hh * ZW;
         const int h = h0 - 2 + hh, w = w0 - 2 + ww;
@@ -258,21 +245,56 @@ __global__ void __launch_bounds__(256) rgb_pool_bwd_kernel(PoolGeom g, int batch
         if (h >= g.H || w >= g.W) continue;
         const float dz = dzt[r][cc] * (zt[r + 2][cc + 2] > 0.f ? 1.f : slope);
         const float yhat = (__ldg(p + (size_t)h * g.W + w) - mu) * rs;
-        if (PASS == 0) {
-            s1 += dz;
-            s2 += dz * yhat;
-        } else {
-            dy[(size_t)plane * g.H * g.W + (size_t)h * g.W + w] = batch_stats ? sc * (dz - sums[0] - yhat * sums[1]) : sc * dz;
+        s1 += dz;
+        s2 += dz * yhat;
+        dy[(size_t)plane * g.H * g.W + (size_t)h * g.W + w] = dz;
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) {
+        const int slot = (blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z) % RGB_SPREAD;
+        atomicAdd(s12 + (size_t)(2 * slot) * g.C + c, (double)s1);
+        atomicAdd(s12 + (size_t)(2 * slot + 1) * g.C + c, (double)s2);
+    }
+}
+
+// dy (holding dz) <- scale * (dz - S1/n - yhat * S2/n) (batch statistics) or scale * dz (running statistics), in place;
+// one (sample, channel) plane per blockIdx.y, float4 where the plane size allows; block (0, c) also emits
+// dgamma = S2, dbeta = S1 in f32.
+__global__ void __launch_bounds__(256) rgb_bn_bwd_apply_kernel(int C, int HW, int batch_stats, double inv_n,
+                                                              const float *__restrict__ y, const float *__restrict__ stats,
+                                                              const double *__restrict__ s12, float *dy, float *dgamma,
+                                                              float *dbeta) {
+    __shared__ float sums[2];
+    const int plane = blockIdx.y, c = plane % C;
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int k = 0; k < RGB_SPREAD; ++k) { t1 += s12[(size_t)(2 * k) * C + c]; t2 += s12[(size_t)(2 * k + 1) * C + c]; }
+        sums[0] = (float)(t1 * inv_n);
+        sums[1] = (float)(t2 * inv_n);
+        if (blockIdx.x == 0 && plane < C) {
+            if (dbeta != nullptr) dbeta[c] = (float)t1;
+            if (dgamma != nullptr) dgamma[c] = (float)t2;
         }
     }
-    if (PASS == 0) {
-        s1 = block_sum(s1, red);
-        s2 = block_sum(s2, red);
-        if (threadIdx.x == 0) {
-            const int slot = (blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z) % RGB_SPREAD;
-            atomicAdd(s12 + (size_t)(2 * slot) * g.C + c, (double)s1);
-            atomicAdd(s12 + (size_t)(2 * slot + 1) * g.C + c, (double)s2);
+    __syncthreads();
+    const float mu = __ldg(stats + c), rs = __ldg(stats + C + c), sc = __ldg(stats + 2 * C + c);
+    const float s1n = batch_stats ? sums[0] : 0.f, s2n = batch_stats ? sums[1] : 0.f;
+    const float *yp = y + (size_t)plane * HW;
+    float *dp = dy + (size_t)plane * HW;
+    if ((HW & 3) == 0) {
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < HW / 4; i += gridDim.x * 256) {
+            const float4 yv = __ldg(reinterpret_cast<const float4 *>(yp) + i);
+            float4 d = reinterpret_cast<float4 *>(dp)[i];
+            d.x = sc * (d.x - s1n - ((yv.x - mu) * rs) * s2n);
+            d.y = sc * (d.y - s1n - ((yv.y - mu) * rs) * s2n);
+            d.z = sc * (d.z - s1n - ((yv.z - mu) * rs) * s2n);
+            d.w = sc * (d.w - s1n - ((yv.w - mu) * rs) * s2n);
+            reinterpret_cast<float4 *>(dp)[i] = d;
         }
+    } else {
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256)
+            dp[i] = sc * (dp[i] - s1n - ((__ldg(yp + i) - mu) * rs) * s2n);
     }
 }
 
@@ -343,12 +365,14 @@ int i2p_rgb_bn_act_pool_bwd(int B, int C, int H, int W, int stride, int batch_st
     dim3 grid(ceil_div(W, RGB_TW), ceil_div(H, RGB_TH), B * C);
     const double inv_n = 1.0 / (double)((long long)B * H * W);
     cudaStream_t s = as_stream(stream);
-    if (stride == 1) rgb_pool_bwd_kernel<1, 0><<<grid, 256, 0, s>>>(g, batch_stats, inv_n, y, stats, slope, dout, s12, dy, dgamma, dbeta);
-    else rgb_pool_bwd_kernel<2, 0><<<grid, 256, 0, s>>>(g, batch_stats, inv_n, y, stats, slope, dout, s12, dy, dgamma, dbeta);
+    if (stride == 1) rgb_pool_bwd_kernel<1><<<grid, 256, 0, s>>>(g, y, stats, slope, dout, s12, dy);
+    else rgb_pool_bwd_kernel<2><<<grid, 256, 0, s>>>(g, y, stats, slope, dout, s12, dy);
     int rc = check_launch("rgb_pool_bwd(reduce)");
     if (rc != I2P_OK) return rc;
-    if (stride == 1) rgb_pool_bwd_kernel<1, 1><<<grid, 256, 0, s>>>(g, batch_stats, inv_n, y, stats, slope, dout, s12, dy, dgamma, dbeta);
-    else rgb_pool_bwd_kernel<2, 1><<<grid, 256, 0, s>>>(g, batch_stats, inv_n, y, stats, slope, dout, s12, dy, dgamma, dbeta);
+    const int HW = H * W;
+    const int per_plane = (HW / 4 + 255) / 256;
+    dim3 grid2(per_plane < 1 ? 1 : (per_plane > 64 ? 64 : per_plane), B * C);
+    rgb_bn_bwd_apply_kernel<<<grid2, 256, 0, s>>>(C, HW, batch_stats, inv_n, y, stats, s12, dy, dgamma, dbeta);
     return check_launch("rgb_pool_bwd(dx)");
 }
 }

@@ -103,6 +103,19 @@ class RegNet_v2(nn.Module):
         lidar_img_raw (B,N,3) the same points in the LiDAR frame (drives the range image);
         intrinsic (B,3,3); lidar_feature (B,N,D) or None.
         -> out_3 (B,7) refined [q,t], result_4 (B,7) coarse [q,t], None, None, sx, sq"""
+        s = self._coarse(rgb_img, lidar_img, lidar_img_raw, intrinsic, lidar_feature, cfg)
+        out_3, W_l3, _, _ = self._refine(s, s["q4"], s["t4"], cfg)
+        return self._result(s, out_3, W_l3)
+
+    def _result(self, s, out_3, W_l3):
+        if self.eval_info:
+            return (out_3.float(), s["result_4"].float(), self.sx, self.sq, W_l3, s["P3_l4"], None, None,
+                    s["P4"].view(s["B"], -1, 3))
+        return out_3.float(), s["result_4"].float(), None, None, self.sx, self.sq
+
+    def _coarse(self, rgb_img, lidar_img, lidar_img_raw, intrinsic, lidar_feature, cfg):
+        """Everything up to the coarse (level-4) pose and the two up-convolutions (:216-343 of the reference):
+        returns the tensors the level-3 refinement needs."""
         dev = rgb_img.device
         intrinsic = intrinsic.float()
         B = rgb_img.shape[0]
@@ -147,29 +160,32 @@ class RegNet_v2(nn.Module):
                                  LF4.view(B, H4 * W4, -1), None)
         result_4 = torch.cat([q4, t4], dim=1)
 
-        # ---- level 3: warp by the coarse pose, refine
-        zero = torch.zeros((B, 1), device=dev)
-        P3_warped = warp_utils.warp_quat_xyz(P3_l4, q4, torch.cat([zero, t4], -1)) * check_valid(P3_l4)
         l3_w_up = self.set_upconv0_w_upsample(P3_raw, P4_raw, P3, P4, l3_grid, LF3, l4_w.view(B, H4, W4, -1), **rfkw)
         l3_up = self.set_upconv0_upsample(P3_raw, P4_raw, P3, P4, l3_grid, LF3, l4_points_predict, **rfkw)
+        return dict(B=B, H3W3=H3 * W3, P3_raw=P3_raw, P3_l4=P3_l4, P4=P4, LF3_cv=LF3_cv, l3_grid=l3_grid,
+                    RF3_index=RF3_index, RF3=RF3, l3_w_up=l3_w_up, l3_up=l3_up, q4=q4, t4=t4, result_4=result_4)
+
+    def _refine(self, s, q_in, t_in, cfg):
+        """Level 3 (:331-404): warp the level-3 points by the pose (q_in, t_in), correlate with the image again,
+        regress the residual pose (q3, t3) and compose  q = q3 q_in,  t = R(q3) t_in + t3.
+        -> out_3 (B,7), attention weights, q3, t3"""
+        B, n3 = s["B"], s["H3W3"]
+        P3_l4, LF3_cv = s["P3_l4"], s["LF3_cv"]
+        zero = torch.zeros((B, 1), device=P3_l4.device)
+        P3_warped = warp_utils.warp_quat_xyz(P3_l4, q_in, torch.cat([zero, t_in], -1)) * check_valid(P3_l4)
         lidar_z = P3_warped[:, :, 2:]
         lidar_uv = P3_warped / (lidar_z + 1e-10)
-        concat_3 = self.cost_volume2(P3_raw, lidar_uv, LF3_cv, l3_grid, RF3_index, RF3, lidar_z, cfg=cfg)
-        l3_predict = self.flow_predictor0_predict(LF3_cv, l3_up.view(B, H3 * W3, -1), concat_3.view(B, H3 * W3, -1))
-        l3_w = self.flow_predictor0_w(LF3_cv, l3_w_up.view(B, H3 * W3, -1), l3_predict)
-        l3_w = _mask_fill(l3_w, check_valid(P3_raw).view(B, -1, 1))
+        concat_3 = self.cost_volume2(s["P3_raw"], lidar_uv, LF3_cv, s["l3_grid"], s["RF3_index"], s["RF3"], lidar_z, cfg=cfg)
+        l3_predict = self.flow_predictor0_predict(LF3_cv, s["l3_up"].view(B, n3, -1), concat_3.view(B, n3, -1))
+        l3_w = self.flow_predictor0_w(LF3_cv, s["l3_w_up"].view(B, n3, -1), l3_predict)
+        l3_w = _mask_fill(l3_w, check_valid(s["P3_raw"]).view(B, -1, 1))
         q3, t3, W_l3 = self.l3_head(l3_predict, l3_w, P3_warped, LF3_cv, None)
 
-        # ---- compose: q = q3 q4, t = R(q3) t4 + t3
-        q = warp_utils.mul_q(q3.view(B, 1, 4), q4.view(B, 1, 4)).squeeze(1)
-        t4q = torch.cat([zero, t4], 1).view(B, 1, 4)
+        q = warp_utils.mul_q(q3.view(B, 1, 4), q_in.view(B, 1, 4)).squeeze(1)
+        tq_in = torch.cat([zero, t_in], 1).view(B, 1, 4)
         t3q = torch.cat([zero, t3], 1).view(B, 1, 4)
-        t = (warp_utils.mul_q(warp_utils.mul_q(q3, t4q), warp_utils.inv_q(q3)) + t3q).squeeze(1)
-        out_3 = torch.cat([q, t[:, 1:]], 1)
-
-        if self.eval_info:
-            return out_3.float(), result_4.float(), self.sx, self.sq, W_l3, P3_l4, None, None, P4.view(B, H4 * W4, 3)
-        return out_3.float(), result_4.float(), None, None, self.sx, self.sq
+        t = (warp_utils.mul_q(warp_utils.mul_q(q3, tq_in), warp_utils.inv_q(q3)) + t3q).squeeze(1)
+        return torch.cat([q, t[:, 1:]], 1), W_l3, q3, t3
 
     def set_bn(self):
         for name in ("flow_predictor0", "flow_predictor0_w", "flow_predictor0_predict", "LiDAR_lv1", "LiDAR_lv2",

@@ -110,7 +110,31 @@ def golden_model():
           **{"grad__" + n: grads[n] for n in keep}, **{"state__" + k: v for k, v in state.items()}, **inter)
 
 
+def golden_iter():
+    """Forward of the reference's iterative-refinement model (src/modellearn_proj_center_iter.py, six level-3
+    iterations) on the inputs and the state dict of ref_model_kitti_b2.npz; only the outputs are stored."""
+    from src.config_proj_lidarcenter import I2PNetConfig as cfg
+    from src.modellearn_proj_center_iter import RegNet_v2
+    cfg.efgh = False
+    g = np.load(os.path.join(HERE, "ref_model_kitti_b2.npz"))
+    state = {k[len("state__"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state__")}
+    model = RegNet_v2(cfg=cfg)
+    model.load_state_dict(state, strict=True)
+    model.train()
+    for head in (model.l4_head, model.l3_head):
+        head.DP1.p = 0.0
+    t = lambda k: torch.from_numpy(g[k])
+    with torch.no_grad():
+        out3, out4, _, _, _, _ = model(t("rgb_u8").float(), t("lidar"), t("raw_point_xyz"), None, t("intrinsic"), None, None,
+                                       None, t("lidar_feats"), cfg)
+    _save("ref_model_iter_kitti_b2.npz", out3=out3, out4=out4)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    golden_ops()
-    golden_model()
+    if len(sys.argv) > 1 and sys.argv[1] == "iter":
+        golden_iter()
+    else:
+        golden_ops()
+        golden_model()
+        golden_iter()

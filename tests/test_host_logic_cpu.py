@@ -105,3 +105,34 @@ def test_product_refuses_cpu_tensors():
     from i2pnet_b200.projectPN.utils import gather_rows
     with pytest.raises(_cabi.I2PError):
         gather_rows(torch.zeros(1, 4, 4), torch.zeros(1, 2, dtype=torch.int32))
+
+
+def _run_iter_model(state, g, device):
+    from i2pnet_b200.config_proj_lidarcenter import I2PNetConfig as cfg
+    from i2pnet_b200.modellearn_proj_center_iter import RegNet_v2
+    model = RegNet_v2()
+    model.load_state_dict(state, strict=True)         # same parameters as the single-pass model
+    model.train()
+    for head in (model.l4_head, model.l3_head):
+        head.DP1.p = 0.0
+    model.to(device)
+    t = lambda k: torch.from_numpy(g[k]).to(device)
+    with torch.no_grad():
+        out3, out4, _, _, _, _ = model(torch.from_numpy(g["rgb_u8"]).float().to(device), t("lidar"), t("raw_point_xyz"), None,
+                                       t("intrinsic"), None, None, None, t("lidar_feats"), cfg)
+    return out3, out4
+
+
+def check_iter_model(device):
+    """The six-iteration inference model against the reference's own
+    src/modellearn_proj_center_iter.py run on the same inputs and weights (tests/golden/make_golden.py iter)."""
+    g, state = load_golden_model()
+    ref = np.load(os.path.join(GOLDEN, "ref_model_iter_kitti_b2.npz"))
+    out3, out4 = _run_iter_model(state, g, device)
+    assert _rel(out4.cpu(), ref["out4"]) < REL
+    assert _rel(out3.cpu(), ref["out3"]) < REL
+    assert _rel(out3.cpu(), g["out3"]) > 1e-3          # and it is not the single-pass answer
+
+
+def test_iter_model_host_logic_matches_reference(oracle_backend):
+    check_iter_model("cpu")

@@ -77,6 +77,14 @@ def test_gradients_match_reference_formulation_on_gpu(tensor_cores):
     assert mine[-1] <= 5 * ref[-1] + 1e-4, rows[:5]
 
 
+def test_iter_model_matches_reference():
+    """src/modellearn_proj_center_iter.py (six refinement iterations) on the sm_100a kernels."""
+    from tests.test_host_logic_cpu import check_iter_model
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    check_iter_model("cuda:0")
+
+
 def test_reference_python_runs_unchanged_on_dropin_modules():
     """The reference's pointnet2_utils.py binds `pointnet2.pointnet2_cuda`; the drop-in module
     exposes that surface.  /root/reference does not exist on the GPU box, so the binding is

@@ -1,0 +1,50 @@
+"""Inference latency of the iterative-refinement model (src/modellearn_proj_center_iter.py: coarse pose + six
+level-3 refinements), the shape of the reference's evaluation loop (evaluation_proj.py:239-264): batch 1 and 8,
+eval-free (training-mode statistics as in the parity tests), forward only, CUDA-graph replay, CUDA events."""
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from i2pnet_b200.config_proj_lidarcenter import I2PNetConfig as cfg  # noqa: E402
+from i2pnet_b200.modellearn_proj_center_iter import RegNet_v2  # noqa: E402
+from i2pnet_b200.synthetic import make_pairs  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    model = RegNet_v2(cfg=cfg).to(dev).train()
+    for head in (model.l4_head, model.l3_head):
+        head.DP1.p = 0.0
+    for batch in (1, 8):
+        d = {k: v.to(dev) for k, v in make_pairs(batch, seed=3).items()}
+        run = lambda: model(d["rgb"], d["lidar"], d["raw_point_xyz"], None, d["intrinsic"], None, None, None, d["lidar_feats"], cfg)
+        with torch.no_grad():
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    run()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = run()
+            ts = []
+            for _ in range(30):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); graph.replay(); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+        ms = statistics.median(ts[5:])
+        print("iter model (6 refinements) batch %d: %.2f ms per forward = %.1f pairs/s; out_3[0] = %s" % (
+            batch, ms, batch / ms * 1e3, [round(float(v), 4) for v in out[0][0]]), flush=True)
+
+
+if __name__ == "__main__":
+    main()
