@@ -185,9 +185,9 @@ def time_hot_kernels(device, peak):
          st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr())
     bn = (y.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), 0.1)
     none_prev = (None, None, None, None, None, 1.0, None)
-    dxf = lambda: call("i2p_pw_linear_bwd_dx_tc", device, rows, cin, cout, gr.data_ptr(), *bn, s12.data_ptr(), pack.data_ptr(),
+    dxf = lambda: call("i2p_pw_linear_bwd_dx_tc", device, rows, cin, cout, gr.data_ptr(), None, None, 1, *bn, s12.data_ptr(), pack.data_ptr(),
                        dx.data_ptr(), *none_prev)
-    dwf = lambda: call("i2p_pw_linear_bwd_dw_tc", device, rows, cin, cout, gr.data_ptr(), *bn, s12.data_ptr(), x.data_ptr(),
+    dwf = lambda: call("i2p_pw_linear_bwd_dw_tc", device, rows, cin, cout, gr.data_ptr(), None, None, 1, *bn, s12.data_ptr(), x.data_ptr(),
                        None, None, 1.0, dw.data_ptr())
     d = make_pairs(BATCH, N_POINTS, IMAGE_HW, seed=7)
     _, (cam,) = project_seq(d["raw_point_xyz"].to(device), [d["lidar"].to(device)], 64, 1800, False)

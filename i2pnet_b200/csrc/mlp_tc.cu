@@ -451,9 +451,46 @@ __device__ __forceinline__ float4 dy4(const DyTab &t, int ch, float4 g, float4 y
 // dX = dY W  (rows x cin), dY rebuilt from (g, y) while the A tile is staged; K = cout (multiple of 32).
 // Epilogue: store, and the batch-norm backward sums of the PREVIOUS layer from the tile.
 // ---------------------------------------------------------------------------------------------
+// Gradient w.r.t. a layer's activated output: dense (rows, cout), or -- MAXK -- the gradient dout (rows / k, cout) of a
+// max-over-k output, routed to the row whose index inside its group equals arg (rows / k, cout).
+struct GSrc {
+    const float *g;       // dense, or dout
+    const int32_t *arg;   // MAXK only
+    int k;
+};
+
+template <bool MAXK>
+struct GQuad {            // what a thread keeps in registers for 4 channels of one row between fetch and stage
+    float4 v;
+    int4 a;
+};
+template <>
+struct GQuad<false> {
+    float4 v;
+};
+
+template <bool MAXK>
+__device__ __forceinline__ GQuad<MAXK> g_fetch(const GSrc &gs, long long r, long long grp, int ch, int cout, bool valid) {
+    GQuad<MAXK> q;
+    if constexpr (MAXK) {
+        q.v = load4<4>(gs.g + (size_t)grp * cout + ch, valid ? 4 : 0);
+        q.a = valid ? __ldg(reinterpret_cast<const int4 *>(gs.arg + (size_t)grp * cout + ch)) : make_int4(-1, -1, -1, -1);
+    } else {
+        q.v = load4<4>(gs.g + (size_t)r * cout + ch, valid ? 4 : 0);
+    }
+    return q;
+}
+template <bool MAXK>
+__device__ __forceinline__ float4 g_resolve(const GQuad<MAXK> &q, int kk) {
+    if constexpr (MAXK)
+        return make_float4(q.a.x == kk ? q.v.x : 0.f, q.a.y == kk ? q.v.y : 0.f, q.a.z == kk ? q.v.z : 0.f, q.a.w == kk ? q.v.w : 0.f);
+    else
+        return q.v;
+}
+
 struct DxArgs {
     int rows, cin, cout;
-    const float *g;      // dense gradient w.r.t. this layer's activated output (rows, cout)
+    GSrc gs;             // gradient w.r.t. this layer's activated output
     BnRef bn;
     const double *s12;
     const float *wpack;  // section X of the pack
@@ -465,8 +502,8 @@ struct DxArgs {
 template <int BN, int SW = 0>
 __host__ __device__ constexpr int dx_smem_bytes() { return fwd_smem_bytes<BN, SW>() + (int)sizeof(DyTab); }
 
-template <int BN, int SW>
-__global__ void __launch_bounds__(THREADS, 3) dx_kernel(const DxArgs a) {
+template <int BN, int SW, bool MAXK>
+__global__ void __launch_bounds__(THREADS, MAXK ? 2 : 3) dx_kernel(const DxArgs a) {
     constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
     constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, SBO = 128;
     constexpr int OPER = fwd_smem_bytes<BN, 0>();
@@ -491,15 +528,22 @@ __global__ void __launch_bounds__(THREADS, 3) dx_kernel(const DxArgs a) {
     const int nchunks = a.cout / BK;
     const float *wblk = a.wpack + (size_t)nt * nchunks * 2 * BN * BK;
 
-    float4 rg[4], ry[4];
+    GQuad<MAXK> rg[4];
+    float4 ry[4];
+    int grp[4], kk[4];   // MAXK: group of each of the thread's rows and the row's index inside it
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int r = r0 + rbase + 32 * p;
+        grp[p] = MAXK ? r / a.gs.k : 0;
+        kk[p] = MAXK ? r - grp[p] * a.gs.k : 0;
+    }
     auto fetch = [&](int c) {
         const int k = c * BK + kg * 4;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int r = r0 + rbase + 32 * p;
-            const int valid = r < a.rows ? 4 : 0;
-            rg[p] = load4<4>(a.g + (size_t)r * a.cout + k, valid);
-            ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + k, valid);
+            rg[p] = g_fetch<MAXK>(a.gs, r, grp[p], k, a.cout, r < a.rows);
+            ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + k, r < a.rows ? 4 : 0);
         }
     };
     auto copy_b = [&](int c) {
@@ -525,7 +569,7 @@ __global__ void __launch_bounds__(THREADS, 3) dx_kernel(const DxArgs a) {
         const int ch = c * BK + kg * 4;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const float4 v = dy4(tab, ch, rg[p], ry[p], a.bn.slope);   // rows beyond `rows` give finite garbage: never stored
+            const float4 v = dy4(tab, ch, g_resolve<MAXK>(rg[p], kk[p]), ry[p], a.bn.slope);   // rows beyond `rows`: finite, never stored
             split_store4(smem, smem + A_BYTES, soff + (uint32_t)p * pstep, v.x, v.y, v.z, v.w);
         }
         if (!SW) cp_async_wait_all();
@@ -592,7 +636,7 @@ __global__ void __launch_bounds__(THREADS, 3) dx_kernel(const DxArgs a) {
 // ---------------------------------------------------------------------------------------------
 struct DwArgs {
     int rows, cin, cout, rows_per_block;
-    const float *g;
+    GSrc gs;
     BnRef bn;
     const double *s12;
     const float *x;                 // (rows, cin) raw input / previous raw output
@@ -612,7 +656,7 @@ __host__ __device__ constexpr int dw_smem_bytes() { return 2 * BM * BK * 4 + 2 *
 // A warp pass stages one atom: lane -> (k-row r4, 16-byte half, 8-channel chunk c8); every 8-lane store phase
 // then covers 4 rows x 32 B in 4 different chunk positions = all 32 banks once, and every global row is read
 // as 128 contiguous bytes.
-template <int BN, int VEC>
+template <int BN, int VEC, bool MAXK>
 __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
     constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
     constexpr uint32_t LBO = 4096, SBO = 512, KSTEP_BYTES = 1024;
@@ -651,7 +695,8 @@ __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
     }
     const bool b_in = b_ch < a.cout;           // cout % 4 == 0: a quad is all in or all out
 
-    float4 rx[4], rg[B_PASSES], ry[B_PASSES];
+    float4 rx[4], ry[B_PASSES];
+    GQuad<MAXK> rg[B_PASSES];
     auto fetch = [&](long long r0) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -661,9 +706,9 @@ __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
 #pragma unroll
         for (int p = 0; p < B_PASSES; ++p) {
             const long long r = r0 + (b_kb0 + p * B_KSTEP) * 4 + r4;
-            const int valid = (r < re && b_in) ? 4 : 0;
-            rg[p] = load4<4>(a.g + (size_t)r * a.cout + b_ch, valid);
-            ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + b_ch, valid);
+            const bool valid = r < re && b_in;
+            rg[p] = g_fetch<MAXK>(a.gs, r, MAXK ? (int)r / a.gs.k : 0, b_ch, a.cout, valid);
+            ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + b_ch, valid ? 4 : 0);
         }
     };
 
@@ -690,7 +735,7 @@ __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
         for (int p = 0; p < B_PASSES; ++p) {
             const long long r = r0 + (b_kb0 + p * B_KSTEP) * 4 + r4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < re && b_in) v = dy4(tab, b_ch, rg[p], ry[p], a.bn.slope);
+            if (r < re && b_in) v = dy4(tab, b_ch, g_resolve<MAXK>(rg[p], MAXK ? (int)r % a.gs.k : 0), ry[p], a.bn.slope);
             split_store4(smem + 2 * A_BYTES, smem + 2 * A_BYTES + B_BYTES, b_off + (uint32_t)(p * B_KSTEP) * SBO, v.x, v.y, v.z, v.w);
         }
         umma::fence_smem_to_async();
@@ -813,47 +858,57 @@ int i2p_pw_linear_fwd_tc(int rows, int cin, int cout, const float *x, const floa
     return check_launch("pw_linear_fwd_tc");
 }
 
-int i2p_pw_linear_bwd_dx_tc(int rows, int cin, int cout, const float *g_dense, const float *y, const float *mean,
-                            const float *rstd, const float *scale, const float *shift, float slope, const double *s12,
-                            const float *wpack, float *dx, const float *prev_y, const float *prev_mean,
-                            const float *prev_rstd, const float *prev_scale, const float *prev_shift, float prev_slope,
-                            double *prev_s12, void *stream) {
+static bool make_gsrc(i2p::tc::GSrc &gs, const float *g_dense, const float *dout, const int32_t *arg, int k) {
+    if (g_dense != nullptr) { gs.g = g_dense; gs.arg = nullptr; gs.k = 1; return i2p::tc::aligned16(g_dense); }
+    gs.g = dout; gs.arg = arg; gs.k = k;
+    return dout != nullptr && arg != nullptr && k >= 1 && i2p::tc::aligned16(dout) && i2p::tc::aligned16(arg);
+}
+
+int i2p_pw_linear_bwd_dx_tc(int rows, int cin, int cout, const float *g_dense, const float *dout, const int32_t *arg, int k,
+                            const float *y, const float *mean, const float *rstd, const float *scale, const float *shift,
+                            float slope, const double *s12, const float *wpack, float *dx, const float *prev_y,
+                            const float *prev_mean, const float *prev_rstd, const float *prev_scale, const float *prev_shift,
+                            float prev_slope, double *prev_s12, void *stream) {
     using namespace i2p;
-    I2P_REQUIRE(i2p_pw_tc_supported(1, rows, cin, cout) && g_dense != nullptr, "pw_linear_bwd_dx_tc: shape not covered");
-    I2P_REQUIRE(tc::aligned16(g_dense) && tc::aligned16(y) && tc::aligned16(wpack) && tc::aligned16(dx),
-                "pw_linear_bwd_dx_tc: g, y, wpack, dx must be 16-byte aligned");
-    const tc::PackGeom g = tc::pack_geom(cin, cout);
+    I2P_REQUIRE(i2p_pw_tc_supported(1, rows, cin, cout), "pw_linear_bwd_dx_tc: shape not covered");
     tc::DxArgs a;
-    a.rows = rows; a.cin = cin; a.cout = cout; a.g = g_dense;
+    I2P_REQUIRE(make_gsrc(a.gs, g_dense, dout, arg, k), "pw_linear_bwd_dx_tc: no (16-byte aligned) gradient source");
+    I2P_REQUIRE(tc::aligned16(y) && tc::aligned16(wpack) && tc::aligned16(dx), "pw_linear_bwd_dx_tc: y, wpack, dx must be 16-byte aligned");
+    const tc::PackGeom g = tc::pack_geom(cin, cout);
+    a.rows = rows; a.cin = cin; a.cout = cout;
     a.bn = tc::BnRef{y, mean, rstd, scale, shift, slope};
     a.s12 = s12; a.wpack = wpack + g.floats_f; a.dx = dx;
     a.prev = tc::BnRef{prev_y, prev_mean, prev_rstd, prev_scale, prev_shift, prev_slope};
     a.prev_s12 = prev_s12;
     cudaStream_t s = as_stream(stream);
     dim3 grid(g.nt_x, ceil_div(rows, tc::BM));
-    const int bdb = tc::swizzled();
-#define I2P_DX(BN_, P_)                                                                                    \
-    do {                                                                                                   \
-        static bool once = false;                                                                          \
-        if (!once) { tc::allow_smem(tc::dx_kernel<BN_, P_>, tc::dx_smem_bytes<BN_, P_>()); once = true; }  \
-        tc::dx_kernel<BN_, P_><<<grid, tc::THREADS, tc::dx_smem_bytes<BN_, P_>(), s>>>(a);                 \
+    const int sw = tc::swizzled();
+    const bool maxk = g_dense == nullptr;
+#define I2P_DX(BN_, P_, M_)                                                                                       \
+    do {                                                                                                          \
+        static bool once = false;                                                                                 \
+        if (!once) { tc::allow_smem(tc::dx_kernel<BN_, P_, M_>, tc::dx_smem_bytes<BN_, P_>()); once = true; }     \
+        tc::dx_kernel<BN_, P_, M_><<<grid, tc::THREADS, tc::dx_smem_bytes<BN_, P_>(), s>>>(a);                    \
     } while (0)
-    if (g.bn_x == 64) { if (bdb) I2P_DX(64, 1); else I2P_DX(64, 0); }
-    else { if (bdb) I2P_DX(128, 1); else I2P_DX(128, 0); }
+#define I2P_DX_M(BN_, P_) do { if (maxk) I2P_DX(BN_, P_, true); else I2P_DX(BN_, P_, false); } while (0)
+    if (g.bn_x == 64) { if (sw) I2P_DX_M(64, 1); else I2P_DX_M(64, 0); }
+    else { if (sw) I2P_DX_M(128, 1); else I2P_DX_M(128, 0); }
+#undef I2P_DX_M
 #undef I2P_DX
     return check_launch("pw_linear_bwd_dx_tc");
 }
 
-int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, const float *y, const float *mean,
-                            const float *rstd, const float *scale, const float *shift, float slope, const double *s12,
-                            const float *x, const float *prev_scale, const float *prev_shift, float prev_slope, float *dw,
-                            void *stream) {
+int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, const float *dout, const int32_t *arg, int k,
+                            const float *y, const float *mean, const float *rstd, const float *scale, const float *shift,
+                            float slope, const double *s12, const float *x, const float *prev_scale, const float *prev_shift,
+                            float prev_slope, float *dw, void *stream) {
     using namespace i2p;
-    I2P_REQUIRE(i2p_pw_tc_supported(2, rows, cin, cout) && g_dense != nullptr, "pw_linear_bwd_dw_tc: shape not covered");
+    I2P_REQUIRE(i2p_pw_tc_supported(2, rows, cin, cout), "pw_linear_bwd_dw_tc: shape not covered");
     I2P_REQUIRE(prev_slope >= 0.f && prev_slope <= 1.f, "pw_linear_bwd_dw_tc: activation slope must be in [0, 1]");
-    I2P_REQUIRE(tc::aligned16(g_dense) && tc::aligned16(y), "pw_linear_bwd_dw_tc: g, y must be 16-byte aligned");
     tc::DwArgs a;
-    a.rows = rows; a.cin = cin; a.cout = cout; a.g = g_dense;
+    I2P_REQUIRE(make_gsrc(a.gs, g_dense, dout, arg, k), "pw_linear_bwd_dw_tc: no (16-byte aligned) gradient source");
+    I2P_REQUIRE(tc::aligned16(y), "pw_linear_bwd_dw_tc: y must be 16-byte aligned");
+    a.rows = rows; a.cin = cin; a.cout = cout;
     a.bn = tc::BnRef{y, mean, rstd, scale, shift, slope};
     a.s12 = s12; a.x = x; a.prev_scale = prev_scale; a.prev_shift = prev_shift; a.prev_slope = prev_slope; a.dw = dw;
     const int bn = cout <= 64 ? 64 : 128;
@@ -864,30 +919,21 @@ int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, c
     rpb = ((rpb + tc::BK - 1) / tc::BK) * tc::BK;
     if (rpb < 8 * tc::BK) rpb = 8 * tc::BK;
     a.rows_per_block = rpb;
-    static bool once = false;
-    if (!once) {
-        tc::allow_smem(tc::dw_kernel<64, 4>, tc::dw_smem_bytes<64>());
-        tc::allow_smem(tc::dw_kernel<64, 2>, tc::dw_smem_bytes<64>());
-        tc::allow_smem(tc::dw_kernel<64, 1>, tc::dw_smem_bytes<64>());
-        tc::allow_smem(tc::dw_kernel<128, 4>, tc::dw_smem_bytes<128>());
-        tc::allow_smem(tc::dw_kernel<128, 2>, tc::dw_smem_bytes<128>());
-        tc::allow_smem(tc::dw_kernel<128, 1>, tc::dw_smem_bytes<128>());
-        once = true;
-    }
     cudaStream_t s = as_stream(stream);
     dim3 grid(ceil_div(rows, rpb), mt, ntl);
     const int vec = tc::vec_of(cin, x);
-    if (bn == 64) {
-        constexpr int sm = tc::dw_smem_bytes<64>();
-        if (vec == 4) tc::dw_kernel<64, 4><<<grid, tc::THREADS, sm, s>>>(a);
-        else if (vec == 2) tc::dw_kernel<64, 2><<<grid, tc::THREADS, sm, s>>>(a);
-        else tc::dw_kernel<64, 1><<<grid, tc::THREADS, sm, s>>>(a);
-    } else {
-        constexpr int sm = tc::dw_smem_bytes<128>();
-        if (vec == 4) tc::dw_kernel<128, 4><<<grid, tc::THREADS, sm, s>>>(a);
-        else if (vec == 2) tc::dw_kernel<128, 2><<<grid, tc::THREADS, sm, s>>>(a);
-        else tc::dw_kernel<128, 1><<<grid, tc::THREADS, sm, s>>>(a);
-    }
+    const bool maxk = g_dense == nullptr;
+#define I2P_DW(BN_, V_, M_)                                                                                   \
+    do {                                                                                                      \
+        static bool once = false;                                                                             \
+        if (!once) { tc::allow_smem(tc::dw_kernel<BN_, V_, M_>, tc::dw_smem_bytes<BN_>()); once = true; }     \
+        tc::dw_kernel<BN_, V_, M_><<<grid, tc::THREADS, tc::dw_smem_bytes<BN_>(), s>>>(a);                    \
+    } while (0)
+#define I2P_DW_V(BN_, M_) do { if (vec == 4) I2P_DW(BN_, 4, M_); else if (vec == 2) I2P_DW(BN_, 2, M_); else I2P_DW(BN_, 1, M_); } while (0)
+    if (bn == 64) { if (maxk) I2P_DW_V(64, true); else I2P_DW_V(64, false); }
+    else { if (maxk) I2P_DW_V(128, true); else I2P_DW_V(128, false); }
+#undef I2P_DW_V
+#undef I2P_DW
     return check_launch("pw_linear_bwd_dw_tc");
 }
 }

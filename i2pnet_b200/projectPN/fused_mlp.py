@@ -121,7 +121,7 @@ class FusedMLPFunction(Function):
         lib = _cabi.lib()
         tc_mask = lib.i2p_get_mlp_tensor_cores()
         packs = ctx.packs
-        if not reduce_k and grad_out.data_ptr() % 16:
+        if grad_out.data_ptr() % 16:
             grad_out = grad_out.clone()        # the tensor-core kernels read gradients with 128-bit loads
         g = None if reduce_k else grad_out
         c_last = ys[-1].shape[1]
@@ -133,12 +133,11 @@ class FusedMLPFunction(Function):
             cout, cin = w.shape
             inp = ys[l - 1] if l > 0 else x
             pst = stats[l - 1] if l > 0 else None
-            dense = not (l == L - 1 and reduce_k)     # the max-over-K source is routed through arg-max: FMA kernels
             pscale = _p(pst[2]) if pst is not None else None
             pshift = _p(pst[3]) if pst is not None else None
             pslope = float(slopes[l - 1]) if l > 0 else 1.0
-            if dense and (tc_mask & 4) and lib.i2p_pw_tc_supported(2, rows, cin, cout):
-                call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, g.data_ptr(), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
+            if (tc_mask & 4) and lib.i2p_pw_tc_supported(2, rows, cin, cout):
+                call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
                      pscale, pshift, pslope, dws[l].data_ptr())
             else:
                 call("i2p_pw_linear_bwd_dw", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
@@ -149,8 +148,8 @@ class FusedMLPFunction(Function):
                 dx = torch.empty(rows, cin, dtype=f32, device=dev)
                 prev = bn(l - 1) if l > 0 else (None, None, None, None, None, 1.0)
                 prev_s12 = s12[l - 1].data_ptr() if l > 0 else None
-                if dense and (tc_mask & 2) and packs[l] is not None and lib.i2p_pw_tc_supported(1, rows, cin, cout):
-                    call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, g.data_ptr(), *bn(l), s12[l].data_ptr(),
+                if (tc_mask & 2) and packs[l] is not None and lib.i2p_pw_tc_supported(1, rows, cin, cout):
+                    call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(),
                          packs[l].data_ptr(), dx.data_ptr(), *prev, prev_s12)
                 else:
                     call("i2p_pw_linear_bwd_dx", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), w.data_ptr(),

@@ -184,22 +184,23 @@ int i2p_pw_linear_bwd_dw(int rows, int cin, int cout, const float *g_dense, cons
  * Same algebra and tensors as i2p_pw_linear_fwd / _bwd_dx / _bwd_dw; the weight operand comes from a
  * per-layer pack (tf32 hi/lo halves in the UMMA shared-memory layout) written by i2p_pw_pack_weights.
  * Covered shapes: i2p_pw_tc_supported(kind, ...) with kind 0 forward, 1 dX, 2 dW (cout % 32 == 0,
- * cout >= 64; backward: cout <= 256, cin >= 32, dense gradient source).  Activation slopes in [0, 1].
+ * cout >= 64; backward: cout <= 256, cin >= 32; gradient source dense or max-over-k as in i2p_bn_bwd_reduce).
+ * Activation slopes in [0, 1].
  * All float tensors must be 16-byte aligned except x, which may be 4-byte aligned. */
 int i2p_pw_tc_supported(int kind, int rows, int cin, int cout);
 long long i2p_pw_pack_floats(int cin, int cout);
 int i2p_pw_pack_weights(int cin, int cout, const float *w, float *pack, void *stream);
 int i2p_pw_linear_fwd_tc(int rows, int cin, int cout, const float *x, const float *in_scale, const float *in_shift,
                          float in_slope, const float *wpack, const float *bias, float *y, float *tile_stats, void *stream);
-int i2p_pw_linear_bwd_dx_tc(int rows, int cin, int cout, const float *g_dense, const float *y, const float *mean,
-                            const float *rstd, const float *scale, const float *shift, float slope, const double *s12,
-                            const float *wpack, float *dx, const float *prev_y, const float *prev_mean,
-                            const float *prev_rstd, const float *prev_scale, const float *prev_shift, float prev_slope,
-                            double *prev_s12, void *stream);
-int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, const float *y, const float *mean,
-                            const float *rstd, const float *scale, const float *shift, float slope, const double *s12,
-                            const float *x, const float *prev_scale, const float *prev_shift, float prev_slope, float *dw,
-                            void *stream);
+int i2p_pw_linear_bwd_dx_tc(int rows, int cin, int cout, const float *g_dense, const float *dout, const int32_t *arg, int k,
+                            const float *y, const float *mean, const float *rstd, const float *scale, const float *shift,
+                            float slope, const double *s12, const float *wpack, float *dx, const float *prev_y,
+                            const float *prev_mean, const float *prev_rstd, const float *prev_scale, const float *prev_shift,
+                            float prev_slope, double *prev_s12, void *stream);
+int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, const float *dout, const int32_t *arg, int k,
+                            const float *y, const float *mean, const float *rstd, const float *scale, const float *shift,
+                            float slope, const double *s12, const float *x, const float *prev_scale, const float *prev_shift,
+                            float prev_slope, float *dw, void *stream);
 
 /* ---- RGB feature-pyramid block tail: replaces BatchNorm2d -> LeakyReLU(0.1) -> MaxPool2d(3, stride, 1)
  * of src/modules/basicConv.py:11-17 on the NCHW f32 output y (B,C,H,W) of the block's convolution.

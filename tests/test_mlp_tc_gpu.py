@@ -158,9 +158,9 @@ def test_backward_tc_matches_f64(shape):
         dw = torch.zeros(cout, cin, device=dev)
         ps12 = torch.zeros(2, cin, dtype=torch.float64, device=dev)
         if kind == "tc":
-            call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, lay.g.data_ptr(), lay.y.data_ptr(), *bn, s12.data_ptr(),
+            call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, lay.g.data_ptr(), None, None, 1, lay.y.data_ptr(), *bn, s12.data_ptr(),
                  pack.data_ptr(), dx.data_ptr(), *prev, ps12.data_ptr() if has_tf else None)
-            call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, lay.g.data_ptr(), lay.y.data_ptr(), *bn, s12.data_ptr(),
+            call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, lay.g.data_ptr(), None, None, 1, lay.y.data_ptr(), *bn, s12.data_ptr(),
                  lay.x.data_ptr(), psc, psh, lay.in_slope if has_tf else 1.0, dw.data_ptr())
         else:
             call("i2p_pw_linear_bwd_dx", dev, rows, cin, cout, lay.g.data_ptr(), None, None, 1, lay.y.data_ptr(), *bn,
@@ -202,3 +202,38 @@ def test_pack_layout_round_trips(operand_layout):
         want = float(wc[nn, k]) if nn < cout and k < cin else 0.0
         hi, lo = float(p[off]), float(p[off + bn * 32])
         assert abs(hi + lo - want) <= 5e-7 * abs(want) + 1e-12, (nn, k, hi, lo, want)
+
+
+@pytest.mark.parametrize("shape", [(29184, 64, 128, 16), (3712, 128, 256, 16), (14592, 128, 64, 8), (2400, 67, 64, 8)],
+                         ids=lambda s: "r%d_%dto%d_k%d" % s)
+def test_backward_tc_max_over_k_source_matches_fma(shape):
+    """Gradient arriving through a max-over-K output (dout + arg-max): tensor-core dX / dW against the FMA kernels."""
+    from i2pnet_b200 import _cabi
+    from i2pnet_b200._cabi import call
+    rows, cin, cout, K = shape
+    L = _cabi.lib()
+    lay = _Layer(rows, cin, cout, False, seed=rows + K)
+    dev = lay.x.device
+    gen = torch.Generator(device=dev).manual_seed(7)
+    dout = torch.randn(rows // K, cout, device=dev, generator=gen)
+    arg = torch.randint(0, K, (rows // K, cout), device=dev, generator=gen, dtype=torch.int32)
+    pack = torch.empty(L.i2p_pw_pack_floats(cin, cout), device=dev)
+    call("i2p_pw_pack_weights", dev, cin, cout, lay.w.data_ptr(), pack.data_ptr())
+    bn = _bn_args(lay.st, lay.slope)
+    s12 = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+    call("i2p_bn_bwd_reduce", dev, rows, cout, None, dout.data_ptr(), arg.data_ptr(), K, lay.y.data_ptr(), *bn, s12.data_ptr())
+    none_prev = (None, None, None, None, None, 1.0, None)
+    out = {}
+    for kind in ("tc", "fma"):
+        dx = torch.full((rows, cin), float("nan"), device=dev)
+        dw = torch.zeros(cout, cin, device=dev)
+        sfx = "_tc" if kind == "tc" else ""
+        src = (None, dout.data_ptr(), arg.data_ptr(), K)
+        call("i2p_pw_linear_bwd_dx" + sfx, dev, rows, cin, cout, *src, lay.y.data_ptr(), *bn, s12.data_ptr(),
+             pack.data_ptr() if kind == "tc" else lay.w.data_ptr(), dx.data_ptr(), *none_prev)
+        call("i2p_pw_linear_bwd_dw" + sfx, dev, rows, cin, cout, *src, lay.y.data_ptr(), *bn, s12.data_ptr(), lay.x.data_ptr(),
+             None, None, 1.0, dw.data_ptr())
+        out[kind] = (dx, dw)
+    for name, i in (("dx", 0), ("dw", 1)):
+        e = _rel(out["tc"][i], out["fma"][i].double())
+        assert e < 1e-5, (name, e)

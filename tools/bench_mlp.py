@@ -85,14 +85,14 @@ def main():
         res["dw_fma"] = timeit(lambda: call("i2p_pw_linear_bwd_dw", dev, rows, cin, cout, g.data_ptr(), None, None, 1, *bn,
                                             s12.data_ptr(), x.data_ptr(), psc, psh, 0.1 if has_tf else 1.0, dw.data_ptr()))
         if L.i2p_pw_tc_supported(1, rows, cin, cout):
-            res["dx_tc"] = timeit(lambda: call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, g.data_ptr(), *bn, s12.data_ptr(),
+            res["dx_tc"] = timeit(lambda: call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, g.data_ptr(), None, None, 1, *bn, s12.data_ptr(),
                                                pack.data_ptr(), dx.data_ptr(), *prev, pp))
             L.i2p_set_mlp_tensor_cores(23)
             call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr())
-            res["dx_tc_sw"] = timeit(lambda: call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, g.data_ptr(), *bn, s12.data_ptr(),
+            res["dx_tc_sw"] = timeit(lambda: call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, g.data_ptr(), None, None, 1, *bn, s12.data_ptr(),
                                                   pack.data_ptr(), dx.data_ptr(), *prev, pp))
             L.i2p_set_mlp_tensor_cores(7)
-            res["dw_tc"] = timeit(lambda: call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, g.data_ptr(), *bn, s12.data_ptr(),
+            res["dw_tc"] = timeit(lambda: call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, g.data_ptr(), None, None, 1, *bn, s12.data_ptr(),
                                                x.data_ptr(), psc, psh, 0.1 if has_tf else 1.0, dw.data_ptr()))
         t_mm = timeit(lambda: torch.addmm(b, x, w.t(), out=y))
         fb, bb = 4.0 * rows * (cin + cout), 4.0 * rows * (2 * cout + cin)

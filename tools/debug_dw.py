@@ -15,7 +15,7 @@ def run():
         st = torch.stack([torch.zeros(cout), torch.ones(cout), torch.ones(cout), torch.full((cout,), 10.0)]).to(dev).contiguous()
         s12 = torch.zeros(2, cout, dtype=torch.float64, device=dev)
         dw = torch.zeros(cout, cin, device=dev)
-        call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, g.data_ptr(), y.data_ptr(), st[0].data_ptr(), st[1].data_ptr(),
+        call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, g.data_ptr(), None, None, 1, y.data_ptr(), st[0].data_ptr(), st[1].data_ptr(),
              st[2].data_ptr(), st[3].data_ptr(), 0.1, s12.data_ptr(), x.data_ptr(), None, None, 1.0, dw.data_ptr())
         torch.cuda.synchronize()
         truth = (g.double().t() @ x.double())
@@ -33,7 +33,7 @@ def run():
             for (r_, i_, o_) in ((0, 0, 0), (1, 0, 0), (8, 0, 0), (0, 1, 0), (0, 4, 0), (0, 0, 1), (0, 0, 4), (9, 5, 6), (33, 17, 70 % cout)):
                 x.zero_(); g.zero_(); dw.zero_()
                 x[r_, i_] = 1.0; g[r_, o_] = 1.0
-                call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, g.data_ptr(), y.data_ptr(), st[0].data_ptr(), st[1].data_ptr(),
+                call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, g.data_ptr(), None, None, 1, y.data_ptr(), st[0].data_ptr(), st[1].data_ptr(),
                      st[2].data_ptr(), st[3].data_ptr(), 0.1, s12.data_ptr(), x.data_ptr(), None, None, 1.0, dw.data_ptr())
                 torch.cuda.synchronize()
                 nz = torch.nonzero(dw.abs() > 1e-3)
