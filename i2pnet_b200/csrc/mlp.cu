@@ -724,8 +724,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 2) pw_linear_bwd_dw_kernel(const 
     __shared__ __align__(16) float As[BK][LDA];  // [row r][o]
     __shared__ __align__(16) float Bs[BK][LDB];  // [row r][i]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * BMo, n0 = blockIdx.z * BNi;
-    const long long rb = (long long)blockIdx.x * a.rows_per_block;
+    // tile indices fastest: CTAs sharing a chunk of rows run together and re-read it from L2
+    const int m0 = blockIdx.x * BMo, n0 = blockIdx.y * BNi;
+    const long long rb = (long long)blockIdx.z * a.rows_per_block;
     const long long re = min((long long)a.rows, rb + a.rows_per_block);
     const int ac = tid % BMo, ar = tid / BMo, bc = tid % BNi, br = tid / BNi;
     const bool has_tf = a.prev.scale != nullptr;
@@ -804,7 +805,7 @@ static int launch_dw(DwArgs a, cudaStream_t s) {
     rpb = ((rpb + BK - 1) / BK) * BK;
     if (rpb < 8 * BK) rpb = 8 * BK;
     a.rows_per_block = rpb;
-    dim3 grid(ceil_div(a.rows, rpb), ceil_div(a.cout, BMo), ceil_div(a.cin, BNi));
+    dim3 grid(ceil_div(a.cout, BMo), ceil_div(a.cin, BNi), ceil_div(a.rows, rpb));
     pw_linear_bwd_dw_kernel<BMo, BNi, BK><<<grid, MLP_THREADS, sizeof(DyTables), s>>>(a);
     return check_launch("pw_linear_bwd_dw");
 }
@@ -819,7 +820,7 @@ static int g_mlp_tc = -1;
 static int mlp_tc_mask() {
     if (g_mlp_tc < 0) {
         const char *e = getenv("I2P_MLP_TC");
-        g_mlp_tc = (e == nullptr) ? 23 : atoi(e);
+        g_mlp_tc = (e == nullptr) ? 55 : atoi(e);
     }
     return g_mlp_tc;
 }

@@ -666,8 +666,11 @@ __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
     DyTab &tab = *reinterpret_cast<DyTab *>(smem + 2 * A_BYTES + 2 * B_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.z * BN;   // input-channel tile, output-channel tile
-    const long long rb = (long long)blockIdx.x * a.rows_per_block;
+    // tile index fastest: the CTAs that share a chunk of rows (every input-channel tile re-stages the same dY, every
+    // output-channel tile the same x) are scheduled together, so the re-reads hit L2 instead of HBM
+    const int mtiles = (a.cin + BM - 1) / BM;
+    const int m0 = (blockIdx.x % mtiles) * BM, n0 = (blockIdx.x / mtiles) * BN;   // input-channel tile, output-channel tile
+    const long long rb = (long long)blockIdx.y * a.rows_per_block;
     const long long re = min((long long)a.rows, rb + a.rows_per_block);
     load_dytab(tab, a.bn, a.s12, a.cout, a.rows);
     const uint32_t tmem_d = tc_prologue<BN>(&mma_bar, &tmem_slot);
@@ -920,7 +923,7 @@ int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, c
     if (rpb < 8 * tc::BK) rpb = 8 * tc::BK;
     a.rows_per_block = rpb;
     cudaStream_t s = as_stream(stream);
-    dim3 grid(ceil_div(rows, rpb), mt, ntl);
+    dim3 grid(mt * ntl, ceil_div(rows, rpb));
     const int vec = tc::vec_of(cin, x);
     const bool maxk = g_dense == nullptr;
 #define I2P_DW(BN_, V_, M_)                                                                                   \

@@ -136,7 +136,8 @@ class FusedMLPFunction(Function):
             pscale = _p(pst[2]) if pst is not None else None
             pshift = _p(pst[3]) if pst is not None else None
             pslope = float(slopes[l - 1]) if l > 0 else 1.0
-            if (tc_mask & 4) and lib.i2p_pw_tc_supported(2, rows, cin, cout):
+            on_tc = (tc_mask & 32) or not (l == L - 1 and reduce_k)      # bit 32: max-over-K sources on the tensor cores too
+            if on_tc and (tc_mask & 4) and lib.i2p_pw_tc_supported(2, rows, cin, cout):
                 call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
                      pscale, pshift, pslope, dws[l].data_ptr())
             else:
@@ -148,7 +149,7 @@ class FusedMLPFunction(Function):
                 dx = torch.empty(rows, cin, dtype=f32, device=dev)
                 prev = bn(l - 1) if l > 0 else (None, None, None, None, None, 1.0)
                 prev_s12 = s12[l - 1].data_ptr() if l > 0 else None
-                if (tc_mask & 2) and packs[l] is not None and lib.i2p_pw_tc_supported(1, rows, cin, cout):
+                if on_tc and (tc_mask & 2) and packs[l] is not None and lib.i2p_pw_tc_supported(1, rows, cin, cout):
                     call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(),
                          packs[l].data_ptr(), dx.data_ptr(), *prev, prev_s12)
                 else:

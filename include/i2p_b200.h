@@ -141,7 +141,8 @@ int i2p_project_seq(int b, int n, int H, int W, float fup_deg, float fdown_deg, 
  * f32-accurate, accumulator in TMEM), as a bit mask: 1 forward, 2 dX, 4 dW (the i2p_pw_*_tc entry points
  * below; the host consults this mask), 8 = the first-generation forward kernel inside i2p_pw_linear_fwd.
  * 16 = SWIZZLE_128B operand tiles + bulk-copied (TMA engine) weights in the forward / dX kernels.
- * Default: environment variable I2P_MLP_TC, else 23 (= 7 | 16).  0 = f32 FMA kernels everywhere. */
+ * 32 = the host also sends max-over-k gradient sources (dout + arg-max) to the tensor-core dX / dW kernels.
+ * Default: environment variable I2P_MLP_TC, else 55 (= 7 | 16 | 32).  0 = f32 FMA kernels everywhere. */
 void i2p_set_mlp_tensor_cores(int mask);
 int i2p_get_mlp_tensor_cores(void);
 /* Number of 128-row tiles (rows of the tile_stats buffer). */

@@ -23,11 +23,12 @@ def oracle_backend(monkeypatch):
     yield
 
 
-@pytest.fixture(params=[0, 7, 23], ids=["fma", "tcgen05", "tcgen05-sw128"])
+@pytest.fixture(params=[0, 7, 23, 55], ids=["fma", "tcgen05", "tcgen05-sw128", "tcgen05-sw128-maxk"])
 def tensor_cores(request):
     """The shared-MLP kernel families: f32 FMA (mask 0), tcgen05 tf32 with the 3-term hi/lo split for the
     forward, dX and dW GEMMs (mask 7), and the same with SWIZZLE_128B operand tiles + bulk-copied weights
-    (mask 7 | 16, include/i2p_b200.h)."""
+    (mask 7 | 16), and with max-over-K gradient sources on the
+    tensor cores as well (mask 7 | 16 | 32, the default; include/i2p_b200.h)."""
     from i2pnet_b200 import _cabi
     L = _cabi.lib()
     before = L.i2p_get_mlp_tensor_cores()
