@@ -74,3 +74,18 @@ def warp_quat_xyz(lidar_xyz, Hi_quat, H_trans):
     homo = torch.cat([lidar_xyz.new_zeros(B, N, 1), lidar_xyz], -1)
     homo = mul_q(mul_q(Hi_quat, homo), inv_q(Hi_quat)) + H_trans.reshape(B, 1, 4)
     return homo[:, :, 1:4]
+
+
+def warp_quat(lidar_xyz, Hi_quat, H_trans, cam_intrinsic, img_shape, LF):
+    """Small-range model (warp_utils.py:59-76): lidar_xyz (B,3,N) -> p' = q [0,p] q^-1 + [0,t], then the
+    normalised-plane position p' / (z' + 1e-10) (B,N,3), the depth z' (B,N,1) and LF unchanged."""
+    homo = warp_quat_xyz(lidar_xyz.permute(0, 2, 1), Hi_quat, H_trans)
+    lidar_z = homo[:, :, 2:]
+    return homo / (lidar_z + 1e-10), lidar_z, LF
+
+
+def projection_initial(lidar_xyz, Hi, cam_intrinsic, img_shape, LF):
+    """lidar_xyz (B,3,N) -> normalised-plane position p / z (B,N,3), depth (B,N,1), LF (warp_utils.py:146-155)"""
+    lidar_xyz = lidar_xyz.permute(0, 2, 1)
+    lidar_z = lidar_xyz[:, :, 2:3]
+    return lidar_xyz / lidar_z, lidar_z, LF

@@ -25,9 +25,11 @@ def _p(t):
 
 class FusedMLPFunction(Function):
     @staticmethod
-    def forward(ctx, x, reduce_k, slopes, eps, *params):
+    def forward(ctx, x, reduce_k, slopes, eps, trackers, *params):
         """x (rows, cin) f32 contiguous; params = (w_1 (c1,cin), b_1, gamma_1, beta_1, w_2, ...);
-        reduce_k: 0 -> out (rows, c_L); K > 0 -> out (rows / K, c_L) = max over each K consecutive rows."""
+        reduce_k: 0 -> out (rows, c_L); K > 0 -> out (rows / K, c_L) = max over each K consecutive rows.
+        trackers[l]: the BatchNorm module whose running statistics layer l updates (training mode of a
+        track_running_stats norm, as nn.BatchNorm2d does: momentum blend with the unbiased batch variance), or None."""
         dev = x.device
         rows = x.shape[0]
         L = len(params) // 4
@@ -59,6 +61,13 @@ class FusedMLPFunction(Function):
             call("i2p_bn_finalize", dev, rows, cout, tiles.data_ptr(), _ptr(gamma, f32, "gamma", dev),
                  _ptr(beta, f32, "beta", dev), float(eps[l]), st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(),
                  st[3].data_ptr())
+            bnm = trackers[l]
+            if bnm is not None:
+                mom = bnm.momentum if bnm.momentum is not None else 0.1
+                var = (1.0 / (st[1] * st[1]) - float(eps[l])).clamp_(min=0.0)       # biased batch variance back from rstd
+                bnm.running_mean.mul_(1.0 - mom).add_(st[0], alpha=mom)
+                bnm.running_var.mul_(1.0 - mom).add_(var, alpha=mom * rows / max(rows - 1, 1))
+                bnm.num_batches_tracked.add_(1)
             ys.append(y)
             stats.append(st)
             packs.append(pack)
@@ -162,25 +171,28 @@ class FusedMLPFunction(Function):
             grads[4 * l + 3] = gb[o12:o12 + couts[l]]
             grads[4 * l + 2] = gb[o12 + couts[l]:o12 + 2 * couts[l]]
             o12 += 2 * couts[l]
-        return (dx if ctx.needs_input_grad[0] else None, None, None, None, *grads)
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
 
 
 def fusable(convs):
-    """The fused path covers the configuration every model in the reference uses (use_bn_p,
-    use_bn_input: affine BatchNorm on batch statistics after every 1x1 conv)."""
-    return all(c.bn and not c.bn_linear.track_running_stats and c.bn_linear.affine and c.out_channels % 16 == 0
-               and c.out_channels <= 512 for c in convs)
+    """The fused path covers what the models in the reference use: an affine BatchNorm on batch statistics after
+    every 1x1 conv -- the large-range model's use_bn_input norms (never tracking), and the small-range model's
+    tracking norms while training (their running statistics are updated from the kernels' batch statistics).
+    A tracking norm in eval mode normalises with its running statistics: layer-by-layer path."""
+    return all(c.bn and c.bn_linear.affine and (c.bn_linear.training or not c.bn_linear.track_running_stats)
+               and c.out_channels % 16 == 0 and c.out_channels <= 512 for c in convs)
 
 
 def fused_mlp(x, convs, reduce_k=False):
     """x (..., [K,] cin) -> (..., [K,] c_L), or (..., c_L) with the max over the K axis when reduce_k."""
     lead = x.shape[:-1]
     x2 = x.reshape(-1, x.shape[-1]).contiguous()
-    params, slopes, eps = [], [], []
+    params, slopes, eps, trackers = [], [], [], []
     for c in convs:
+        trackers.append(c.bn_linear if c.bn_linear.track_running_stats and c.bn_linear.running_mean is not None else None)
         params += [c.conv.weight.view(c.out_channels, c.in_channels), c.conv.bias, c.bn_linear.weight, c.bn_linear.bias]
         slopes.append(1.0 if not c.activation_fn else (0.1 if c.leaky_relu else 0.0))
         eps.append(c.bn_linear.eps)
     k = int(lead[-1]) if reduce_k else 0
-    out = FusedMLPFunction.apply(x2, k, tuple(slopes), tuple(eps), *params)
+    out = FusedMLPFunction.apply(x2, k, tuple(slopes), tuple(eps), tuple(trackers), *params)
     return out.view(*(lead[:-1] if reduce_k else lead), out.shape[-1])

@@ -80,3 +80,35 @@ def make_pairs(batch, n_points=20480, image_hw=(160, 512), init_H=64, init_W=180
         out["q_gt"].append(_quat_from_matrix(Rr.T).astype(np.float32))
         out["t_gt"].append((-Rr.T @ tr).astype(np.float32))
     return {k: torch.from_numpy(np.stack(v)) for k, v in out.items()}
+
+
+def make_pairs_small(batch, n_points=8192, image_hw=(160, 512), seed=0, max_rot_deg=10.0, max_trans=1.0):
+    """Input contract of the small-range model (src/kitti_odometry_cmr.py: rgb, lidar, raw_point_xyz,
+    init_intrinsic, decalib_*_gt): the cloud is cropped to the camera frustum, in front of the camera, and
+    mis-calibrated by a small rotation / translation.  -> the same keys as make_pairs (lidar_feats is zeros).
+    Points: depth log-uniform in [3, 50] m, bearing uniform over the image's field of view."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    h, w = image_hw
+    f = 360.8
+    Pc = np.array([[0., -1., 0.], [0., 0., -1.], [1., 0., 0.]])      # LiDAR -> camera axes
+    deg = np.pi / 180.0
+    out = {k: [] for k in ("rgb", "lidar", "raw_point_xyz", "lidar_feats", "intrinsic", "q_gt", "t_gt")}
+    for _ in range(batch):
+        out["rgb"].append(rng.integers(0, 256, size=(3, h, w)).astype(np.float32))
+        z = np.exp(rng.uniform(np.log(3.0), np.log(50.0), size=n_points))
+        u = rng.uniform(-0.5 * w / f, 0.5 * w / f, size=n_points)
+        v = rng.uniform(-0.5 * h / f, 0.5 * h / f, size=n_points)
+        cam = np.stack([u * z, v * z, z], -1)
+        axis = rng.standard_normal(3)
+        axis /= np.linalg.norm(axis)
+        ang = rng.uniform(0.0, max_rot_deg) * deg
+        Kx = np.array([[0., -axis[2], axis[1]], [axis[2], 0., -axis[0]], [-axis[1], axis[0], 0.]])
+        Rr = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+        tr = rng.uniform(-max_trans, max_trans, size=3)
+        out["lidar"].append((cam @ Rr.T + tr).astype(np.float32))
+        out["raw_point_xyz"].append((cam @ Pc).astype(np.float32))    # Pc^-1 = Pc^T, row vectors: cam @ Pc
+        out["lidar_feats"].append(np.zeros((n_points, 1), np.float32))
+        out["intrinsic"].append(np.array([[f, 0., w / 2.0], [0., f, h / 2.0], [0., 0., 1.]], np.float32))
+        out["q_gt"].append(_quat_from_matrix(Rr.T).astype(np.float32))
+        out["t_gt"].append((-Rr.T @ tr).astype(np.float32))
+    return {k: torch.from_numpy(np.stack(v)) for k, v in out.items()}

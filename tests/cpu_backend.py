@@ -64,10 +64,14 @@ def group_points_grad(b, c, n, npoints, nsample, grad_out, idx, grad_points):
     grad_points.add_(torch.from_numpy(orc.group_points_grad(_np(grad_out), _np(idx), n)))
 
 
+def furthest_point_sampling(b, n, m, points, temp, idx):
+    _put(idx, orc.furthest_point_sample(_np(points), m))
+
+
 def patch(monkeypatch):
     from i2pnet_b200 import _cabi
     for name in ("select_k_flat", "fused_conv_select_k", "gather_rows", "gather_rows_grad", "knn_point",
-                 "project_seq", "group_points", "group_points_grad"):
+                 "project_seq", "group_points", "group_points_grad", "furthest_point_sampling"):
         monkeypatch.setattr(_cabi, name, globals()[name])
     from i2pnet_b200.projectPN import PPBackbone_center as P
     monkeypatch.setattr(P, "_batch_norm_rows", P._batch_norm_rows_stable)   # see its docstring

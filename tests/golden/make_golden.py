@@ -130,11 +130,59 @@ def golden_iter():
     _save("ref_model_iter_kitti_b2.npz", out3=out3, out4=out4)
 
 
+def golden_small():
+    """Forward + loss + backward of the reference's small-range RegNet_v2 (src/modellearn.py with
+    src/config_lidarcenter.py: 8192 points -> 2048 / 1024 / 256 / 64, 160x512 image), B = 2, training mode."""
+    import types
+    sys.modules.setdefault("cv2", types.ModuleType("cv2"))      # src/utils.py imports it; unused on this path
+    import compute_loss
+    from src.config_lidarcenter import I2PNetConfig as cfg
+    from src.modellearn import RegNet_v2
+    from i2pnet_b200.synthetic import make_pairs_small
+    torch.manual_seed(0)
+    model = RegNet_v2(cfg=cfg)
+    model.train()
+    for head in (model.l4_head, model.l3_head):
+        head.DP1.p = 0.0
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "bn" in n or (".1." in n and "RGB" in n) or ".5." in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    d = make_pairs_small(2, n_points=8192, seed=21)
+    inter = {}
+    for name in ("LiDAR_lv1", "LiDAR_lv3", "cost_volume1", "layer_idx", "set_upconv0_upsample", "cost_volume2"):
+        def hook(mod, args, out, name=name):
+            t = out[1] if isinstance(out, tuple) else out
+            inter["inter_" + name] = t.detach().clone()
+        getattr(model, name).register_forward_hook(hook)
+    out3, out4, _, _, sx, sq = model(d["rgb"], d["lidar"], None, d["intrinsic"], None, None, None, None, cfg=cfg,
+                                     lidar_img_raw=d["raw_point_xyz"])
+    loss, lq, lx = compute_loss.Get_loss(out3, out4, d["q_gt"], d["t_gt"], sx, sq, cfg)
+    loss.backward()
+    grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    names = sorted(grads)
+    keep = ["sq", "sx", "l3_head.quat_head.composed_module.0.weight", "cost_volume1.mlp1_convs.0.conv.weight",
+            "LiDAR_lv1.mlp_convs.0.weight", "RGB_net1.0.weight", "cost_volume2.pc_encoding.bn_linear.weight"]
+    inter["inter_LiDAR_lv1"] = inter["inter_LiDAR_lv1"][:, :, ::8]
+    after = {k: v for k, v in model.state_dict().items() if "running" in k and ("LiDAR_lv3" in k or "cost_volume1.mlp1_convs.0" in k)}
+    _save("ref_model_small_b2.npz",
+          rgb_u8=d["rgb"].to(torch.uint8), lidar=d["lidar"], raw_point_xyz=d["raw_point_xyz"], intrinsic=d["intrinsic"],
+          q_gt=d["q_gt"], t_gt=d["t_gt"], out3=out3, out4=out4, loss=loss, grad_names=np.array(names),
+          grad_norms=np.array([float(grads[n].norm()) for n in names]),
+          **{"grad__" + n: grads[n] for n in keep}, **{"state__" + k: v for k, v in state.items()},
+          **{"after__" + k: v for k, v in after.items()}, **inter)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "iter":
         golden_iter()
+    elif len(sys.argv) > 1 and sys.argv[1] == "small":
+        golden_small()
     else:
         golden_ops()
         golden_model()
         golden_iter()
+        golden_small()

@@ -1,0 +1,118 @@
+"""Small-range model (BASELINE.json configs[0] shapes: 160x512 image + 8192 points ->
+2048 / 1024 / 256 / 64): i2pnet_b200.modellearn.RegNet_v2 against the reference's own src/modellearn.py +
+src/config_lidarcenter.py, recorded by tests/golden/make_golden.py small (forward, loss, gradients, running
+statistics).  CPU: host logic on the oracle stand-ins; GPU: the sm_100a kernels."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLDEN
+from tests.test_host_logic_cpu import REL, _bias_cancelled_by_bn, _rel
+
+HOOKS = ("LiDAR_lv1", "LiDAR_lv3", "cost_volume1", "layer_idx", "set_upconv0_upsample", "cost_volume2")
+
+
+def load_golden():
+    g = np.load(os.path.join(GOLDEN, "ref_model_small_b2.npz"))
+    state = {k[len("state__"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state__")}
+    return g, state
+
+
+def build(state, device):
+    from i2pnet_b200.modellearn import RegNet_v2
+    model = RegNet_v2()
+    res = model.load_state_dict(state, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    model.train()
+    for head in (model.l4_head, model.l3_head):
+        head.DP1.p = 0.0
+    return model.to(device)
+
+
+def run(model, g, device):
+    from i2pnet_b200.compute_loss import Get_loss
+    from i2pnet_b200.config_lidarcenter import I2PNetConfig as cfg
+    t = lambda k: torch.from_numpy(g[k]).to(device)
+    inter = {}
+    for name in HOOKS:
+        def hook(mod, args, out, name=name):
+            inter[name] = (out[1] if isinstance(out, tuple) else out).detach()
+        getattr(model, name).register_forward_hook(hook)
+    out3, out4, pm3, pm4, sx, sq = model(torch.from_numpy(g["rgb_u8"]).float().to(device), t("lidar"), None, t("intrinsic"), None,
+                                         None, None, None, cfg=cfg, lidar_img_raw=t("raw_point_xyz"))
+    assert pm3 is None and pm4 is None
+    loss, _, _ = Get_loss(out3, out4, t("q_gt"), t("t_gt"), sx, sq, cfg)
+    loss.backward()
+    return out3, out4, loss, inter
+
+
+def check(model, g, out3, out4, loss, inter, tol=REL, grad_tol=5e-3):
+    inter["LiDAR_lv1"] = inter["LiDAR_lv1"][:, :, ::8]
+    for name, val in inter.items():
+        ref = g["inter_" + name]
+        assert _rel(val.cpu().reshape(ref.shape), ref) < tol, name
+    assert _rel(out4.detach().cpu(), g["out4"]) < tol
+    assert _rel(out3.detach().cpu(), g["out3"]) < tol
+    assert abs(float(loss.detach()) - float(g["loss"])) < tol * abs(float(g["loss"]))
+    grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    names = [str(n) for n in g["grad_names"]]
+    assert sorted(grads) == names
+    for n, ref_norm in zip(names, g["grad_norms"]):
+        mine = float(grads[n].norm())
+        if _bias_cancelled_by_bn(n) or (".mlp_convs." in n and n.endswith(".bias")):
+            assert mine < 1e-3, (n, mine)        # a bias in front of a batch-statistics norm: exactly zero, noise in autograd
+            continue
+        assert abs(mine - ref_norm) <= grad_tol * max(ref_norm, 1e-6) + 1e-7, (n, mine, ref_norm)
+    for k in g.files:
+        if k.startswith("grad__"):
+            assert _rel(grads[k[len("grad__"):]].cpu(), g[k]) < 10 * grad_tol, k
+    # the tracking norms blended the batch statistics into their running buffers like nn.BatchNorm2d does
+    sd = model.state_dict()
+    for k in g.files:
+        if k.startswith("after__"):
+            assert _rel(sd[k[len("after__"):]].cpu().float(), g[k]) < 1e-4, k
+
+
+def test_state_dict_matches_reference_layout():
+    g, state = load_golden()
+    from i2pnet_b200.modellearn import RegNet_v2
+    mine = RegNet_v2().state_dict()
+    assert list(mine.keys()) == list(state.keys())
+    assert all(mine[k].shape == state[k].shape for k in mine)
+
+
+def test_small_range_host_logic_matches_reference(oracle_backend):
+    g, state = load_golden()
+    model = build(state, "cpu")
+    check(model, g, *run(model, g, "cpu"))
+
+
+@pytest.mark.gpu
+def test_small_range_model_matches_reference_on_gpu():
+    assert torch.cuda.is_available()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    g, state = load_golden()
+    model = build(state, dev)
+    check(model, g, *run(model, g, dev))
+
+
+@pytest.mark.gpu
+def test_small_range_eval_mode_uses_running_statistics():
+    """eval(): the tracking norms normalise with their running buffers (layer-by-layer path) and leave them untouched."""
+    dev = torch.device("cuda:0")
+    from i2pnet_b200.config_lidarcenter import I2PNetConfig as cfg
+    g, state = load_golden()
+    model = build(state, dev).eval()
+    before = {k: v.clone() for k, v in model.state_dict().items() if "running" in k}
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    with torch.no_grad():
+        out3, out4, _, _, _, _ = model(torch.from_numpy(g["rgb_u8"]).float().to(dev), t("lidar"), None, t("intrinsic"), None, None,
+                                       None, None, cfg=cfg, lidar_img_raw=t("raw_point_xyz"))
+    assert torch.isfinite(out3).all() and torch.isfinite(out4).all()
+    assert abs(float(out3[:, :4].norm(dim=1).mean()) - 1.0) < 0.5
+    after = model.state_dict()
+    assert all(torch.equal(after[k], v) for k, v in before.items())
