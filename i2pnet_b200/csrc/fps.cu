@@ -30,12 +30,13 @@ constexpr int FPS_THREADS = 512;
 constexpr int FPS_WARPS = FPS_THREADS / 32;
 constexpr int FPS_MAX_CLUSTER = 16;
 
+// One record per warp and iteration: the warp winner's coordinates and index (16 bytes) and, in a separate array, its
+// (distance bits, tie key) pair (8 bytes).  The reduction over the records reads only the key array, with consecutive
+// lanes on consecutive 8-byte words -- conflict-free (32-byte records put lanes 8 words apart: an 8-way bank conflict
+// on every key load, ~1000 shared-memory cycles per iteration at 128 records).
 struct __align__(16) FpsRec {
     float x, y, z;
-    unsigned dbits;
-    unsigned tie;
     int k;
-    unsigned pad0, pad1;
 };
 
 struct FpsArgs {
@@ -57,7 +58,8 @@ template <int PPT, bool SMEM_XYZ>
 __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsArgs a) {
     extern __shared__ __align__(16) unsigned char fps_smem[];
     FpsRec *recs = reinterpret_cast<FpsRec *>(fps_smem);  // [2][FPS_WARPS * csize]
-    float *sx = reinterpret_cast<float *>(fps_smem + 2 * FPS_WARPS * FPS_MAX_CLUSTER * sizeof(FpsRec));
+    uint2 *keys = reinterpret_cast<uint2 *>(fps_smem + 2 * FPS_WARPS * FPS_MAX_CLUSTER * sizeof(FpsRec));  // same shape
+    float *sx = reinterpret_cast<float *>(fps_smem + 2 * FPS_WARPS * FPS_MAX_CLUSTER * (sizeof(FpsRec) + sizeof(uint2)));
     float *sy = sx + (SMEM_XYZ ? PPT * FPS_THREADS : 0);
     float *sz = sy + (SMEM_XYZ ? PPT * FPS_THREADS : 0);
 
@@ -144,13 +146,14 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsArgs a) {
         r.y = __shfl_sync(FULL, by, src);
         r.z = __shfl_sync(FULL, bz, src);
         r.k = __shfl_sync(FULL, kbase + pbest * FPS_THREADS, src);
-        r.dbits = wd;
-        r.tie = wt;  // 0xffffffff when this warp holds no real point
-        r.pad0 = r.pad1 = 0;
+        const uint2 key = make_uint2(wd, wt);  // tie 0xffffffff when this warp holds no real point
         FpsRec *buf = recs + (j & 1) * (FPS_WARPS * FPS_MAX_CLUSTER);
+        uint2 *kbuf = keys + (j & 1) * (FPS_WARPS * FPS_MAX_CLUSTER);
         if (lane < csize) {
             FpsRec *dst = csize > 1 ? cluster.map_shared_rank(buf, lane) : buf;
+            uint2 *kdst = csize > 1 ? cluster.map_shared_rank(kbuf, lane) : kbuf;
             dst[crank * FPS_WARPS + warp] = r;
+            kdst[crank * FPS_WARPS + warp] = key;
         }
         if (csize > 1) cluster.sync(); else __syncthreads();
 
@@ -158,7 +161,8 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsArgs a) {
         unsigned gd = 0, gt = 0xffffffffu;
         int gi = 0;
         for (int i = lane; i < nrec; i += 32) {
-            const unsigned d = buf[i].dbits, t = buf[i].tie;
+            const uint2 kv = kbuf[i];
+            const unsigned d = kv.x, t = kv.y;
             if (t != 0xffffffffu && (d > gd || (d == gd && t < gt))) { gd = d; gt = t; gi = i; }
         }
         const unsigned fd = __reduce_max_sync(FULL, gt != 0xffffffffu ? gd : 0u);
@@ -189,7 +193,7 @@ static int ref_block_size(int n) {
 
 template <int PPT, bool SMEM_XYZ>
 static int launch_fps(const FpsArgs &a, int b, int csize, cudaStream_t stream) {
-    const size_t smem = 2 * FPS_WARPS * FPS_MAX_CLUSTER * sizeof(FpsRec) +
+    const size_t smem = 2 * FPS_WARPS * FPS_MAX_CLUSTER * (sizeof(FpsRec) + sizeof(uint2)) +
                         (SMEM_XYZ ? (size_t)3 * PPT * FPS_THREADS * sizeof(float) : 0);
     auto kern = fps_kernel<PPT, SMEM_XYZ>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -246,6 +250,13 @@ extern "C" int i2p_furthest_point_sampling(int b, int n, int m, const float *dat
         const double waves = (double)((b * c + 147) / 148);
         const double cost = (40.0 * ppt + (c > 1 ? 550.0 : 150.0)) * waves;
         if (cost < best_cost) { best_cost = cost; best_c = c; best_ppt = ppt; }
+    }
+    static int forced = -1;   // I2P_FPS_CLUSTER=c: tuning override of the cluster size (measurements in profiles/)
+    if (forced < 0) { const char *e = getenv("I2P_FPS_CLUSTER"); forced = e ? atoi(e) : 0; }
+    if (forced > 0 && forced <= FPS_MAX_CLUSTER && (forced & (forced - 1)) == 0) {
+        int ppt = 1;
+        while ((long long)forced * FPS_THREADS * ppt < n) ppt *= 2;
+        if (ppt <= 32) { best_c = forced; best_ppt = ppt; }
     }
     if (best_c == 0) {
         set_error("furthest_point_sampling: n=%d exceeds the on-chip capacity of a 16-CTA cluster (262144)", n);
