@@ -59,9 +59,11 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsArgs a) {
     extern __shared__ __align__(16) unsigned char fps_smem[];
     FpsRec *recs = reinterpret_cast<FpsRec *>(fps_smem);  // [2][FPS_WARPS * csize]
     uint2 *keys = reinterpret_cast<uint2 *>(fps_smem + 2 * FPS_WARPS * FPS_MAX_CLUSTER * sizeof(FpsRec));  // same shape
+    // coordinates of this CTA's slice, [p][tid]: the winner's are read from here by index (no select chain over the
+    // register copies); with SMEM_XYZ (32 points per thread) the distance update reads them from here as well
     float *sx = reinterpret_cast<float *>(fps_smem + 2 * FPS_WARPS * FPS_MAX_CLUSTER * (sizeof(FpsRec) + sizeof(uint2)));
-    float *sy = sx + (SMEM_XYZ ? PPT * FPS_THREADS : 0);
-    float *sz = sy + (SMEM_XYZ ? PPT * FPS_THREADS : 0);
+    float *sy = sx + PPT * FPS_THREADS;
+    float *sz = sy + PPT * FPS_THREADS;
 
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
@@ -80,20 +82,19 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsArgs a) {
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
         const int k = kbase + p * FPS_THREADS;
-        float x = 0.f, y = 0.f, z = 0.f, t = 0.f;
+        // slots beyond the cloud keep a NEGATIVE running distance: min() leaves it negative for ever, so it never
+        // equals the (non-negative) warp maximum and needs no index test in the loop
+        float x = 0.f, y = 0.f, z = 0.f, t = -1.f;
         if (k < n) {
             x = data[(size_t)k * 3 + 0];
             y = data[(size_t)k * 3 + 1];
             z = data[(size_t)k * 3 + 2];
             t = temp[k];  // caller pre-fills 1e10 (pointnet2_utils.py:56)
         }
-        if (SMEM_XYZ) {
-            sx[p * FPS_THREADS + tid] = x;
-            sy[p * FPS_THREADS + tid] = y;
-            sz[p * FPS_THREADS + tid] = z;
-        } else {
-            px[p] = x; py[p] = y; pz[p] = z;
-        }
+        sx[p * FPS_THREADS + tid] = x;
+        sy[p * FPS_THREADS + tid] = y;
+        sz[p * FPS_THREADS + tid] = z;
+        if (!SMEM_XYZ) { px[p] = x; py[p] = y; pz[p] = z; }
         td[p] = t;
     }
 
@@ -118,29 +119,25 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsArgs a) {
             td[p] = d2;
             best = fmaxf(best, d2);
         }
-        // --- warp winner under (distance desc, tie_key asc)
+        // --- warp winner under (distance desc, tie_key asc).  Only the lanes that hold the warp maximum (one, unless
+        // distances tie exactly) look for the slots attaining it and evaluate their tie keys.
         const unsigned wd = __reduce_max_sync(FULL, __float_as_uint(best));
         unsigned tie = 0xffffffffu;
         int pbest = 0;
+        if (__float_as_uint(best) == wd) {
+            unsigned hit = 0;
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            const int k = kbase + p * FPS_THREADS;
-            if (__float_as_uint(td[p]) == wd && k < n) {
-                const unsigned tk = tie_key(k, a);
+            for (int p = 0; p < PPT; ++p) hit |= (__float_as_uint(td[p]) == wd) ? (1u << p) : 0u;
+            while (hit) {
+                const int p = __ffs(hit) - 1;
+                hit &= hit - 1;
+                const unsigned tk = tie_key(kbase + p * FPS_THREADS, a);
                 if (tk < tie) { tie = tk; pbest = p; }
             }
         }
         const unsigned wt = __reduce_min_sync(FULL, tie);
         const int src = __ffs(__ballot_sync(FULL, tie == wt)) - 1;  // tie keys are unique per point
-        float bx, by, bz;
-        if (SMEM_XYZ) {
-            bx = sx[pbest * FPS_THREADS + tid]; by = sy[pbest * FPS_THREADS + tid]; bz = sz[pbest * FPS_THREADS + tid];
-        } else {
-            bx = px[0]; by = py[0]; bz = pz[0];
-#pragma unroll
-            for (int p = 1; p < PPT; ++p)
-                if (p == pbest) { bx = px[p]; by = py[p]; bz = pz[p]; }
-        }
+        const float bx = sx[pbest * FPS_THREADS + tid], by = sy[pbest * FPS_THREADS + tid], bz = sz[pbest * FPS_THREADS + tid];
         FpsRec r;
         r.x = __shfl_sync(FULL, bx, src);
         r.y = __shfl_sync(FULL, by, src);
@@ -194,7 +191,7 @@ static int ref_block_size(int n) {
 template <int PPT, bool SMEM_XYZ>
 static int launch_fps(const FpsArgs &a, int b, int csize, cudaStream_t stream) {
     const size_t smem = 2 * FPS_WARPS * FPS_MAX_CLUSTER * (sizeof(FpsRec) + sizeof(uint2)) +
-                        (SMEM_XYZ ? (size_t)3 * PPT * FPS_THREADS * sizeof(float) : 0);
+                        (size_t)3 * PPT * FPS_THREADS * sizeof(float);
     auto kern = fps_kernel<PPT, SMEM_XYZ>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess && csize > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -247,8 +244,11 @@ extern "C" int i2p_furthest_point_sampling(int b, int n, int m, const float *dat
         while ((long long)c * FPS_THREADS * ppt < n) ppt *= 2;
         if (ppt > 32) continue;
         if (c == 16 && best_c != 0) continue;  // non-portable size only when nothing else fits
+        // cycles per sampling step, fitted to B200 measurements (profiles/r1_fps_cluster.md): a per-point term and the
+        // fixed chain of warp reductions + record exchange, which costs ~850 cycles more through a cluster barrier
         const double waves = (double)((b * c + 147) / 148);
-        const double cost = (40.0 * ppt + (c > 1 ? 550.0 : 150.0)) * waves;
+        const double fixed = c == 1 ? 920.0 : (c <= 4 ? 1770.0 : (c == 8 ? 2060.0 : 2400.0));
+        const double cost = ((ppt == 32 ? 90.0 : 60.0) * ppt + fixed) * waves;
         if (cost < best_cost) { best_cost = cost; best_c = c; best_ppt = ppt; }
     }
     static int forced = -1;   // I2P_FPS_CLUSTER=c: tuning override of the cluster size (measurements in profiles/)
