@@ -244,11 +244,11 @@ extern "C" int i2p_furthest_point_sampling(int b, int n, int m, const float *dat
         while ((long long)c * FPS_THREADS * ppt < n) ppt *= 2;
         if (ppt > 32) continue;
         if (c == 16 && best_c != 0) continue;  // non-portable size only when nothing else fits
-        // cycles per sampling step, fitted to B200 measurements (profiles/r1_fps_cluster.md): a per-point term and the
+        // cycles per sampling step, fitted to B200 measurements (profiles/r1_fps_cluster.txt): a per-point term and the
         // fixed chain of warp reductions + record exchange, which costs ~850 cycles more through a cluster barrier
         const double waves = (double)((b * c + 147) / 148);
-        const double fixed = c == 1 ? 920.0 : (c <= 4 ? 1770.0 : (c == 8 ? 2060.0 : 2400.0));
-        const double cost = ((ppt == 32 ? 90.0 : 60.0) * ppt + fixed) * waves;
+        const double fixed = c == 1 ? 1280.0 : (c <= 4 ? 1950.0 : (c == 8 ? 2400.0 : 2800.0));
+        const double cost = ((ppt == 32 ? 70.0 : 55.0) * ppt + fixed) * waves;
         if (cost < best_cost) { best_cost = cost; best_c = c; best_ppt = ppt; }
     }
     static int forced = -1;   // I2P_FPS_CLUSTER=c: tuning override of the cluster size (measurements in profiles/)

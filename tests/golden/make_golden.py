@@ -130,6 +130,49 @@ def golden_iter():
     _save("ref_model_iter_kitti_b2.npz", out3=out3, out4=out4)
 
 
+def golden_nus():
+    """Forward + loss + gradient norms of the reference RegNet_v2 at the nuScenes shape (BASELINE.json configs[3]:
+    320x640 image, 21x1800 range image of src/config_proj_lidarcenter_nus.py), B = 2, 20480 distinct cells."""
+    import compute_loss
+    from src.config_proj_lidarcenter_nus import I2PNetConfig as cfg
+    from src.modellearn_proj_center import RegNet_v2
+    cfg.efgh = False
+    torch.manual_seed(1)
+    model = RegNet_v2(cfg=cfg)
+    model.train()
+    for head in (model.l4_head, model.l3_head):
+        head.DP1.p = 0.0
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "bn" in n or (".1." in n and "RGB" in n) or ".5." in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    d = make_pairs(2, n_points=20480, image_hw=(320, 640), init_H=cfg.init_H, init_W=cfg.init_W, fup=cfg.fup, fdown=cfg.fdown,
+                   seed=13, occupy_centres=(cfg.stride_Hs[0], cfg.stride_Ws[0]))
+    inter = {}
+    for name in ("LiDAR_lv2", "LiDAR_lv3", "cost_volume1", "layer_idx", "set_upconv0_upsample", "cost_volume2"):
+        def hook(mod, args, out, name=name):
+            t = out[2] if isinstance(out, tuple) else out
+            inter["inter_" + name] = t.detach().clone()
+        getattr(model, name).register_forward_hook(hook)
+    out3, out4, _, _, sx, sq = model(d["rgb"], d["lidar"], d["raw_point_xyz"], None, d["intrinsic"], None, None,
+                                     None, d["lidar_feats"], cfg)
+    loss, lq, lx = compute_loss.Get_loss(out3, out4, d["q_gt"], d["t_gt"], sx, sq, cfg)
+    loss.backward()
+    grads = {n: p.grad for n, p in model.named_parameters()}
+    names = sorted(grads)
+    keep = ["sq", "sx", "l3_head.quat_head.composed_module.0.weight", "cost_volume1.mlp1_convs.0.conv.weight",
+            "LiDAR_lv1.mlp_convs.0.conv.weight", "cost_volume2.pc_encoding.bn_linear.weight"]
+    inter["inter_LiDAR_lv2"] = inter["inter_LiDAR_lv2"][:, ::2, ::7]
+    _save("ref_model_nus_b2.npz",
+          rgb_u8=d["rgb"].to(torch.uint8), lidar=d["lidar"], raw_point_xyz=d["raw_point_xyz"],
+          lidar_feats=d["lidar_feats"], intrinsic=d["intrinsic"], q_gt=d["q_gt"], t_gt=d["t_gt"],
+          out3=out3, out4=out4, loss=loss, grad_names=np.array(names),
+          grad_norms=np.array([float(grads[n].norm()) for n in names]),
+          **{"grad__" + n: grads[n] for n in keep}, **{"state__" + k: v for k, v in state.items()}, **inter)
+
+
 def golden_small():
     """Forward + loss + backward of the reference's small-range RegNet_v2 (src/modellearn.py with
     src/config_lidarcenter.py: 8192 points -> 2048 / 1024 / 256 / 64, 160x512 image), B = 2, training mode."""
@@ -181,8 +224,11 @@ if __name__ == "__main__":
         golden_iter()
     elif len(sys.argv) > 1 and sys.argv[1] == "small":
         golden_small()
+    elif len(sys.argv) > 1 and sys.argv[1] == "nus":
+        golden_nus()
     else:
         golden_ops()
         golden_model()
         golden_iter()
         golden_small()
+        golden_nus()
