@@ -8,8 +8,6 @@ assembly exists because the reference file forces one host round-trip per forwar
 of which keep the step from being captured into a CUDA graph; here the whole forward is
 asynchronous on the current stream.
 """
-import os
-
 import numpy as np
 import torch
 import torch.nn as nn
@@ -19,6 +17,7 @@ from .modules import warp_utils
 from .modules.basicConv import createCNNs
 from .projectPN.PPBackbone_center import CostVolume, FlowPredictor, PoseHead, ProjectPointNet, ProjSetUpconvModule
 from .projectPN.utils import StrideGrid, check_valid, inverse3x3, project_seq
+from .streams import Fork
 
 
 def set_id_grid(rf):
@@ -36,17 +35,6 @@ def change_intrinsic(intrinsic, RF, rgb_img):
     # row scaling only (no host tensor: the forward must stay capturable into a CUDA graph);
     # K[0,1] and K[1,0] are zero for a pinhole intrinsic, as the reference assumes too
     return torch.cat([intrinsic[:, 0:1] * sx, intrinsic[:, 1:2] * sy, intrinsic[:, 2:3]], dim=1)
-
-
-RGB_SIDE_STREAM = os.environ.get("I2P_RGB_STREAM", "1") != "0"   # image branch on its own stream (see _coarse)
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(torch.device("cuda", key))
-    return _SIDE_STREAMS[key]
 
 
 def _mask_fill(x, valid):
@@ -135,18 +123,9 @@ class RegNet_v2(nn.Module):
         N = lidar_img.shape[1]
         rfkw = dict(cfg=cfg, raw_feat_point=cfg.raw_feat_point)
 
-        # The image pyramid and the LiDAR pyramid are independent up to the first cost volume.  On CUDA the image
-        # branch is issued on a side stream (forked from / joined back into the current one, so it is captured into
-        # the same CUDA graph); autograd replays each branch's backward on the stream of its forward, so the two
-        # backward chains overlap as well.  Most kernels of either branch fill only part of the 148 SMs.
-        side = _side_stream(dev) if (RGB_SIDE_STREAM and rgb_img.is_cuda) else None
-        if side is not None:
-            main = torch.cuda.current_stream(dev)
-            side.wait_stream(main)
-            rgb_img.record_stream(side)
-            with torch.cuda.stream(side):
-                RF3 = self.RGB_net3(self.RGB_net2(self.RGB_net1(rgb_img)))
-        else:
+        # The image pyramid and the LiDAR pyramid are independent up to the first cost volume: the image branch goes
+        # to a side stream (streams.py), joined right before its output is first read.
+        with Fork(rgb_img) as rgb_branch:
             RF3 = self.RGB_net3(self.RGB_net2(self.RGB_net1(rgb_img)))
 
         lidar_norm = torch.zeros(B, N, 3, device=dev) if lidar_feature is None else lidar_feature
@@ -160,9 +139,7 @@ class RegNet_v2(nn.Module):
         P3_raw, P3, LF3, _, _ = self.LiDAR_lv3(P2_raw, P2, LF2, **rfkw)
         P4_raw, P4, LF4, _, sample_idx_4 = self.LiDAR_lv4(P3_raw, P3, LF3, **rfkw)
 
-        if side is not None:
-            main.wait_stream(side)
-            RF3.record_stream(main)
+        RF3 = rgb_branch.join(RF3)
         # pixel centres of RF3 on the normalised camera plane: K3^-1 [u, v, 1]
         K3_inv = inverse3x3(change_intrinsic(intrinsic, RF3, rgb_img))
         RF3_index = torch.bmm(K3_inv, set_id_grid(RF3.permute(0, 2, 3, 1)).permute(0, 2, 1)).permute(0, 2, 1)
@@ -186,8 +163,11 @@ class RegNet_v2(nn.Module):
                                  LF4.view(B, H4 * W4, -1), None)
         result_4 = torch.cat([q4, t4], dim=1)
 
-        l3_w_up = self.set_upconv0_w_upsample(P3_raw, P4_raw, P3, P4, l3_grid, LF3, l4_w.view(B, H4, W4, -1), **rfkw)
+        l4_w_img = l4_w.view(B, H4, W4, -1)
+        with Fork(P3_raw, P4_raw, P3, P4, LF3, l4_w_img) as up_branch:      # the two up-convolutions are independent
+            l3_w_up = self.set_upconv0_w_upsample(P3_raw, P4_raw, P3, P4, l3_grid, LF3, l4_w_img, **rfkw)
         l3_up = self.set_upconv0_upsample(P3_raw, P4_raw, P3, P4, l3_grid, LF3, l4_points_predict, **rfkw)
+        l3_w_up = up_branch.join(l3_w_up)
         return dict(B=B, H3W3=H3 * W3, P3_raw=P3_raw, P3_l4=P3_l4, P4=P4, LF3_cv=LF3_cv, l3_grid=l3_grid,
                     RF3_index=RF3_index, RF3=RF3, l3_w_up=l3_w_up, l3_up=l3_up, q4=q4, t4=t4, result_4=result_4)
 

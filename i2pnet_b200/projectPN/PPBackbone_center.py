@@ -22,6 +22,7 @@ import torch.nn.functional as F
 
 from ..modules.basicConv import Conv1d
 from . import fused_mlp as _fm
+from ..streams import Fork
 from .utils import (FLAG_COPY, FLAG_SHIFT, StrideGrid, check_valid, gather_rows, gather_torch, knn_point,
                     select_flat)
 
@@ -383,23 +384,29 @@ class CostVolume(nn.Module):
         else:
             pi_feat1_new, pi_xyz_diff_concat, warped_xyz = self._first_layer_operand(warped_xyz, warped_points, f2_xyz,
                                                                                  f2_points, lidar_z)
+        # The neighbourhoods and the position encoding of the second stage depend on the coordinates alone, the
+        # pixel-pair encoding on xyz6 alone: both run beside the feature MLP of the first stage (streams.py).
+        warped_xyz_bhw = warped_xyz.view(B, self.H, self.W, 3)
+        xyz_pr = warped_xyz_bhw if self.use_trans else xyz_proj_raw
+        with Fork(warped_xyz, xyz_pr) as pc_branch:
+            flat, valid_mask = select_flat(xyz_pr, xyz_pr, idx_n2, self.kernel_size, self.nsample, FLAG_SHIFT,
+                                           self.distance)
+            pc_xyz_grouped = gather_rows(warped_xyz_bhw, flat)           # B,N,K,3
+            pc_xyz_new = warped_xyz[:, :, None, :].expand(-1, -1, self.nsample, -1)
+            pc_xyz_diff = pc_xyz_grouped - pc_xyz_new
+            pc_euc_diff = torch.sqrt(torch.sum(pc_xyz_diff * pc_xyz_diff, dim=3, keepdim=True) + 1e-20)
+            pc_xyz_encoding = self.pc_encoding(torch.cat([pc_xyz_new, pc_xyz_grouped, pc_xyz_diff, pc_euc_diff], dim=3))
+        with Fork(pi_xyz_diff_concat) as pi_branch:
+            pi_xyz_encoding = self.pi_encoding(pi_xyz_diff_concat)
         pi_feat1_new = run_mlp(self.mlp1_convs, pi_feat1_new)
-        pi_concat = torch.cat([self.pi_encoding(pi_xyz_diff_concat), pi_feat1_new], dim=3)
+        pi_concat = torch.cat([pi_branch.join(pi_xyz_encoding), pi_feat1_new], dim=3)
         pi_concat = run_mlp(self.mlp2_convs, pi_concat)
         pi_feat1_new = _softmax_wsum(pi_concat, pi_feat1_new)        # B,N,mlp1[-1]
 
         # second stage: re-weight over the nsample 3-D neighbours of every point
-        warped_xyz_bhw = warped_xyz.view(B, self.H, self.W, 3)
-        xyz_pr = warped_xyz_bhw if self.use_trans else xyz_proj_raw
-        flat, valid_mask = select_flat(xyz_pr, xyz_pr, idx_n2, self.kernel_size, self.nsample, FLAG_SHIFT,
-                                       self.distance)
-        pc_xyz_grouped = gather_rows(warped_xyz_bhw, flat)           # B,N,K,3
+        flat, valid_mask, pc_xyz_encoding = pc_branch.join(flat, valid_mask, pc_xyz_encoding)
         pc_points_grouped = gather_rows(pi_feat1_new, flat)          # B,N,K,mlp1[-1]
-        pc_xyz_new = warped_xyz[:, :, None, :].expand(-1, -1, self.nsample, -1)
         pc_points_new = warped_points[:, :, None, :].expand(-1, -1, self.nsample, -1)
-        pc_xyz_diff = pc_xyz_grouped - pc_xyz_new
-        pc_euc_diff = torch.sqrt(torch.sum(pc_xyz_diff * pc_xyz_diff, dim=3, keepdim=True) + 1e-20)
-        pc_xyz_encoding = self.pc_encoding(torch.cat([pc_xyz_new, pc_xyz_grouped, pc_xyz_diff, pc_euc_diff], dim=3))
         pc_concat = torch.cat([pc_xyz_encoding, pc_points_new, pc_points_grouped], dim=-1)
         pc_concat = run_mlp(self.mlp2_convs_2, pc_concat)
         pc_feat1_new = _softmax_wsum(pc_concat, pc_points_grouped, valid_mask)

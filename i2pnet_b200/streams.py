@@ -1,0 +1,68 @@
+"""Branch-level concurrency: independent sub-graphs of the forward are issued on side CUDA streams.
+
+Most kernels of this network (everything at pyramid levels 2-4, the second cost-volume stage, the heads) occupy a
+fraction of the 148 SMs, and the step is a long chain of them.  Where the data flow forks -- image pyramid vs LiDAR
+pyramid, the two up-convolutions, the position encodings of a cost volume vs its feature MLP -- one side of the fork
+is issued on another stream, forked from and joined back into the current one with events, so that it is captured
+into the same CUDA graph (and, in eager mode, simply overlaps).  Autograd replays every backward function on the
+stream its forward ran on and inserts the cross-stream waits itself, so the backward chains overlap as well.
+
+Memory safety with the caching allocator: tensors produced on one stream and consumed on the other are
+`record_stream`-ed on the consumer (inputs at the fork, outputs at the join).
+
+    with Fork(x, y) as f:          # x, y: tensors the branch reads
+        z = branch(x, y)           # issued on a side stream
+    w = other_work()               # current stream, concurrent with the branch
+    z = f.join(z)                  # the current stream waits for the branch
+"""
+import os
+
+import torch
+
+ENABLED = os.environ.get("I2P_STREAMS", "1") != "0"
+_POOL_SIZE = 4
+_pools = {}
+
+
+def _side_stream(device, avoid):
+    pool = _pools.setdefault(device.index, {"streams": [torch.cuda.Stream(device) for _ in range(_POOL_SIZE)], "next": 0})
+    for _ in range(_POOL_SIZE):
+        s = pool["streams"][pool["next"]]
+        pool["next"] = (pool["next"] + 1) % _POOL_SIZE
+        if s != avoid:
+            return s
+    raise RuntimeError("no side stream available")
+
+
+class Fork:
+    def __init__(self, *inputs, enabled=True):
+        self.inputs = [t for t in inputs if isinstance(t, torch.Tensor) and t.is_cuda]
+        self.on = ENABLED and enabled and len(self.inputs) > 0
+        self.ctx = None
+
+    def __enter__(self):
+        if self.on:
+            dev = self.inputs[0].device
+            self.main = torch.cuda.current_stream(dev)
+            self.side = _side_stream(dev, self.main)
+            self.side.wait_stream(self.main)
+            for t in self.inputs:
+                t.record_stream(self.side)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+        return False
+
+    def join(self, *outputs):
+        """Make the stream that was current at the fork wait for the branch; -> the outputs (one, or a tuple)."""
+        if self.on:
+            self.main.wait_stream(self.side)
+            for t in outputs:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(self.main)
+        return outputs[0] if len(outputs) == 1 else outputs
