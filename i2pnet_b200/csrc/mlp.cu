@@ -810,6 +810,112 @@ static int launch_dw(DwArgs a, cudaStream_t s) {
     return check_launch("pw_linear_bwd_dw");
 }
 
+// dW for skinny layers (cin <= 16; cout tile CO = 16 / 32 / 64): the output tile is so small that the kernel above
+// spends two shared-memory loads per two FMAs.  Here a thread owns a 4 x 4 block of the tile (two LDS.128 per 16 FMAs),
+// CO threads cover the tile, and the 256 / CO groups of the CTA take every (256 / CO)-th staged row; the groups' partial
+// tiles meet in shared memory at the end.  Same operands, staging and epilogue (atomics into dW) as the general kernel.
+template <int CO>
+__global__ void __launch_bounds__(MLP_THREADS, 2) pw_linear_bwd_dw_skinny_kernel(const DwArgs a) {
+    constexpr int CI = 16, BK = 64, T = CO, KG = MLP_THREADS / T, LDA = CO + 4, LDB = CI + 4;
+    constexpr int APT = BK * CO / MLP_THREADS, BPT = BK * CI / MLP_THREADS;
+    constexpr int AROWS = MLP_THREADS / CO, BROWS = MLP_THREADS / CI;
+    constexpr int STAGE_FLOATS = BK * LDA + BK * LDB, RED_FLOATS = KG * CO * CI;
+    constexpr int BUF_FLOATS = STAGE_FLOATS > RED_FLOATS ? STAGE_FLOATS : RED_FLOATS;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    DyTables &tab = *reinterpret_cast<DyTables *>(dyn_smem);
+    __shared__ __align__(16) float buf[BUF_FLOATS];
+    float (*As)[LDA] = reinterpret_cast<float (*)[LDA]>(buf);             // [row][o]
+    float (*Bs)[LDB] = reinterpret_cast<float (*)[LDB]>(buf + BK * LDA);  // [row][i]
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * CO;
+    const long long rb = (long long)blockIdx.y * a.rows_per_block;
+    const long long re = min((long long)a.rows, rb + a.rows_per_block);
+    const int ac = tid % CO, ar = tid / CO, bc = tid % CI, br = tid / CI;
+    const int t = tid % T, kg = tid / T, to = t / (CI / 4), ti = t % (CI / 4);
+    const bool has_tf = a.prev.scale != nullptr;
+    load_dy_tables(tab, a.bn, a.s12, a.cout, a.rows);
+    float bsc = 1.f, bsh = 0.f;
+    if (has_tf && bc < a.cin) { bsc = __ldg(a.prev.scale + bc); bsh = __ldg(a.prev.shift + bc); }
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    RawDy pa[APT];
+    float pb[BPT];
+    auto fetch = [&](long long rr0) {
+#pragma unroll
+        for (int i = 0; i < APT; ++i) {
+            const long long r = rr0 + ar + AROWS * i;
+            if (r < re && m0 + ac < a.cout) pa[i] = fetch_dy(a.gs, a.bn.y, r, m0 + ac, a.cout);
+        }
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const long long r = rr0 + br + BROWS * i;
+            pb[i] = (r < re && bc < a.cin) ? __ldg(a.x + (size_t)r * a.cin + bc) : 0.f;
+        }
+    };
+    auto stage = [&](long long rr0) {
+#pragma unroll
+        for (int i = 0; i < APT; ++i)
+            As[ar + AROWS * i][ac] = (rr0 + ar + AROWS * i < re && m0 + ac < a.cout)
+                                         ? finish_dy(tab, pa[i], m0 + ac, a.bn.slope) : 0.f;
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            float v = pb[i];
+            if (has_tf) v = (rr0 + br + BROWS * i < re && bc < a.cin) ? act_fwd(__fmaf_rn(v, bsc, bsh), a.prev.slope) : 0.f;
+            Bs[br + BROWS * i][bc] = v;
+        }
+    };
+
+    fetch(rb);
+    for (long long rr0 = rb; rr0 < re; rr0 += BK) {
+        __syncthreads();
+        stage(rr0);
+        __syncthreads();
+        if (rr0 + BK < re) fetch(rr0 + BK);
+#pragma unroll
+        for (int k = kg; k < BK; k += KG) {
+            const float4 av = *reinterpret_cast<const float4 *>(&As[k][4 * to]);
+            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k][4 * ti]);
+            const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(a4[i], b4[j], acc[i][j]);
+        }
+    }
+    __syncthreads();   // staging buffers are dead: they become the partial-tile exchange
+    float *red = buf;  // [kg][o][i]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4 *>(&red[(kg * CO + 4 * to + i) * CI + 4 * ti]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();
+    for (int e = tid; e < CO * CI; e += MLP_THREADS) {
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < KG; ++g) sum += red[g * CO * CI + e];
+        const int o = m0 + e / CI, ci = e % CI;
+        if (o < a.cout && ci < a.cin) atomicAdd(a.dw + (size_t)o * a.cin + ci, sum);
+    }
+}
+
+template <int CO>
+static int launch_dw_skinny(DwArgs a, cudaStream_t s) {
+    constexpr int BK = 64;
+    const int tiles = ceil_div(a.cout, CO);
+    const int chunks = (4 * 148 + tiles - 1) / tiles;     // two waves of CTAs at 2 per SM
+    int rpb = (a.rows + chunks - 1) / chunks;
+    rpb = ((rpb + BK - 1) / BK) * BK;
+    if (rpb < 4 * BK) rpb = 4 * BK;
+    a.rows_per_block = rpb;
+    dim3 grid(tiles, ceil_div(a.rows, rpb));
+    pw_linear_bwd_dw_skinny_kernel<CO><<<grid, MLP_THREADS, sizeof(DyTables), s>>>(a);
+    return check_launch("pw_linear_bwd_dw(skinny)");
+}
+
 static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : 64); }
 
 // Which shared-MLP GEMMs run on the tensor cores (tcgen05, 3xTF32; kernels in mlp_tc.cu), as a bit mask:
@@ -955,6 +1061,13 @@ int i2p_pw_linear_bwd_dw(int rows, int cin, int cout, const float *g_dense, cons
     a.prev = BnRef{nullptr, nullptr, nullptr, prev_scale, prev_shift, prev_slope};
     a.dw = dw;
     cudaStream_t st = as_stream(stream);
+    static int skinny = -1;   // I2P_DW_SKINNY=0: the general tile kernel for cin <= 16 as well (A/B measurements)
+    if (skinny < 0) { const char *e = getenv("I2P_DW_SKINNY"); skinny = e ? atoi(e) : 1; }
+    if (cin <= 16 && skinny) {
+        if (cout <= 16) return launch_dw_skinny<16>(a, st);
+        if (cout <= 32) return launch_dw_skinny<32>(a, st);
+        return launch_dw_skinny<64>(a, st);
+    }
     if (cout <= 16) return cin <= 16 ? launch_dw<16, 16, 64>(a, st) : launch_dw<16, 64, 32>(a, st);
     if (cout <= 32) return cin <= 16 ? launch_dw<32, 16, 32>(a, st) : launch_dw<32, 64, 32>(a, st);
     return cin <= 16 ? launch_dw<64, 16, 32>(a, st) : launch_dw<64, 64, 16>(a, st);

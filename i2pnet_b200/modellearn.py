@@ -18,8 +18,9 @@ from .modules import warp_utils
 from .modules.basicConv import createCNNs
 from .modules.MainModules import CostVolume, DelayWeight, FlowPredictor, PoseHead, ProjectMask
 from .modules.pointnet2_module import SetUpconvModule
-from .pointnet_util import PointNetSetAbstraction, index_points
+from .pointnet_util import PointNetSetAbstraction, farthest_point_sample, index_points
 from .projectPN.utils import inverse3x3
+from .streams import Fork
 
 
 class RegNet_v2(nn.Module):
@@ -88,8 +89,8 @@ class RegNet_v2(nn.Module):
         intrinsic = intrinsic.float()
         B = rgb_img.shape[0]
         N = lidar_img.shape[1]
-        RF3 = self.RGB_net3(self.RGB_net2(self.RGB_net1(rgb_img)))
-        RF3_index = set_id_grid(RF3.permute(0, 2, 3, 1))                  # B,h3*w3,3 pixel coordinates
+        with Fork(rgb_img) as rgb_branch:          # image pyramid beside the (sequential, FPS-bound) point pyramid: streams.py
+            RF3 = self.RGB_net3(self.RGB_net2(self.RGB_net1(rgb_img)))
 
         lidar_img = lidar_img.permute(0, 2, 1).float()
         if lidar_feature is None:
@@ -98,12 +99,32 @@ class RegNet_v2(nn.Module):
             lidar_norm = lidar_feature.permute(0, 2, 1).float()
         raw = dict(raw_feat_point=cfg.raw_feat_point)
         lv1 = dict(feat_mode=cfg.featmode) if cfg.featmode is not None else {}
-        P1, LF1, _, fps_idx_1, P1_raw = self.LiDAR_lv1(lidar_img, lidar_norm, raw_xyz=lidar_img_raw, **lv1, **raw)
-        P2, LF2, _, fps_idx_2, P2_raw = self.LiDAR_lv2(P1, LF1, raw_xyz=P1_raw, **raw)
-        P3, LF3, _, fps_idx_3, P3_raw = self.LiDAR_lv3(P2, LF2, raw_xyz=P2_raw, **raw)
-        P4, LF4, _, fps_idx_4, P4_raw = self.LiDAR_lv4(P3, LF3, raw_xyz=P3_raw, **raw)
+        # Furthest point sampling is a chain of M dependent steps per level (~1 us each) and depends on coordinates
+        # only: the four samplings run back to back on a side stream, one level ahead of the grouping + shared MLP of the
+        # previous level on the current stream (same indices as sampling inside each level, :183 of pointnet_util.py).
+        levels = [self.LiDAR_lv1, self.LiDAR_lv2, self.LiDAR_lv3, self.LiDAR_lv4]
+        xyz0 = lidar_img.permute(0, 2, 1).contiguous()
+        fps = Fork(xyz0)
+
+        def sample(xyz, npoint):
+            with fps:
+                idx = farthest_point_sample(xyz, npoint)
+                return idx, index_points(xyz, idx)
+        idx_next, xyz_next = fps.join(*sample(xyz0, levels[0].npoint))
+        xyz_l, feat_l, raw_l, outs = lidar_img, lidar_norm, lidar_img_raw, []
+        for lv, level in enumerate(levels):
+            idx_cur = idx_next
+            if lv + 1 < len(levels):
+                ahead = sample(xyz_next, levels[lv + 1].npoint)              # issued before this level's own work
+            xyz_l, feat_l, _, _, raw_l = level(xyz_l, feat_l, sample_idx=idx_cur, raw_xyz=raw_l, **(lv1 if lv == 0 else {}), **raw)
+            outs.append((xyz_l, feat_l, idx_cur, raw_l))
+            if lv + 1 < len(levels):
+                idx_next, xyz_next = fps.join(*ahead)
+        (P1, LF1, fps_idx_1, P1_raw), (P2, LF2, fps_idx_2, P2_raw), (P3, LF3, fps_idx_3, P3_raw), (P4, LF4, fps_idx_4, P4_raw) = outs
 
         # pixels on the normalised camera plane
+        RF3 = rgb_branch.join(RF3)
+        RF3_index = set_id_grid(RF3.permute(0, 2, 3, 1))                  # B,h3*w3,3 pixel coordinates
         intrinsic_3_inv = inverse3x3(change_intrinsic(intrinsic, RF3, rgb_img))
         RF3_index = torch.bmm(intrinsic_3_inv, RF3_index.permute(0, 2, 1)).permute(0, 2, 1)
         lidar_uv, lidar_z, LF3 = warp_utils.projection_initial(P3, None, None, None, LF3)
@@ -141,8 +162,10 @@ class RegNet_v2(nn.Module):
         lidar_uv, lidar_z, LF3 = warp_utils.warp_quat(P3, q4, t4_quat, None, None, LF3)
         concat_3 = self.cost_volume2(lidar_uv, LF3_t, RF3_index, RF3, lidar_z)
         up = dict(raw_feat_point=True, raw_xyz1=P3_raw, raw_xyz2=P4_raw) if cfg.raw_feat_point else {}
-        l3_cost_volume_w_upsample = self.set_upconv0_w_upsample(P3_t, P4_t, LF3_t, l4_cost_volume_w, **up)
+        with Fork(P3_t, P4_t, LF3_t, l4_cost_volume_w, P3_raw, P4_raw) as up_branch:     # independent up-convolutions
+            l3_cost_volume_w_upsample = self.set_upconv0_w_upsample(P3_t, P4_t, LF3_t, l4_cost_volume_w, **up)
         l3_cost_volume_upsample = self.set_upconv0_upsample(P3_t, P4_t, LF3_t, l4_points_predict, **up)
+        l3_cost_volume_w_upsample = up_branch.join(l3_cost_volume_w_upsample)
         l3_cost_volume_predict = self.flow_predictor0_predict(LF3_t, l3_cost_volume_upsample, concat_3)
         l3_cost_volume_w = self.flow_predictor0_w(LF3_t, l3_cost_volume_w_upsample, l3_cost_volume_predict)
         l3_prediction_mask = None

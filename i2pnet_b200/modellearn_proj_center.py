@@ -156,20 +156,23 @@ class RegNet_v2(nn.Module):
         # ---- level 4: coarse pose from the all-pixel cost volume
         concat_4 = self.cost_volume1(P3_raw, lidar_uv, LF3_cv, l3_grid, RF3_index, RF3, lidar_z, cfg=cfg)
         _, _, l4_points_predict, _, _ = self.layer_idx(P3_raw, P3, concat_4, sample_idx=sample_idx_4, **rfkw)
+        # The two up-convolutions need only the level-4 embedding / mask, not the coarse pose: each is forked as soon as
+        # its input exists and joined where the level-3 refinement first reads it (_refine), so they run beside the
+        # mask predictor, the coarse pose head and the second cost volume.
+        with Fork(P3_raw, P4_raw, P3, P4, LF3, l4_points_predict) as up_branch:
+            l3_up = self.set_upconv0_upsample(P3_raw, P4_raw, P3, P4, l3_grid, LF3, l4_points_predict, **rfkw)
         l4_valid = check_valid(P4_raw).view(B, -1, 1)
         l4_w = self.flow_predictor0(LF4.view(B, H4 * W4, -1), None, l4_points_predict.view(B, H4 * W4, -1))
         l4_w = _mask_fill(l4_w, l4_valid)
+        l4_w_img = l4_w.view(B, H4, W4, -1)
+        with Fork(P3_raw, P4_raw, P3, P4, LF3, l4_w_img) as up_w_branch:
+            l3_w_up = self.set_upconv0_w_upsample(P3_raw, P4_raw, P3, P4, l3_grid, LF3, l4_w_img, **rfkw)
         q4, t4, _ = self.l4_head(l4_points_predict.view(B, H4 * W4, -1), l4_w, P4.view(B, H4 * W4, 3),
                                  LF4.view(B, H4 * W4, -1), None)
         result_4 = torch.cat([q4, t4], dim=1)
-
-        l4_w_img = l4_w.view(B, H4, W4, -1)
-        with Fork(P3_raw, P4_raw, P3, P4, LF3, l4_w_img) as up_branch:      # the two up-convolutions are independent
-            l3_w_up = self.set_upconv0_w_upsample(P3_raw, P4_raw, P3, P4, l3_grid, LF3, l4_w_img, **rfkw)
-        l3_up = self.set_upconv0_upsample(P3_raw, P4_raw, P3, P4, l3_grid, LF3, l4_points_predict, **rfkw)
-        l3_w_up = up_branch.join(l3_w_up)
         return dict(B=B, H3W3=H3 * W3, P3_raw=P3_raw, P3_l4=P3_l4, P4=P4, LF3_cv=LF3_cv, l3_grid=l3_grid,
-                    RF3_index=RF3_index, RF3=RF3, l3_w_up=l3_w_up, l3_up=l3_up, q4=q4, t4=t4, result_4=result_4)
+                    RF3_index=RF3_index, RF3=RF3, l3_w_up=l3_w_up, l3_up=l3_up, q4=q4, t4=t4, result_4=result_4,
+                    pending={"l3_up": up_branch, "l3_w_up": up_w_branch})
 
     def _refine(self, s, q_in, t_in, cfg):
         """Level 3 (:331-404): warp the level-3 points by the pose (q_in, t_in), correlate with the image again,
@@ -182,6 +185,10 @@ class RegNet_v2(nn.Module):
         lidar_z = P3_warped[:, :, 2:]
         lidar_uv = P3_warped / (lidar_z + 1e-10)
         concat_3 = self.cost_volume2(s["P3_raw"], lidar_uv, LF3_cv, s["l3_grid"], s["RF3_index"], s["RF3"], lidar_z, cfg=cfg)
+        for key in ("l3_up", "l3_w_up"):                       # first refinement: the up-convolution branches end here
+            branch = s["pending"].pop(key, None)
+            if branch is not None:
+                s[key] = branch.join(s[key])
         l3_predict = self.flow_predictor0_predict(LF3_cv, s["l3_up"].view(B, n3, -1), concat_3.view(B, n3, -1))
         l3_w = self.flow_predictor0_w(LF3_cv, s["l3_w_up"].view(B, n3, -1), l3_predict)
         l3_w = _mask_fill(l3_w, check_valid(s["P3_raw"]).view(B, -1, 1))

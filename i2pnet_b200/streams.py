@@ -38,16 +38,17 @@ class Fork:
     def __init__(self, *inputs, enabled=True):
         self.inputs = [t for t in inputs if isinstance(t, torch.Tensor) and t.is_cuda]
         self.on = ENABLED and enabled and len(self.inputs) > 0
-        self.ctx = None
+        self.ctx = self.side = None
 
     def __enter__(self):
         if self.on:
             dev = self.inputs[0].device
             self.main = torch.cuda.current_stream(dev)
-            self.side = _side_stream(dev, self.main)
+            if self.side is None:       # a Fork may be re-entered: later sections continue on the same side stream
+                self.side = _side_stream(dev, self.main)
+                for t in self.inputs:
+                    t.record_stream(self.side)
             self.side.wait_stream(self.main)
-            for t in self.inputs:
-                t.record_stream(self.side)
             self.ctx = torch.cuda.stream(self.side)
             self.ctx.__enter__()
         return self
