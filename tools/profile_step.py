@@ -114,6 +114,48 @@ def main():
             for k, n, t in rows[:80]:
                 fh.write("| %.1f %% | %.1f | %.1f | `%s` |\n" % (100 * t / total, t / 3, n / 3, k[:120]))
         print("wrote", out)
+    elif what == "kineto_graph":
+        # the captured step as it is replayed (side streams overlapping): per-stream busy time, span, top kernels
+        from torch.profiler import ProfilerActivity, profile
+        eng2 = TrainStep(8, device=dev, use_graph=True)
+        eng2.load({k: v.to(dev) for k, v in make_pairs(8, seed=0).items()})
+        eng2.warmup_and_capture(eager_steps=3)
+        for _ in range(3):
+            eng2.step()
+        torch.cuda.synchronize()
+        reps = 5
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(reps):
+                eng2.step()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.elapsed_us() > 0]
+        streams, names = {}, {}
+        for e in evs:
+            tr = e.time_range
+            st = getattr(e, "device_resource_id", None)     # the CUDA stream id of a kernel record
+            rec = streams.setdefault(st, [0.0, 0, None, None])
+            rec[0] += e.time_range.elapsed_us()
+            rec[1] += 1
+            rec[2] = tr.start if rec[2] is None else min(rec[2], tr.start)
+            rec[3] = tr.end if rec[3] is None else max(rec[3], tr.end)
+            n = names.setdefault(e.name, [0.0, 0])
+            n[0] += e.time_range.elapsed_us()
+            n[1] += 1
+        t0 = min(r[2] for r in streams.values())
+        t1 = max(r[3] for r in streams.values())
+        out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/kineto_graph.md"
+        with open(out, "w") as fh:
+            fh.write("# CUPTI kernel records of the replayed CUDA-graph training step (%d replays; per-step figures)\n\n" % reps)
+            fh.write("span of all kernels: %.1f us per step; sum of kernel durations: %.1f us per step\n\n" % (
+                (t1 - t0) / reps, sum(r[0] for r in streams.values()) / reps))
+            fh.write("| stream | busy us / step | kernels / step |\n|---|---:|---:|\n")
+            for st, r in sorted(streams.items(), key=lambda kv: -kv[1][0]):
+                fh.write("| %s | %.1f | %.1f |\n" % (st, r[0] / reps, r[1] / reps))
+            fh.write("\n| share | us / step | launches / step | kernel |\n|---:|---:|---:|---|\n")
+            total = sum(v[0] for v in names.values())
+            for k, v in sorted(names.items(), key=lambda kv: -kv[1][0])[:60]:
+                fh.write("| %.1f %% | %.1f | %.1f | `%s` |\n" % (100 * v[0] / total, v[0] / reps, v[1] / reps, k[:120]))
+        print("wrote", out)
     elif what == "marked":
         marked_step(eng, sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/markers.json")
     else:  # forward only
