@@ -233,7 +233,8 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False
 
     eng = TrainStep(BATCH, N_POINTS, IMAGE_HW, device=device, seed=0, use_graph=not args.no_graph,
-                    channels_last_rgb=args.channels_last, cudnn_benchmark=args.cudnn_benchmark)
+                    channels_last_rgb=args.channels_last, cudnn_benchmark=args.cudnn_benchmark,
+                    fused_optimizer=not args.stock_optimizer)
     nb = 4  # distinct batches, cycled
     host = [make_pairs(BATCH, N_POINTS, IMAGE_HW, seed=100 * rank + i) for i in range(nb)]
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
@@ -292,7 +293,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points": N_POINTS, "image": list(IMAGE_HW), "per_gpu_batch": BATCH,
-                       "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "rgb_channels_last": args.channels_last, "cudnn_benchmark": args.cudnn_benchmark,
+                       "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "optimizer": "torch.optim.Adam" if args.stock_optimizer else "fused clip+Adam (2 launches)", "side_streams": os.environ.get("I2P_STREAMS", "1") != "0", "rgb_channels_last": args.channels_last, "cudnn_benchmark": args.cudnn_benchmark,
                        "l2": "256 MB flush write between steps", "tf32": False,
                        "shared_mlp": "tcgen05 3xTF32 split (f32-accurate), mask %d" % _cabi.lib().i2p_get_mlp_tensor_cores(),
                        "final_loss": loss},
@@ -323,6 +324,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stock-optimizer", action="store_true", help="torch.optim.Adam + clip instead of the fused flat step")
     ap.add_argument("--channels-last", action="store_true", help="NHWC memory format for the RGB conv stack")
     ap.add_argument("--cudnn-benchmark", action="store_true", help="cuDNN algorithm search for the RGB convolutions")
     args = ap.parse_args()

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "i2p_softmax_wsum": [_ll, _int, _int] + [_vp] * 5,
     "i2p_softmax_wsum_bwd": [_ll, _int, _int] + [_vp] * 8,
     "i2p_quat_mul": [_int] * 6 + [_vp] * 4,
+    "i2p_clip_adam_step": [_ll] + [_vp] * 5 + [_flt] * 6 + [_int, _vp],
     "i2p_rgb_bn_stats": [_int] * 4 + [_vp, _vp, _vp],
     "i2p_rgb_bn_finalize": [_int, _int, _vp, _vp, _vp, _flt, _flt, _vp, _vp, _vp, _vp, _vp, _vp],
     "i2p_rgb_bn_from_running": [_int, _vp, _vp, _flt, _vp, _vp, _vp, _vp, _vp],
@@ -73,7 +74,7 @@ _SIGNATURES = {
 def exported_symbols():
     """Every entry point include/i2p_b200.h declares."""
     return sorted(list(_SIGNATURES) + ["i2p_last_error", "i2p_abi_version", "i2p_launch_count", "i2p_pw_num_tiles",
-                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out", "i2p_rgb_s12_slots", "i2p_pw_tc_supported", "i2p_pw_pack_floats"])
+                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out", "i2p_rgb_s12_slots", "i2p_pw_tc_supported", "i2p_pw_pack_floats", "i2p_optim_state_bytes"])
 
 
 def lib():
@@ -97,6 +98,7 @@ def lib():
         L.i2p_pw_tc_supported.restype = _int
         L.i2p_pw_pack_floats.argtypes = [_int, _int]
         L.i2p_pw_pack_floats.restype = _ll
+        L.i2p_optim_state_bytes.restype = _int
         L.i2p_rgb_num_chunks.argtypes = [_int]
         L.i2p_rgb_num_chunks.restype = _int
         L.i2p_rgb_s12_slots.restype = _int

@@ -34,16 +34,20 @@ class FlatGradBucket:
     and `gather()` packs them into the flat buffer with a single batched concatenation; `p.grad` then
     alias slices of the flat buffer for the all-reduce, the clip and the optimiser."""
 
-    def __init__(self, params):
+    def __init__(self, params, align=1):
+        """align: every parameter's slice starts at a multiple of `align` elements (zero padding in between), so that a
+        second flat buffer with the same layout can hold the parameters themselves at a vector-load alignment."""
         self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
         ref = self.params[0]
-        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
-        self.views = []
-        off = 0
+        self.offsets, off = [], 0
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            self.offsets.append(off)
+            off += -(-p.numel() // align) * align
+        self.flat = torch.zeros(off, dtype=ref.dtype, device=ref.device)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        self._pads = [torch.zeros(self.offsets[i + 1] - self.offsets[i] - p.numel() if i + 1 < len(self.params)
+                                  else off - self.offsets[i] - p.numel(), dtype=ref.dtype, device=ref.device)
+                      for i, p in enumerate(self.params)]
         self._alias()
 
     def _alias(self):
@@ -55,7 +59,11 @@ class FlatGradBucket:
             p.grad = None
 
     def gather(self):
-        pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        pieces = []
+        for p, pad in zip(self.params, self._pads):
+            pieces.append((p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1))
+            if pad.numel():
+                pieces.append(pad)
         torch.cat(pieces, out=self.flat)
         self._alias()
 
@@ -69,6 +77,13 @@ class FlatGradBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(dist.get_world_size(group))
 
+    def all_reduce_sum(self, group=None):
+        """Sum over ranks, left un-averaged (the fused optimiser step divides); -> world size."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            return dist.get_world_size(group)
+        return 1
+
     def clip_(self, max_norm):
         """clip_grad_norm_ on the flat buffer, no host synchronisation."""
         norm = torch.linalg.vector_norm(self.flat)
@@ -76,10 +91,38 @@ class FlatGradBucket:
         return norm
 
 
+class FlatAdam:
+    """clip_grad_norm_(max_norm) + torch.optim.Adam(lr, betas, eps, weight_decay).step() of the reference trainer
+    (train20v2learn_wandb_proj.py:198-205, 481-483) as two launches of csrc/optim.cu on flat buffers.
+
+    The parameters are re-seated as views into one flat f32 buffer laid out like the gradient bucket (`bucket.offsets`),
+    both moments are flat buffers of the same layout, and the step count lives on the device, so the update is
+    capturable into a CUDA graph.  The gradient buffer is expected to hold the SUM over `world` ranks."""
+
+    def __init__(self, bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_norm=10.0):
+        self.bucket, self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = bucket, lr, betas, eps, weight_decay, max_norm
+        flat = bucket.flat
+        self.param = torch.zeros_like(flat)
+        with torch.no_grad():
+            for p, o in zip(bucket.params, bucket.offsets):
+                view = self.param[o:o + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
+        self.state = torch.zeros(_cabi.lib().i2p_optim_state_bytes(), dtype=torch.uint8, device=flat.device)
+
+    def step(self, world=1):
+        b = self.bucket
+        _cabi.call("i2p_clip_adam_step", b.flat.device, b.flat.numel(), self.param.data_ptr(), b.flat.data_ptr(),
+                   self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.state.data_ptr(), float(self.lr),
+                   float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay), float(self.max_norm),
+                   int(world))
+
+
 class TrainStep:
     def __init__(self, batch, n_points=20480, image_hw=(160, 512), cfg=I2PNetConfig, device="cuda:0", seed=0,
                  use_graph=True, lr=1e-3, weight_decay=1e-4, clip=10.0, group=None, channels_last_rgb=False,
-                 cudnn_benchmark=False):
+                 cudnn_benchmark=False, fused_optimizer=True):
         self.device = torch.device(device)
         self.cfg, self.batch, self.clip, self.group, self.use_graph = cfg, batch, clip, group, use_graph
         if cudnn_benchmark:   # let cuDNN time its f32 algorithms for the 15 convolutions during the eager warm-up
@@ -91,9 +134,14 @@ class TrainStep:
         if channels_last_rgb:  # NHWC image branch: ATen's channels-last batch-norm / pooling kernels
             for name in ("RGB_net1", "RGB_net2", "RGB_net3"):
                 getattr(self.model, name).to(memory_format=torch.channels_last)
-        self.bucket = FlatGradBucket(self.model.parameters())
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay, capturable=use_graph,
-                                    foreach=True)
+        self.fused_optimizer = fused_optimizer and not channels_last_rgb
+        if self.fused_optimizer:
+            self.bucket = FlatGradBucket(self.model.parameters(), align=64)
+            self.opt = FlatAdam(self.bucket, lr=lr, weight_decay=weight_decay, max_norm=clip)
+        else:   # the stock optimiser (A/B measurements, parity tests of the fused one)
+            self.bucket = FlatGradBucket(self.model.parameters())
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay, capturable=use_graph,
+                                        foreach=True)
         h, w = image_hw
         shapes = dict(rgb=(batch, 3, h, w), lidar=(batch, n_points, 3), raw_point_xyz=(batch, n_points, 3),
                       lidar_feats=(batch, n_points, 1), intrinsic=(batch, 3, 3), q_gt=(batch, 4), t_gt=(batch, 3))
@@ -113,9 +161,13 @@ class TrainStep:
         loss, _, _ = Get_loss(out3, out4, x["q_gt"], x["t_gt"], sx, sq, self.cfg)
         loss.backward()
         self.bucket.gather()
-        self.bucket.all_reduce_mean(self.group)
-        self.bucket.clip_(self.clip)
-        self.opt.step()
+        if self.fused_optimizer:
+            world = self.bucket.all_reduce_sum(self.group)      # averaging, clipping and the update: one fused step
+            self.opt.step(world)
+        else:
+            self.bucket.all_reduce_mean(self.group)
+            self.bucket.clip_(self.clip)
+            self.opt.step()
         self.loss.copy_(loss.detach())
 
     def load(self, batch_dict, non_blocking=True):
