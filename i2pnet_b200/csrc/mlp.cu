@@ -60,7 +60,7 @@ __device__ __forceinline__ void load_bvec(float (&bv)[TN], const float *p) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(MLP_THREADS, 2) pw_linear_fwd_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(MLP_THREADS, BN == 16 ? 4 : (BN == 32 ? 3 : 2)) pw_linear_fwd_kernel(const FwdArgs a) {
     constexpr int TN = BN / 16, TM = 8, LDA = MLP_BM + 4, LDB = BN + 4;
     __shared__ __align__(16) float As[MLP_BK][LDA];
     __shared__ __align__(16) float Bs[MLP_BK][LDB];
@@ -480,10 +480,16 @@ struct GradSrc {
     const float *dout;   // (groups, c)
     const int32_t *arg;  // (groups, c)
     int k;
+    int kshift;          // log2(k) when k is a power of two (every group size of the model), else -1
+    // group of row r (rows fit 31 bits): a shift, or one 32-bit division -- never the emulated 64-bit one, which at one
+    // division per staged element dominated the skinny dW / dX kernels
+    __device__ __forceinline__ unsigned group_of(long long r) const {
+        return kshift >= 0 ? ((unsigned)r >> kshift) : ((unsigned)r / (unsigned)k);
+    }
     __device__ __forceinline__ float at(long long r, int ch, int c) const {
         if (dense != nullptr) return __ldg(dense + (size_t)r * c + ch);
-        const long long g = r / k;
-        const int kk = (int)(r - g * k);
+        const unsigned g = group_of(r);
+        const int kk = (int)((unsigned)r - g * (unsigned)k);
         return __ldg(arg + (size_t)g * c + ch) == kk ? __ldg(dout + (size_t)g * c + ch) : 0.f;
     }
 };
@@ -568,9 +574,9 @@ __device__ __forceinline__ RawDy fetch_dy(const GradSrc &gs, const float *y, lon
         v.g = __ldg(gs.dense + (size_t)r * c + ch);
         v.arg = INT_MIN;  // dense source: always taken
     } else {
-        const long long g = r / gs.k;
+        const unsigned g = gs.group_of(r);
         v.g = __ldg(gs.dout + (size_t)g * c + ch);
-        v.arg = __ldg(gs.arg + (size_t)g * c + ch) - (int)(r - g * gs.k);  // 0 <=> this row is the arg-max
+        v.arg = __ldg(gs.arg + (size_t)g * c + ch) - (int)((unsigned)r - g * (unsigned)gs.k);  // 0 <=> this row is the arg-max
     }
     return v;
 }
@@ -593,7 +599,7 @@ struct DxArgs {
 
 // dx[r,i] = sum_o dY[r,o] W[o,i]; epilogue accumulates the previous layer's S1/S2.
 template <int BN>
-__global__ void __launch_bounds__(MLP_THREADS, 2) pw_linear_bwd_dx_kernel(const DxArgs a) {
+__global__ void __launch_bounds__(MLP_THREADS, BN == 16 ? 4 : (BN == 32 ? 3 : 2)) pw_linear_bwd_dx_kernel(const DxArgs a) {
     constexpr int TN = BN / 16, TM = 8, LDA = MLP_BM + 4, LDB = BN + 4;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     DyTables &tab = *reinterpret_cast<DyTables *>(dyn_smem);
@@ -815,7 +821,7 @@ static int launch_dw(DwArgs a, cudaStream_t s) {
 // CO threads cover the tile, and the 256 / CO groups of the CTA take every (256 / CO)-th staged row; the groups' partial
 // tiles meet in shared memory at the end.  Same operands, staging and epilogue (atomics into dW) as the general kernel.
 template <int CO>
-__global__ void __launch_bounds__(MLP_THREADS, 2) pw_linear_bwd_dw_skinny_kernel(const DwArgs a) {
+__global__ void __launch_bounds__(MLP_THREADS, CO == 64 ? 2 : 3) pw_linear_bwd_dw_skinny_kernel(const DwArgs a) {
     constexpr int CI = 16, BK = 64, T = CO, KG = MLP_THREADS / T, LDA = CO + 4, LDB = CI + 4;
     constexpr int APT = BK * CO / MLP_THREADS, BPT = BK * CI / MLP_THREADS;
     constexpr int AROWS = MLP_THREADS / CO, BROWS = MLP_THREADS / CI;
@@ -1001,6 +1007,8 @@ int i2p_bn_act_maxk(long long groups, int k, int c, const float *y, const float 
 static i2p::GradSrc make_gs(const float *g_dense, const float *dout, const int32_t *arg, int k) {
     i2p::GradSrc gs;
     gs.dense = g_dense; gs.dout = dout; gs.arg = arg; gs.k = k > 0 ? k : 1;
+    gs.kshift = -1;
+    if ((gs.k & (gs.k - 1)) == 0) { gs.kshift = 0; while ((1 << gs.kshift) < gs.k) ++gs.kshift; }
     return gs;
 }
 
@@ -1010,6 +1018,7 @@ int i2p_bn_bwd_reduce(long long rows, int c, const float *g_dense, const float *
     using namespace i2p;
     I2P_REQUIRE(rows >= 0 && c >= 16 && c % 16 == 0 && c <= MLP_MAXC, "bn_bwd_reduce: c must be a multiple of 16, <= 512");
     I2P_REQUIRE(g_dense != nullptr || (dout != nullptr && arg != nullptr && k >= 1), "bn_bwd_reduce: no gradient source");
+    I2P_REQUIRE(rows <= 0x7fffffffLL, "bn_bwd_reduce: at most 2^31 - 1 rows");
     if (rows == 0) return I2P_OK;
     const int cw = c < 64 ? c : 64;
     // about four waves of blocks; each block owns whole groups of k rows

@@ -456,7 +456,8 @@ __device__ __forceinline__ float4 dy4(const DyTab &t, int ch, float4 g, float4 y
 struct GSrc {
     const float *g;       // dense, or dout
     const int32_t *arg;   // MAXK only
-    int k;
+    int k, kshift;        // kshift = log2(k) for a power of two (every group size of the model), else -1
+    __device__ __forceinline__ int group_of(int r) const { return kshift >= 0 ? (r >> kshift) : (r / k); }
 };
 
 template <bool MAXK>
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(THREADS, MAXK ? 2 : 3) dx_kernel(const DxArgs 
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int r = r0 + rbase + 32 * p;
-        grp[p] = MAXK ? r / a.gs.k : 0;
+        grp[p] = MAXK ? a.gs.group_of(r) : 0;
         kk[p] = MAXK ? r - grp[p] * a.gs.k : 0;
     }
     auto fetch = [&](int c) {
@@ -710,7 +711,7 @@ __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
         for (int p = 0; p < B_PASSES; ++p) {
             const long long r = r0 + (b_kb0 + p * B_KSTEP) * 4 + r4;
             const bool valid = r < re && b_in;
-            rg[p] = g_fetch<MAXK>(a.gs, r, MAXK ? (int)r / a.gs.k : 0, b_ch, a.cout, valid);
+            rg[p] = g_fetch<MAXK>(a.gs, r, MAXK ? a.gs.group_of((int)r) : 0, b_ch, a.cout, valid);
             ry[p] = load4<4>(a.bn.y + (size_t)r * a.cout + b_ch, valid ? 4 : 0);
         }
     };
@@ -738,7 +739,7 @@ __global__ void __launch_bounds__(THREADS, 2) dw_kernel(const DwArgs a) {
         for (int p = 0; p < B_PASSES; ++p) {
             const long long r = r0 + (b_kb0 + p * B_KSTEP) * 4 + r4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < re && b_in) v = dy4(tab, b_ch, g_resolve<MAXK>(rg[p], MAXK ? (int)r % a.gs.k : 0), ry[p], a.bn.slope);
+            if (r < re && b_in) v = dy4(tab, b_ch, g_resolve<MAXK>(rg[p], MAXK ? (int)r - a.gs.group_of((int)r) * a.gs.k : 0), ry[p], a.bn.slope);
             split_store4(smem + 2 * A_BYTES, smem + 2 * A_BYTES + B_BYTES, b_off + (uint32_t)(p * B_KSTEP) * SBO, v.x, v.y, v.z, v.w);
         }
         umma::fence_smem_to_async();
@@ -862,8 +863,11 @@ int i2p_pw_linear_fwd_tc(int rows, int cin, int cout, const float *x, const floa
 }
 
 static bool make_gsrc(i2p::tc::GSrc &gs, const float *g_dense, const float *dout, const int32_t *arg, int k) {
+    gs.kshift = 0;
     if (g_dense != nullptr) { gs.g = g_dense; gs.arg = nullptr; gs.k = 1; return i2p::tc::aligned16(g_dense); }
     gs.g = dout; gs.arg = arg; gs.k = k;
+    gs.kshift = -1;
+    if (k >= 1 && (k & (k - 1)) == 0) { gs.kshift = 0; while ((1 << gs.kshift) < k) ++gs.kshift; }
     return dout != nullptr && arg != nullptr && k >= 1 && i2p::tc::aligned16(dout) && i2p::tc::aligned16(arg);
 }
 
