@@ -410,26 +410,40 @@ __device__ __forceinline__ void chan_merge(float &n, float &mu, float &m2, float
     }
 }
 
+// Merge of the per-tile (mean, M2) pairs of one channel: two passes over the tile statistics (they sit in L2) --
+// the row-weighted mean first, then M2 = sum_t M2_t + n_t (mean_t - mean)^2 -- with f64 accumulators.  No serial chain
+// of Chan merges (a division each): 45 of these kernels sit between the layers of the step.
 __global__ void __launch_bounds__(128) bn_finalize_kernel(int rows, int cout, int ntiles, const float *tile_stats,
                                                           const float *gamma, const float *beta, float eps,
                                                           float *mean, float *rstd, float *scale, float *shift) {
-    __shared__ float sn[4], smu[4], sm2[4];
+    __shared__ double part[4];
+    __shared__ double bcast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x;
-    float n = 0.f, mu = 0.f, m2 = 0.f;
-    for (int t = threadIdx.x; t < ntiles; t += 128) {
-        const float2 ts = __ldg(reinterpret_cast<const float2 *>(tile_stats) + (size_t)t * cout + c);
-        chan_merge(n, mu, m2, (float)min(MLP_BM, rows - t * MLP_BM), ts.x, ts.y);
-    }
+    const float2 *ts = reinterpret_cast<const float2 *>(tile_stats);
+    auto block_sum = [&](double v) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-        chan_merge(n, mu, m2, __shfl_down_sync(FULL, n, off), __shfl_down_sync(FULL, mu, off),
-                   __shfl_down_sync(FULL, m2, off));
-    if (lane == 0) { sn[warp] = n; smu[warp] = mu; sm2[warp] = m2; }
-    __syncthreads();
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(FULL, v, off);
+        if (lane == 0) part[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) bcast = part[0] + part[1] + part[2] + part[3];
+        __syncthreads();
+        return bcast;
+    };
+    double s = 0.0;
+    for (int t = threadIdx.x; t < ntiles; t += 128)
+        s += (double)((float)min(MLP_BM, rows - t * MLP_BM) * __ldg(ts + (size_t)t * cout + c).x);
+    const double mu_d = block_sum(s) / (double)rows;
+    const float mu = (float)mu_d;
+    double q = 0.0;
+    for (int t = threadIdx.x; t < ntiles; t += 128) {
+        const float2 v = __ldg(ts + (size_t)t * cout + c);
+        const float d = v.x - mu;
+        q += (double)__fmaf_rn((float)min(MLP_BM, rows - t * MLP_BM) * d, d, v.y);
+    }
+    const double m2 = block_sum(q);
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 4; ++w) chan_merge(n, mu, m2, sn[w], smu[w], sm2[w]);
-        const double var = (double)m2 / (double)n;  // biased, as BatchNorm normalises
+        const double var = m2 / (double)rows;  // biased, as BatchNorm normalises
         const float r = (float)(1.0 / sqrt(var + (double)eps));
         const float g = gamma != nullptr ? gamma[c] : 1.f, b = beta != nullptr ? beta[c] : 0.f;
         mean[c] = mu;
