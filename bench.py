@@ -8,8 +8,8 @@ step (forward + loss + backward + grad all-reduce + clip + Adam) on KITTI-shaped
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N     # one rank per GPU, weak scaling
 
 Keys follow the driver's contract: `value` = whole-job pairs/s with inputs resident in HBM,
-`e2e` = the same through TrainStep.step_from_host (pinned host batch -> device -> step -> loss on
-host), `roofline` = the dominant own kernel (the tensor-core dW GEMM of the largest shared-MLP layer; the other hot
+`e2e` = the same through engine.HostPipeline (every batch from pinned host memory, copied while the
+previous step runs; every loss back on the host), `roofline` = the dominant own kernel (the tensor-core dW GEMM of the largest shared-MLP layer; the other hot
 kernels follow in `roofline_others`) against the measured HBM peak, `cpu_baseline` = the
 CPU oracle port (oracle/model_cpu.py) on a bounded sample.  The oracle is executed only in the
 cpu_baseline leg and the --impl reference arm.
@@ -215,7 +215,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from i2pnet_b200 import _cabi
-    from i2pnet_b200.engine import INPUT_KEYS, TrainStep
+    from i2pnet_b200.engine import INPUT_KEYS, HostPipeline, TrainStep
     from i2pnet_b200.synthetic import make_pairs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -248,15 +248,26 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    pipe = HostPipeline(eng)
+
     def timed(n_steps, from_host):
         barrier()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        for i in range(n_steps):
-            flush.fill_(i & 0xff)
-            if from_host:
-                eng.step_from_host(host[i % nb])
-            else:
+        if from_host:
+            # end to end: every step's batch comes from pinned host memory (copied while the previous step runs) and
+            # every step's loss goes back to the host (read one step later); the region ends when the last loss has landed
+            pipe.submit(host[0])
+            for i in range(n_steps):
+                flush.fill_(i & 0xff)
+                pipe.step()
+                if i + 1 < n_steps:
+                    pipe.submit(host[(i + 1) % nb])
+                pipe.loss()
+            pipe.drain()
+        else:
+            for i in range(n_steps):
+                flush.fill_(i & 0xff)
                 eng.load(dev_batches[i % nb])
                 eng.step()
         stop.record()

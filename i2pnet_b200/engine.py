@@ -204,3 +204,69 @@ class TrainStep:
         self.load(host_batch, non_blocking=True)
         self.step()
         return float(self.loss.item())
+
+
+class HostPipeline:
+    """Double-buffered end-to-end feed of a TrainStep (the reference trainer copies eight
+    tensors synchronously and calls loss.item() every iteration, train20v2learn_wandb_proj.py:435-470).
+
+    Batch i + 1 travels from pinned host memory to a device staging set on a copy stream while step i runs; the step
+    stream then waits for that copy, moves the staging set into the graph's static inputs (device to device) and replays.
+    Each step's loss is copied to pinned host memory asynchronously and handed out one call later, so the host never
+    blocks on the step it has just launched.
+
+        pipe = HostPipeline(eng)
+        pipe.submit(batches[0])
+        for i in range(n):
+            pipe.step()                          # step i on the batch submitted last
+            if i + 1 < n: pipe.submit(batches[i + 1])
+            prev = pipe.loss()                   # loss of step i - 1 (None at i = 0); pipe.drain() -> the last one
+    """
+
+    def __init__(self, eng):
+        self.eng = eng
+        dev = eng.device
+        self.staging = {k: torch.empty_like(v) for k, v in eng.inputs.items()}
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.copied, self.consumed = torch.cuda.Event(), torch.cuda.Event()
+        self.consumed.record(torch.cuda.current_stream(dev))
+        self.loss_host = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
+        self.loss_ready = [None, None]
+        self.n_steps = 0
+
+    def submit(self, host_batch):
+        """Start the host-to-device copy of the next batch (pinned tensors)."""
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed)        # the staging set has been moved into the static inputs
+            for k in INPUT_KEYS:
+                self.staging[k].copy_(host_batch[k], non_blocking=True)
+            self.copied.record(self.copy_stream)
+
+    def step(self):
+        eng = self.eng
+        main = torch.cuda.current_stream(eng.device)
+        main.wait_event(self.copied)
+        for k in INPUT_KEYS:
+            eng.inputs[k].copy_(self.staging[k], non_blocking=True)
+        self.consumed.record(main)
+        eng.step()
+        slot = self.n_steps & 1
+        self.loss_host[slot].copy_(eng.loss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.loss_ready[slot] = ev
+        self.n_steps += 1
+
+    def loss(self):
+        """Loss of the step before the one launched last (its copy has long landed), or None before there is one."""
+        if self.n_steps < 2:
+            return None
+        slot = (self.n_steps - 2) & 1
+        self.loss_ready[slot].synchronize()
+        return float(self.loss_host[slot])
+
+    def drain(self):
+        """Wait for everything; -> loss of the last step."""
+        slot = (self.n_steps - 1) & 1
+        self.loss_ready[slot].synchronize()
+        return float(self.loss_host[slot])

@@ -62,3 +62,35 @@ def test_train_step_fused_optimizer_tracks_stock_optimizer():
         losses[fused] = out
     for a, b in zip(losses[True], losses[False]):
         assert abs(a - b) < 2e-3 * abs(b), losses
+
+
+def test_host_pipeline_matches_sequential_feed():
+    """engine.HostPipeline (double-buffered host feed, losses read one step late) runs the same steps as the blocking
+    step_from_host: identical loss trajectory, bit for bit (graph replay on the same inputs in the same order)."""
+    from i2pnet_b200.engine import HostPipeline, TrainStep
+    from i2pnet_b200.synthetic import make_pairs
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    host = [{k: v.pin_memory() for k, v in make_pairs(2, seed=60 + i).items()} for i in range(4)]
+    out = {}
+    for piped in (False, True):
+        eng = TrainStep(2, device=dev, seed=0, use_graph=True)
+        eng.load({k: v.to(dev) for k, v in host[0].items()})
+        eng.warmup_and_capture(eager_steps=2)
+        torch.cuda.synchronize()
+        if piped:
+            pipe, got = HostPipeline(eng), []
+            pipe.submit(host[0])
+            for i in range(4):
+                pipe.step()
+                if i + 1 < 4:
+                    pipe.submit(host[i + 1])
+                v = pipe.loss()
+                if v is not None:
+                    got.append(v)
+            got.append(pipe.drain())
+        else:
+            got = [eng.step_from_host(host[i]) for i in range(4)]
+        out[piped] = got
+    assert len(out[True]) == 4 and out[True] == out[False], out
