@@ -2,7 +2,7 @@
 N in {4k ... 131k}, M = N / 4, B = 8, points uniform in a 80 x 80 x 4 m slab; furthest point sampling, ball query
 (r = 0.5, nsample = 32), grouping (C = 64) forward / backward, 3-NN, kNN (k = 16).
 
-    python tools/bench_sweep.py [--with-reference] [--out gpurun_out/sweep.md]
+    python tests/sweep_ops.py [--with-reference] [--out gpurun_out/sweep.md]
 
 Every kernel is timed alone with CUDA events on torch's current stream (the stream the C ABI launches on), the L2
 flushed before every launch, median of the repetitions.  Achieved GB/s = SURVEY.md section 8d's algorithmic bytes /
@@ -18,7 +18,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # lives under tests/: it may time the reference kernels of oracle/_ref
 sys.path.insert(0, ROOT)
 
 from i2pnet_b200 import _cabi  # noqa: E402
