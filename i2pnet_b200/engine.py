@@ -17,7 +17,7 @@ clip 10, train...proj.py:198-205,481).
 import torch
 import torch.distributed as dist
 
-from . import _cabi
+from . import _cabi, streams
 from .compute_loss import Get_loss
 from .config_proj_lidarcenter import I2PNetConfig
 from .modellearn_proj_center import RegNet_v2
@@ -159,7 +159,12 @@ class TrainStep:
         out3, out4, _, _, sx, sq = self.model(x["rgb"], x["lidar"], x["raw_point_xyz"], None, x["intrinsic"], None,
                                               None, None, x["lidar_feats"], self.cfg)
         loss, _, _ = Get_loss(out3, out4, x["q_gt"], x["t_gt"], sx, sq, self.cfg)
-        loss.backward()
+        streams.DEFER_JOINS = True           # weight-gradient branches float until the whole backward has been issued
+        try:
+            loss.backward()
+        finally:
+            streams.DEFER_JOINS = False
+        streams.join_pending()
         self.bucket.gather()
         if self.fused_optimizer:
             world = self.bucket.all_reduce_sum(self.group)      # averaging, clipping and the update: one fused step

@@ -7,9 +7,11 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from .. import _cabi
+from .. import streams as _streams
 from .._cabi import _ptr, call, f32
 
 USE_FUSED_RGB_TAIL = True   # False: nn.BatchNorm2d -> nn.LeakyReLU -> nn.MaxPool2d through ATen / cuDNN
+SPLIT_CONV_BACKWARD = True  # weight gradients of the 3x3 convolutions on a side stream (see _ConvSplitBackward)
 
 
 class _BlockTail(Function):
@@ -64,6 +66,42 @@ class _BlockTail(Function):
         return dy, dgb[0], dgb[1], None, None, None
 
 
+class _ConvSplitBackward(Function):
+    """nn.Conv2d (library convolution, cuDNN) whose backward issues the weight gradient on a side stream: only the data
+    gradient is on the dependent chain of the image branch, the weight gradients are needed by the optimiser alone
+    (streams.defer_or_join: they stay un-joined until the end of the backward pass when a step engine asks for that)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, conf):
+        ctx.save_for_backward(x, w)
+        ctx.conf, ctx.has_bias = conf, b is not None
+        stride, padding, dilation, groups = conf
+        return torch.nn.functional.conv2d(x, w, b, stride, padding, dilation, groups)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.conf
+        bias_sizes = [w.shape[0]] if ctx.has_bias else None
+        back = torch.ops.aten.convolution_backward
+        with _streams.Fork(gy, x, w) as branch:
+            _, gw, gb = back(gy, x, w, bias_sizes, stride, padding, dilation, False, [0, 0], groups,
+                             [False, True, ctx.has_bias])
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = back(gy, x, w, bias_sizes, stride, padding, dilation, False, [0, 0], groups, [True, False, False])[0]
+        _streams.defer_or_join(branch, gw, gb)
+        return gx, gw, gb, None
+
+
+def _conv(conv, x):
+    if (SPLIT_CONV_BACKWARD and x.is_cuda and torch.is_grad_enabled() and conv.padding_mode == "zeros"
+            and not isinstance(conv.padding, str)):
+        return _ConvSplitBackward.apply(x, conv.weight, conv.bias, (list(conv.stride), list(conv.padding), list(conv.dilation),
+                                                                    conv.groups))
+    return conv(x)
+
+
 def _fusable(y, bn, act, pool):
     def one(v):
         return v if isinstance(v, int) else (v[0] if v[0] == v[1] else None)
@@ -81,7 +119,7 @@ class _Pyramid(nn.Sequential):
         mods = list(self)
         for i in range(0, len(mods), 4):
             conv, bn, act, pool = mods[i:i + 4]
-            y = conv(x)
+            y = _conv(conv, x)
             if _fusable(y, bn, act, pool):
                 stride = pool.stride if isinstance(pool.stride, int) else pool.stride[0]
                 x = _BlockTail.apply(y, bn.weight, bn.bias, bn, act.negative_slope, stride)

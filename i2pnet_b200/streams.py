@@ -59,11 +59,33 @@ class Fork:
             self.ctx = None
         return False
 
-    def join(self, *outputs):
-        """Make the stream that was current at the fork wait for the branch; -> the outputs (one, or a tuple)."""
+    def join(self, *outputs, on_current=False):
+        """Make the stream that was current at the fork (or, on_current, the stream current now) wait for the branch;
+        -> the outputs (one, or a tuple)."""
         if self.on:
-            self.main.wait_stream(self.side)
+            target = torch.cuda.current_stream(self.inputs[0].device) if on_current else self.main
+            target.wait_stream(self.side)
             for t in outputs:
                 if isinstance(t, torch.Tensor) and t.is_cuda:
-                    t.record_stream(self.main)
+                    t.record_stream(target)
         return outputs[0] if len(outputs) == 1 else outputs
+
+
+# Branches whose results nobody needs until the end of the backward pass (weight gradients): a step engine that calls
+# join_pending() after loss.backward() sets DEFER_JOINS, and such branches then stay un-joined until that call.
+DEFER_JOINS = False
+_pending = []
+
+
+def defer_or_join(fork, *outputs):
+    if DEFER_JOINS and fork.on:
+        _pending.append((fork, outputs))
+    else:
+        fork.join(*outputs)
+
+
+def join_pending():
+    """The current stream waits for every deferred branch."""
+    while _pending:
+        fork, outputs = _pending.pop()
+        fork.join(*outputs, on_current=True)
