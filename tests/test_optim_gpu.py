@@ -64,33 +64,32 @@ def test_train_step_fused_optimizer_tracks_stock_optimizer():
         assert abs(a - b) < 2e-3 * abs(b), losses
 
 
-def test_host_pipeline_matches_sequential_feed():
-    """engine.HostPipeline (double-buffered host feed, losses read one step late) runs the same steps as the blocking
-    step_from_host: identical loss trajectory, bit for bit (graph replay on the same inputs in the same order)."""
-    from i2pnet_b200.engine import HostPipeline, TrainStep
+def test_host_pipeline_feeds_the_right_batches_and_losses():
+    """engine.HostPipeline (double-buffered host feed, losses read one step late): step i runs on batch i, and the
+    loss handed out one call later is that step's.  (Loss trajectories of two engines are not comparable bit for bit:
+    the scatter / dW atomics make a training step non-deterministic in the last bits.)"""
+    from i2pnet_b200.engine import INPUT_KEYS, HostPipeline, TrainStep
     from i2pnet_b200.synthetic import make_pairs
     dev = torch.device("cuda:0")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     host = [{k: v.pin_memory() for k, v in make_pairs(2, seed=60 + i).items()} for i in range(4)]
-    out = {}
-    for piped in (False, True):
-        eng = TrainStep(2, device=dev, seed=0, use_graph=True)
-        eng.load({k: v.to(dev) for k, v in host[0].items()})
-        eng.warmup_and_capture(eager_steps=2)
+    eng = TrainStep(2, device=dev, seed=0, use_graph=True)
+    eng.load({k: v.to(dev) for k, v in host[0].items()})
+    eng.warmup_and_capture(eager_steps=2)
+    torch.cuda.synchronize()
+    pipe, seen, handed = HostPipeline(eng), [], []
+    pipe.submit(host[0])
+    for i in range(4):
+        pipe.step()
+        if i + 1 < 4:
+            pipe.submit(host[i + 1])          # overlaps step i; must not disturb the inputs step i is reading
+        v = pipe.loss()
+        if v is not None:
+            handed.append(v)
         torch.cuda.synchronize()
-        if piped:
-            pipe, got = HostPipeline(eng), []
-            pipe.submit(host[0])
-            for i in range(4):
-                pipe.step()
-                if i + 1 < 4:
-                    pipe.submit(host[i + 1])
-                v = pipe.loss()
-                if v is not None:
-                    got.append(v)
-            got.append(pipe.drain())
-        else:
-            got = [eng.step_from_host(host[i]) for i in range(4)]
-        out[piped] = got
-    assert len(out[True]) == 4 and out[True] == out[False], out
+        for k in INPUT_KEYS:
+            assert torch.equal(eng.inputs[k].cpu(), host[i][k]), (i, k)
+        seen.append(float(eng.loss.item()))
+    handed.append(pipe.drain())
+    assert handed == seen and all(v == v and v > 0 for v in seen), (handed, seen)
