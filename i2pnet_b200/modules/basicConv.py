@@ -2,6 +2,8 @@
 createCNNs :6-20, Conv1d :63-85).  Module indices inside the Sequential -- hence the
 state_dict keys `RGB_net1.{0,1,4,5,...}` -- follow the reference: block i owns slots
 4i (conv), 4i+1 (BatchNorm2d), 4i+2 (LeakyReLU 0.1), 4i+3 (MaxPool 3x3)."""
+import os
+
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -11,7 +13,7 @@ from .. import streams as _streams
 from .._cabi import _ptr, call, f32
 
 USE_FUSED_RGB_TAIL = True   # False: nn.BatchNorm2d -> nn.LeakyReLU -> nn.MaxPool2d through ATen / cuDNN
-SPLIT_CONV_BACKWARD = True  # weight gradients of the 3x3 convolutions on a side stream (see _ConvSplitBackward)
+SPLIT_CONV_BACKWARD = os.environ.get("I2P_SPLIT_WGRAD", "1") != "0"  # weight gradients of the 3x3 convolutions on a side stream (see _ConvSplitBackward)
 
 
 class _BlockTail(Function):
