@@ -61,3 +61,58 @@ def test_flat_bucket_allreduce_world2():
         ret = m.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+def _worker_fused(rank, world, port, ret):
+    """The fused-step form of the exchange: aligned flat layout, all-reduce SUM (the averaging happens inside the
+    optimiser step), checked against clip_grad_norm_ + torch.optim.Adam on the mean gradient of the global batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from i2pnet_b200.engine import FlatGradBucket
+    from oracle.optim_cpu import clip_adam_step
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    bucket = FlatGradBucket(net.parameters(), align=64)
+    assert all(o % 64 == 0 for o in bucket.offsets)
+    assert bucket.flat.numel() % 64 == 0 and len(bucket.offsets) == 4
+    # flat parameter / moment buffers with the bucket's layout (what engine.FlatAdam sets up on the GPU)
+    flat_p = torch.zeros_like(bucket.flat)
+    for p, o in zip(bucket.params, bucket.offsets):
+        view = flat_p[o:o + p.numel()].view_as(p)
+        view.copy_(p.detach())
+        p.data = view
+    m, v, step = torch.zeros_like(flat_p), torch.zeros_like(flat_p), 0
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=1e-4)
+    for it in range(3):
+        batches = []
+        for r in range(world):
+            gr = torch.Generator().manual_seed(1000 * it + r)
+            batches.append((torch.randn(4, 6, generator=gr) * 30, torch.randn(4, 3, generator=gr) * 30))
+        bucket.release()
+        torch.nn.functional.mse_loss(net(batches[rank][0]), batches[rank][1]).backward()
+        bucket.gather()
+        used = torch.zeros_like(bucket.flat, dtype=torch.bool)
+        for p, o in zip(bucket.params, bucket.offsets):
+            used[o:o + p.numel()] = True
+        assert float(bucket.flat[~used].abs().sum()) == 0.0            # the padding carries nothing
+        assert bucket.all_reduce_sum() == world
+        step = clip_adam_step(flat_p, bucket.flat, m, v, step, max_norm=10.0, world=world)
+        ref_opt.zero_grad()
+        torch.nn.functional.mse_loss(ref(torch.cat([b[0] for b in batches])), torch.cat([b[1] for b in batches])).backward()
+        norm = torch.nn.utils.clip_grad_norm_(ref.parameters(), 10.0)
+        assert float(norm) > 10.0                                       # clipping is active
+        ref_opt.step()
+        for a, b in zip(net.parameters(), ref.parameters()):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (it, float((a - b).abs().max()))
+    ret[rank] = True
+    dist.destroy_process_group()
+
+
+def test_fused_step_exchange_world2():
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker_fused, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
