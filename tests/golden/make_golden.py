@@ -173,6 +173,38 @@ def golden_nus():
           **{"grad__" + n: grads[n] for n in keep}, **{"state__" + k: v for k, v in state.items()}, **inter)
 
 
+def golden_metric():
+    """RTE / RRE of the reference's own metric.py (RteRreEval, cal_rete_once) on seeded random poses."""
+    import types
+    sys.modules.setdefault("cv2", types.ModuleType("cv2"))
+    msee = types.ModuleType("src.util.lie_metric.MSEE")          # needs geomstats (absent); unused by RteRreEval
+    msee.SE3_to_se3 = msee.cal_metric = None
+    sys.modules.setdefault("src.util.lie_metric.MSEE", msee)
+    import metric as ref_metric
+    rng = np.random.Generator(np.random.PCG64(77))
+
+    def poses(n, ang, tr):
+        axis = rng.standard_normal((n, 3))
+        axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+        half = np.deg2rad(rng.uniform(0, ang, n)) / 2
+        q = np.concatenate([np.cos(half)[:, None], axis * np.sin(half)[:, None]], 1)
+        return np.concatenate([q, rng.uniform(-tr, tr, (n, 3))], 1).astype(np.float32)
+    pred, gt = poses(64, 40.0, 8.0), poses(64, 40.0, 8.0)
+    pred[:32] = gt[:32] + rng.normal(0, 2e-3, (32, 7)).astype(np.float32)      # near-hits as well as misses
+    to_ext = lambda p: np.concatenate([ref_metric.quat_to_rotmat_batch(p[:, :4]), p[:, 4:].reshape(-1, 3, 1)], -1)
+    out = {}
+    for name, kw in (("plain", {}), ("thresholded", dict(threshold=True, rre_th=10., rte_th=5.))):
+        ev = ref_metric.RteRreEval(**kw)
+        for i in range(0, 64, 16):
+            ev.addBatch(to_ext(pred[i:i + 16]), to_ext(gt[i:i + 16]))
+        out[name + "_seq"] = np.array(ev.evalSeq())
+        out[name + "_recall"] = ev.get_recall()
+        out[name + "_rre_all"], out[name + "_rte_all"] = np.array(ev.r_diff_all), np.array(ev.t_diff_all)
+    data_valid = {"decalib_real_gt": torch.from_numpy(gt[:, :4]), "decalib_dual_gt": torch.from_numpy(gt[:, 4:])}
+    out["once"] = np.array(ref_metric.cal_rete_once(torch.from_numpy(pred), data_valid))
+    _save("ref_metric.npz", pred=pred, gt=gt, **out)
+
+
 def golden_small():
     """Forward + loss + backward of the reference's small-range RegNet_v2 (src/modellearn.py with
     src/config_lidarcenter.py: 8192 points -> 2048 / 1024 / 256 / 64, 160x512 image), B = 2, training mode."""
@@ -226,9 +258,12 @@ if __name__ == "__main__":
         golden_small()
     elif len(sys.argv) > 1 and sys.argv[1] == "nus":
         golden_nus()
+    elif len(sys.argv) > 1 and sys.argv[1] == "metric":
+        golden_metric()
     else:
         golden_ops()
         golden_model()
         golden_iter()
         golden_small()
         golden_nus()
+        golden_metric()

@@ -69,6 +69,8 @@ def check_against_golden(model, g, out3, out4, loss, inter, tol=REL, grad_tol=2e
     assert _rel(out4.detach().cpu(), g["out4"]) < tol
     assert _rel(out3.detach().cpu(), g["out3"]) < tol
     assert abs(float(loss) - float(g["loss"])) < tol * abs(float(g["loss"]))
+    check_pose_distance(out3, g["out3"])
+    check_pose_distance(out4, g["out4"])
     grads = {n: p.grad for n, p in model.named_parameters()}
     names = [str(n) for n in g["grad_names"]]
     assert sorted(grads) == names
@@ -81,6 +83,15 @@ def check_against_golden(model, g, out3, out4, loss, inter, tol=REL, grad_tol=2e
     for k in g.files:
         if k.startswith("grad__"):
             assert _rel(grads[k[len("grad__"):]].cpu(), g[k]) < 10 * grad_tol, k
+
+
+def check_pose_distance(pose, ref_pose):
+    """BASELINE.json's "pose RTE/RRE vs ref": the regressed pose against the reference's own, in the units of the
+    reference's evaluation (metric.RteRreEval): well below a milli-degree / a tenth of a millimetre at 1e-5 relative."""
+    from tests.test_metric_cpu import pose_distance_to_reference
+    rre, rte = pose_distance_to_reference(pose, ref_pose)
+    scale = max(1.0, float(np.abs(np.asarray(ref_pose)[:, 4:]).max()))
+    assert rre < 0.05 and rte < 1e-3 * scale, (rre, rte)
 
 
 def test_state_dict_matches_reference_layout():

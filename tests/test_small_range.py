@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from tests.conftest import GOLDEN
-from tests.test_host_logic_cpu import REL, _bias_cancelled_by_bn, _rel
+from tests.test_host_logic_cpu import REL, _bias_cancelled_by_bn, _rel, check_pose_distance
 
 HOOKS = ("LiDAR_lv1", "LiDAR_lv3", "cost_volume1", "layer_idx", "set_upconv0_upsample", "cost_volume2")
 
@@ -56,6 +56,8 @@ def check(model, g, out3, out4, loss, inter, tol=REL, grad_tol=5e-3, rgb_grad_to
     assert _rel(out4.detach().cpu(), g["out4"]) < tol
     assert _rel(out3.detach().cpu(), g["out3"]) < tol
     assert abs(float(loss.detach()) - float(g["loss"])) < tol * abs(float(g["loss"]))
+    check_pose_distance(out3, g["out3"])
+    check_pose_distance(out4, g["out4"])
     grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
     names = [str(n) for n in g["grad_names"]]
     assert sorted(grads) == names
