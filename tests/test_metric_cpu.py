@@ -32,3 +32,21 @@ def pose_distance_to_reference(out3, ref_out3):
     to_np = lambda v: v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
     r, t = metric.rre_rte(metric.pose_to_extrinsic(to_np(out3)), metric.pose_to_extrinsic(to_np(ref_out3)))
     return float(r.max()), float(t.max())
+
+
+def test_evaluation_loop_host_logic(oracle_backend):
+    """i2pnet_b200.evaluation.evaluate (evaluation_proj.py's loop) on the reference-initialised model and the golden
+    batch: its RTE / RRE equal cal_rete_once of the golden outputs of the reference model."""
+    from i2pnet_b200 import metric
+    from i2pnet_b200.config_proj_lidarcenter import I2PNetConfig as cfg
+    from i2pnet_b200.evaluation import evaluate
+    from tests.test_host_logic_cpu import build_model, load_golden_model
+    g, state = load_golden_model()
+    model = build_model(state)
+    t = lambda k: torch.from_numpy(g[k])
+    batch = dict(rgb=torch.from_numpy(g["rgb_u8"]).float(), lidar=t("lidar"), raw_point_xyz=t("raw_point_xyz"),
+                 lidar_feats=t("lidar_feats"), intrinsic=t("intrinsic"), q_gt=t("q_gt"), t_gt=t("t_gt"))
+    res = evaluate(model, [batch], cfg)
+    want_rre, want_rte = metric.cal_rete_once(t("out3"), t("q_gt"), t("t_gt"))          # from the REFERENCE's output
+    assert abs(res["rre_mean"] - want_rre) < 1e-3 and abs(res["rte_mean"] - want_rte) < 1e-4
+    assert res["recall"] == 1.0 and len(res["ms_per_batch"]) == 1 and len(res["rre"]) == 2
