@@ -242,6 +242,14 @@ def golden_small():
             "LiDAR_lv1.mlp_convs.0.weight", "RGB_net1.0.weight", "cost_volume2.pc_encoding.bn_linear.weight"]
     inter["inter_LiDAR_lv1"] = inter["inter_LiDAR_lv1"][:, :, ::8]
     after = {k: v for k, v in model.state_dict().items() if "running" in k and ("LiDAR_lv3" in k or "cost_volume1.mlp1_convs.0" in k)}
+    # eval(): every norm uses the running statistics this one training step has just blended in
+    state_after = {k: v.clone() for k, v in model.state_dict().items()}
+    model.eval()
+    with torch.no_grad():
+        e3, e4, _, _, _, _ = model(d["rgb"], d["lidar"], None, d["intrinsic"], None, None, None, None, cfg=cfg,
+                                   lidar_img_raw=d["raw_point_xyz"])
+    _save("ref_model_small_eval_b2.npz", out3=e3, out4=e4,
+          **{"state__" + k: v for k, v in state_after.items() if "running" in k or "num_batches" in k})
     _save("ref_model_small_b2.npz",
           rgb_u8=d["rgb"].to(torch.uint8), lidar=d["lidar"], raw_point_xyz=d["raw_point_xyz"], intrinsic=d["intrinsic"],
           q_gt=d["q_gt"], t_gt=d["t_gt"], out3=out3, out4=out4, loss=loss, grad_names=np.array(names),

@@ -127,3 +127,21 @@ def test_small_range_eval_mode_uses_running_statistics():
     assert abs(float(out3[:, :4].norm(dim=1).mean()) - 1.0) < 0.5
     after = model.state_dict()
     assert all(torch.equal(after[k], v) for k, v in before.items())
+
+
+def test_small_range_eval_mode_host_logic_matches_reference(oracle_backend):
+    """eval(): every BatchNorm normalises with its running statistics (layer-by-layer path for the point branch, the
+    running-statistics form of the image-branch tail).  Reference: the same model, after the golden training step,
+    switched to eval() (tests/golden/make_golden.py small)."""
+    from i2pnet_b200.config_lidarcenter import I2PNetConfig as cfg
+    g, state = load_golden()
+    e = np.load(os.path.join(GOLDEN, "ref_model_small_eval_b2.npz"))
+    state = dict(state)
+    state.update({k[len("state__"):]: torch.from_numpy(e[k]) for k in e.files if k.startswith("state__")})
+    model = build(state, "cpu").eval()
+    t = lambda k: torch.from_numpy(g[k])
+    with torch.no_grad():
+        out3, out4, _, _, _, _ = model(torch.from_numpy(g["rgb_u8"]).float(), t("lidar"), None, t("intrinsic"), None, None, None,
+                                       None, cfg=cfg, lidar_img_raw=t("raw_point_xyz"))
+    assert _rel(out4, e["out4"]) < REL and _rel(out3, e["out3"]) < REL
+    check_pose_distance(out3, e["out3"])
