@@ -111,6 +111,44 @@ class FlatAdam:
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
         self.state = torch.zeros(_cabi.lib().i2p_optim_state_bytes(), dtype=torch.uint8, device=flat.device)
 
+    # ---- checkpoint / resume in torch.optim.Adam's own format, so that the reference trainer's
+    # `optimizer_state_dict` (train20v2learn_wandb_proj.py:220, 259) loads here and vice versa
+    def _step_count(self):
+        return self.state[:32].view(torch.float64)[1]
+
+    def state_dict(self):
+        b, step = self.bucket, self._step_count().to(torch.float32).cpu()
+        state = {}
+        if float(step) > 0:
+            for i, (p, o) in enumerate(zip(b.params, b.offsets)):
+                state[i] = {"step": step.clone(), "exp_avg": self.exp_avg[o:o + p.numel()].view_as(p).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view_as(p).clone()}
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
+                     maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     params=list(range(len(b.params))))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        b = self.bucket
+        group = sd["param_groups"][0]
+        if len(sd["param_groups"]) != 1 or len(group["params"]) != len(b.params):
+            raise ValueError("FlatAdam.load_state_dict: expected one parameter group over %d tensors" % len(b.params))
+        self.lr, self.betas, self.eps, self.weight_decay = group["lr"], tuple(group["betas"]), group["eps"], group["weight_decay"]
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        with torch.no_grad():
+            for i, (p, o) in enumerate(zip(b.params, b.offsets)):
+                st = sd["state"].get(i)
+                if st is None:
+                    continue
+                self.exp_avg[o:o + p.numel()].view_as(p).copy_(st["exp_avg"])
+                self.exp_avg_sq[o:o + p.numel()].view_as(p).copy_(st["exp_avg_sq"])
+                steps.add(float(st["step"]))
+            if len(steps) > 1:
+                raise ValueError("FlatAdam.load_state_dict: parameters with different step counts %s" % sorted(steps))
+            self._step_count().fill_(steps.pop() if steps else 0.0)
+
     def step(self, world=1):
         b = self.bucket
         _cabi.call("i2p_clip_adam_step", b.flat.device, b.flat.numel(), self.param.data_ptr(), b.flat.data_ptr(),
@@ -203,6 +241,16 @@ class TrainStep:
             self.graph.replay()
         else:
             self._step_body()
+
+    def state_dict(self):
+        """Checkpoint with the keys the reference trainer writes (train20v2learn_wandb_proj.py:255-260)."""
+        return {"model_state_dict": self.model.state_dict(), "optimizer_state_dict": self.opt.state_dict()}
+
+    def load_state_dict(self, ckpt):
+        """Resume: parameters and buffers are copied IN PLACE (the flat buffers and a captured graph stay valid)."""
+        self.model.load_state_dict(ckpt["model_state_dict"])
+        if ckpt.get("optimizer_state_dict") is not None:
+            self.opt.load_state_dict(ckpt["optimizer_state_dict"])
 
     def step_from_host(self, host_batch):
         """End-to-end form: pinned host batch -> device, one step, loss back on the host."""

@@ -116,3 +116,33 @@ def test_fused_step_exchange_world2():
         ret = m.dict()
         mp.spawn(_worker_fused, args=(world, port, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+def test_flat_adam_checkpoint_round_trips_through_torch_adam_format():
+    """engine.FlatAdam.state_dict() / load_state_dict() speak torch.optim.Adam's format (the reference trainer's
+    `optimizer_state_dict`): moments and step count survive FlatAdam -> torch Adam -> FlatAdam.  Host logic only (CPU)."""
+    from i2pnet_b200.engine import FlatAdam, FlatGradBucket
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    ref = torch.optim.Adam(net.parameters(), lr=2e-3, weight_decay=1e-4)
+    for _ in range(3):                                          # a torch Adam with three steps of history
+        ref.zero_grad()
+        net(torch.randn(4, 6)).square().mean().backward()
+        ref.step()
+    want = ref.state_dict()
+    opt = FlatAdam(FlatGradBucket(net.parameters(), align=64), lr=1e-3)
+    opt.load_state_dict(want)
+    assert opt.lr == 2e-3 and float(opt._step_count()) == 3.0
+    got = opt.state_dict()
+    assert got["param_groups"][0]["params"] == want["param_groups"][0]["params"]
+    for i, st in want["state"].items():
+        assert torch.equal(got["state"][i]["exp_avg"], st["exp_avg"]) and torch.equal(got["state"][i]["exp_avg_sq"], st["exp_avg_sq"])
+        assert float(got["state"][i]["step"]) == float(st["step"]) == 3.0
+    fresh = torch.optim.Adam(net.parameters(), lr=1e-3)
+    fresh.load_state_dict(got)                                   # and torch's own optimiser accepts what FlatAdam wrote
+    assert fresh.state_dict()["param_groups"][0]["lr"] == 2e-3
+    # the padding of the flat moment buffers stays zero
+    used = torch.zeros_like(opt.exp_avg, dtype=torch.bool)
+    for p, o in zip(opt.bucket.params, opt.bucket.offsets):
+        used[o:o + p.numel()] = True
+    assert float(opt.exp_avg[~used].abs().sum()) == 0.0
