@@ -205,6 +205,35 @@ def golden_metric():
     _save("ref_metric.npz", pred=pred, gt=gt, **out)
 
 
+def golden_configs():
+    """Every plain hyper-parameter of the reference's three shipped configurations, as JSON."""
+    import json
+    import types
+    sys.modules.setdefault("cv2", types.ModuleType("cv2"))
+    from src.config_lidarcenter import I2PNetConfig as small
+    from src.config_proj_lidarcenter import I2PNetConfig as kitti
+    from src.config_proj_lidarcenter_nus import I2PNetConfig as nus
+
+    def plain(cls):
+        out = {}
+        for k, v in vars(cls).items():
+            if k.startswith("__") or callable(v):
+                continue
+            if hasattr(v, "name") and hasattr(v, "value"):
+                v = "enum:" + v.name
+            try:
+                json.dumps(v)
+            except TypeError:
+                continue
+            out[k] = v
+        return out
+    path = os.path.join(HERE, "ref_configs.json")
+    with open(path, "w") as fh:
+        json.dump({"config_lidarcenter": plain(small), "config_proj_lidarcenter": plain(kitti),
+                   "config_proj_lidarcenter_nus": plain(nus)}, fh, indent=1, sort_keys=True)
+    print("wrote", path)
+
+
 def golden_small():
     """Forward + loss + backward of the reference's small-range RegNet_v2 (src/modellearn.py with
     src/config_lidarcenter.py: 8192 points -> 2048 / 1024 / 256 / 64, 160x512 image), B = 2, training mode."""
@@ -268,6 +297,8 @@ if __name__ == "__main__":
         golden_nus()
     elif len(sys.argv) > 1 and sys.argv[1] == "metric":
         golden_metric()
+    elif len(sys.argv) > 1 and sys.argv[1] == "configs":
+        golden_configs()
     else:
         golden_ops()
         golden_model()
@@ -275,3 +306,4 @@ if __name__ == "__main__":
         golden_small()
         golden_nus()
         golden_metric()
+        golden_configs()
