@@ -9,7 +9,7 @@ step (forward + loss + backward + grad all-reduce + clip + Adam) on KITTI-shaped
 
 Keys follow the driver's contract: `value` = whole-job pairs/s with inputs resident in HBM,
 `e2e` = the same through engine.HostPipeline (every batch from pinned host memory, copied while the
-previous step runs; every loss back on the host), `roofline` = the dominant own kernel (the tensor-core dW GEMM of the largest shared-MLP layer; the other hot
+previous step runs; every loss back on the host), `roofline` = the dominant own kernel (the tensor-core dX GEMM, at the largest shared-MLP layer; the other hot
 kernels follow in `roofline_others`) against the measured HBM peak, `cpu_baseline` = the
 CPU oracle port (oracle/model_cpu.py) on a bounded sample.  The oracle is executed only in the
 cpu_baseline leg and the --impl reference arm.
@@ -196,8 +196,8 @@ def time_hot_kernels(device, peak):
     n, K = 3600, 32
     shape = "cost-volume-1 mlp1 layer 1 (rows 8x228x80 = %d, 262 -> 128), batch 8" % rows
     specs = [   # name, launcher, algorithmic bytes per launch
+        ("tc::dx_kernel<128> @ " + shape, dxf, 4 * rows * (2 * cout + cin)),      # largest share of the step (profiles/r1_launches_step.md)
         ("tc::dw_kernel<128,2> @ " + shape, dwf, 4 * rows * (2 * cout + cin)),
-        ("tc::dx_kernel<128> @ " + shape, dxf, 4 * rows * (2 * cout + cin)),
         ("tc::fwd_kernel<128,2> @ " + shape, fwd, 4 * rows * (cin + cout)),
         ("select_k_kernel<5,flat> @ SA1 (64x1800, 3600 centres, 9x15, K=32), batch 8", sel, BATCH * (12 * 64 * 1800 + 8 * n * K)),
     ]
