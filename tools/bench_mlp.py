@@ -23,6 +23,9 @@ except Exception:
 SHAPES = [  # rows, cin, cout
     (145920, 262, 128), (145920, 128, 64), (145920, 64, 64), (145920, 128, 128), (58368, 134, 128), (58368, 128, 64),
     (29184, 67, 64), (29184, 64, 128), (14848, 131, 128), (14848, 128, 256), (145920, 6, 64),
+    # the narrow layers of SA1 (8 x 3600 x 32 rows) and SA2 (8 x 904 x 16 rows): FMA kernels only (run once with
+    # I2P_DW_SKINNY=0 and once with the default to compare the two dW kernels for cin <= 16)
+    (921600, 10, 16), (921600, 16, 16), (921600, 16, 32), (115712, 35, 32), (115712, 32, 32), (115712, 32, 64),
 ]
 
 
