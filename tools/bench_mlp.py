@@ -50,7 +50,8 @@ def main():
         g = torch.randn(rows, cout, device=dev)
         tiles = torch.empty(L.i2p_pw_num_tiles(rows), cout, 2, device=dev)
         st = torch.empty(4, cout, device=dev)
-        pack = torch.empty(L.i2p_pw_pack_floats(cin, cout), device=dev)
+        tc_fwd = bool(L.i2p_pw_tc_supported(0, rows, cin, cout))
+        pack = torch.empty(max(L.i2p_pw_pack_floats(cin, cout), 4) if tc_fwd else 4, device=dev)
         s12 = torch.zeros(2, cout, dtype=torch.float64, device=dev)
         ps12 = torch.zeros(2, cin, dtype=torch.float64, device=dev)
         dx = torch.empty(rows, cin, device=dev)
@@ -60,7 +61,7 @@ def main():
         prev = (x.data_ptr(), pst[0].data_ptr(), pst[1].data_ptr(), pst[2].data_ptr(), pst[3].data_ptr(), 0.1) if has_tf \
             else (None, None, None, None, None, 1.0)
         pp = ps12.data_ptr() if has_tf else None
-        t_pack = timeit(lambda: call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr()))
+        t_pack = timeit(lambda: call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr())) if tc_fwd else 0.0
 
         def fwd_mask(mask):
             L.i2p_set_mlp_tensor_cores(mask)
@@ -71,6 +72,8 @@ def main():
                                 b.data_ptr(), y.data_ptr(), tiles.data_ptr())
         res = {}
         for name, mask in (("fma", 0), ("tc", 1), ("tc_sw", 17)):
+            if mask and not tc_fwd:
+                continue
             if mask & 16:   # the pack layout follows the mask
                 L.i2p_set_mlp_tensor_cores(mask)
                 call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr())
@@ -79,7 +82,8 @@ def main():
                 y0 = y.clone()
         err = float((y - y0).abs().max() / y0.abs().max())
         L.i2p_set_mlp_tensor_cores(7)
-        call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr())
+        if tc_fwd:
+            call("i2p_pw_pack_weights", dev, cin, cout, w.data_ptr(), pack.data_ptr())
         call("i2p_bn_finalize", dev, rows, cout, tiles.data_ptr(), sc[:1].expand(cout).contiguous().data_ptr(), b.data_ptr(), 1e-5,
              st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr())
         bn = (y.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), 0.1)
@@ -87,7 +91,7 @@ def main():
                                             s12.data_ptr(), w.data_ptr(), dx.data_ptr(), *prev, pp))
         res["dw_fma"] = timeit(lambda: call("i2p_pw_linear_bwd_dw", dev, rows, cin, cout, g.data_ptr(), None, None, 1, *bn,
                                             s12.data_ptr(), x.data_ptr(), psc, psh, 0.1 if has_tf else 1.0, dw.data_ptr()))
-        if L.i2p_pw_tc_supported(1, rows, cin, cout):
+        if tc_fwd and L.i2p_pw_tc_supported(1, rows, cin, cout):
             res["dx_tc"] = timeit(lambda: call("i2p_pw_linear_bwd_dx_tc", dev, rows, cin, cout, g.data_ptr(), None, None, 1, *bn, s12.data_ptr(),
                                                pack.data_ptr(), dx.data_ptr(), *prev, pp))
             L.i2p_set_mlp_tensor_cores(23)
@@ -101,6 +105,8 @@ def main():
         fb, bb = 4.0 * rows * (cin + cout), 4.0 * rows * (2 * cout + cin)
         line = "rows=%7d %3d->%3d pack %5.1f us | fwd" % (rows, cin, cout, t_pack)
         for k in ("fma", "tc", "tc_sw"):
+            if "fwd_" + k not in res:
+                continue
             t = res["fwd_" + k]
             line += "  %s %6.1f us (%4.0f GB/s %.2f)" % (k, t, fb / t / 1e3, fb / t / 1e3 / PEAK)
         line += "  cublas %6.1f us  maxrel %.1e |" % (t_mm, err)
