@@ -79,6 +79,71 @@ __global__ void __launch_bounds__(Q_THREADS) ball_query_kernel(int n, int m, flo
         for (int l = cnt; l < nsample; ++l) out[l] = first;
 }
 
+// Warp-cooperative form for small clouds: one thread per query leaves the GPU almost empty when B * M is a few
+// thousand (N <= 8192 in the operator sweep: 2 warps per SM).  Here a warp owns BQ_QPW queries and its 32 lanes test 32
+// consecutive candidates of the shared tile at once; the lanes inside the radius are compacted in index order with a
+// ballot (rank = popcount of the lower lanes), so the slots fill exactly as the reference's sequential scan fills them.
+// Selected with I2P_BALL_WARP=1 (off by default until measured on the GPU).
+constexpr int BQ_QPW = 4;
+
+__global__ void __launch_bounds__(Q_THREADS) ball_query_warp_kernel(int n, int m, float radius2, int nsample,
+                                                                    const float *__restrict__ new_xyz,
+                                                                    const float *__restrict__ xyz,
+                                                                    int32_t *__restrict__ idx) {
+    __shared__ float4 tile[Q_TILE];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = (blockIdx.x * (Q_THREADS / 32) + warp) * BQ_QPW;
+    const float *pts = xyz + (size_t)b * n * 3;
+    float qx[BQ_QPW], qy[BQ_QPW], qz[BQ_QPW];
+    int cnt[BQ_QPW], first[BQ_QPW];
+#pragma unroll
+    for (int j = 0; j < BQ_QPW; ++j) {
+        const bool valid = q0 + j < m;
+        const float *c = new_xyz + ((size_t)b * m + (valid ? q0 + j : 0)) * 3;
+        qx[j] = c[0]; qy[j] = c[1]; qz[j] = c[2];
+        cnt[j] = valid ? 0 : nsample;          // a padding query counts as finished
+        first[j] = 0;
+    }
+    const unsigned lower = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += Q_TILE) {
+        const int count = min(Q_TILE, n - base);
+        __syncthreads();
+        load_tile<false>(tile, pts, base, count);
+        __syncthreads();
+        bool done = true;
+#pragma unroll
+        for (int j = 0; j < BQ_QPW; ++j) done = done && cnt[j] >= nsample;
+        for (int i0 = 0; i0 < count && !done; i0 += 32) {
+            const int i = i0 + lane;
+            const bool in = i < count;
+            const float4 p = tile[in ? i : 0];
+            done = true;
+#pragma unroll
+            for (int j = 0; j < BQ_QPW; ++j) {
+                if (cnt[j] >= nsample) continue;                 // warp-uniform
+                const float d2 = sqlen(__fsub_rn(qx[j], p.x), __fsub_rn(qy[j], p.y), __fsub_rn(qz[j], p.z));  // :33
+                const bool hit = in && d2 < radius2;             // :34 strict
+                const unsigned mask = __ballot_sync(FULL, hit);
+                if (mask != 0u) {
+                    if (cnt[j] == 0) first[j] = base + i0 + __ffs(mask) - 1;
+                    const int slot = cnt[j] + __popc(mask & lower);
+                    if (hit && slot < nsample) idx[((size_t)b * m + q0 + j) * nsample + slot] = base + i;
+                    cnt[j] = min(nsample, cnt[j] + __popc(mask));
+                }
+                done = done && cnt[j] >= nsample;
+            }
+        }
+        if (__syncthreads_and(done)) break;
+    }
+    // :35-39 the slots behind the last hit hold the first hit; a query without any hit leaves the caller's zeros
+#pragma unroll
+    for (int j = 0; j < BQ_QPW; ++j) {
+        if (q0 + j >= m || cnt[j] == 0) continue;
+        for (int l = cnt[j] + lane; l < nsample; l += 32) idx[((size_t)b * m + q0 + j) * nsample + l] = first[j];
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // three nearest neighbours
 // ---------------------------------------------------------------------------------------
@@ -218,6 +283,13 @@ int i2p_ball_query(int b, int n, int m, float radius, int nsample, const float *
     I2P_REQUIRE(b <= 65535, "ball_query: batch > 65535");
     if (b == 0 || m == 0 || n == 0) return I2P_OK;
     const float radius2 = radius * radius;  // ball_query_gpu.cu:24
+    static int warp_form = -1;   // I2P_BALL_WARP=1: the warp-cooperative kernel
+    if (warp_form < 0) { const char *e = getenv("I2P_BALL_WARP"); warp_form = e ? atoi(e) : 0; }
+    if (warp_form) {
+        dim3 grid(ceil_div(m, (Q_THREADS / 32) * BQ_QPW), b);
+        ball_query_warp_kernel<<<grid, Q_THREADS, 0, as_stream(stream)>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
+        return check_launch("ball_query(warp)");
+    }
     dim3 grid(ceil_div(m, Q_THREADS), b);
     ball_query_kernel<<<grid, Q_THREADS, 0, as_stream(stream)>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
     return check_launch("ball_query");
