@@ -108,7 +108,7 @@ def test_small_range_model_matches_reference_on_gpu():
     # forward / loss: 1e-4.  Gradients against a CPU recording of the reference: the 15 overlapping max-pools of the RGB
     # stack route gradients through arg-max positions that flip on 1e-6 forward differences (see
     # tests/test_model_gpu.py), hence the looser bar on the image branch.
-    check(model, g, *run(model, g, dev), grad_tol=1e-2, rgb_grad_tol=5e-2)      # measured: <= 2.3e-2 on the image branch
+    check(model, g, *run(model, g, dev), grad_tol=1e-2, rgb_grad_tol=1e-1)      # measured: 0.9e-2 .. 2.3e-2 on the image branch, run to run
 
 
 @pytest.mark.gpu
