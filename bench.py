@@ -25,8 +25,39 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "kitti_160x512_rgb+20480pts_batch8_per_gpu_fwd+bwd+adam"
+# BASELINE.json configs: [1] = the default bench line; [2]'s shape (batch 32) in f32; [3] nuScenes shape, batch 16
+CONFIGS = {
+    "kitti_b8": dict(workload="kitti_160x512_rgb+20480pts_batch8_per_gpu_fwd+bwd+adam", points=20480, image=(160, 512),
+                     batch=8, nus=False),
+    "kitti_b32": dict(workload="kitti_160x512_rgb+20480pts_batch32_per_gpu_fwd+bwd+adam", points=20480, image=(160, 512),
+                      batch=32, nus=False),
+    "nus_b16": dict(workload="nuscenes_320x640_rgb+40960pts_batch16_per_gpu_fwd+bwd+adam", points=40960, image=(320, 640),
+                    batch=16, nus=True),
+}
+WORKLOAD = CONFIGS["kitti_b8"]["workload"]
 N_POINTS, IMAGE_HW, BATCH = 20480, (160, 512), 8
+
+
+def _cfg_of(conf):
+    from i2pnet_b200.config_proj_lidarcenter import I2PNetConfig, I2PNetConfigNus
+    return I2PNetConfigNus if conf["nus"] else I2PNetConfig
+
+
+def _pairs(conf, batch, seed):
+    from i2pnet_b200.synthetic import make_pairs
+    if conf["nus"]:
+        cfg = _cfg_of(conf)
+        return make_pairs(batch, conf["points"], conf["image"], init_H=cfg.init_H, init_W=cfg.init_W, fup=cfg.fup,
+                          fdown=cfg.fdown, seed=seed)
+    return make_pairs(batch, conf["points"], conf["image"], seed=seed)
+
+
+def _config_dict(conf, name, per_gpu_batch, world, strong):
+    """The `config` object both arms print (same keys and values, so that the driver sees the same configuration)."""
+    return {"workload": conf["workload"] if not strong else conf["workload"].replace("_per_gpu", "_global"),
+            "name": name, "points": conf["points"], "image": list(conf["image"]), "per_gpu_batch": per_gpu_batch,
+            "global_batch": per_gpu_batch * world, "parallelism": "dp%d" % world,
+            "l2": "256 MB flush write between steps (GPU arm)"}
 
 
 def _peaks():
@@ -79,12 +110,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_steps(steps, warmup, batch, threads=None, seed=0):
+def cpu_reference_steps(steps, warmup, batch, threads=None, seed=0, conf=None):
     """The reference path on host cores: oracle/model_cpu.py forward + loss + backward + Adam on
     `batch` pairs per step.  -> (seconds per step list, cores)"""
     import torch
-    from i2pnet_b200.synthetic import make_pairs
     from oracle import model_cpu
+    conf = conf or CONFIGS["kitti_b8"]
+    if conf["nus"]:
+        raise SystemExit("bench.py: the CPU port (oracle/model_cpu.py) covers the KITTI configuration only")
     # every host thread this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
     # silently turn the reference arm into a single-thread run
     if not threads:
@@ -98,7 +131,7 @@ def cpu_reference_steps(steps, warmup, batch, threads=None, seed=0):
     opt = torch.optim.Adam(list(sd.values()), lr=1e-3, weight_decay=1e-4)
     times = []
     for i in range(warmup + steps):
-        d = make_pairs(batch, N_POINTS, IMAGE_HW, seed=1000 + i)
+        d = _pairs(conf, batch, 1000 + i)
         t0 = time.perf_counter()
         opt.zero_grad()
         out3, out4 = model_cpu.forward(sd, d["rgb"], d["lidar"], d["raw_point_xyz"], d["intrinsic"], d["lidar_feats"])
@@ -113,22 +146,58 @@ def cpu_reference_steps(steps, warmup, batch, threads=None, seed=0):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    batch = BATCH   # ~3 s per step on 8 cores: the full per-GPU batch fits the time budget
-    times, cores = cpu_reference_steps(args.steps, args.warmup, batch)
+    conf = CONFIGS[args.config]
+    per_gpu = _per_gpu_batch(conf, world, args.strong)
+    # a bounded sample of the workload: batch <= 8 pairs per step (~1 s on 16 cores), the metric is per pair
+    batch = min(per_gpu, 8)
+    times, cores = cpu_reference_steps(args.steps, args.warmup, batch, conf=conf)
     total = sum(times)
     value = batch * len(times) / total
     sample = "%d steps of batch %d (of the batch-%d workload) on %d host threads, oracle/model_cpu.py" % (
-        len(times), batch, BATCH, cores)
+        len(times), batch, per_gpu, cores)
     print(json.dumps({
         "impl": "reference", "metric": "pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "points": N_POINTS, "image": list(IMAGE_HW), "sample_batch": batch},
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": _config_dict(conf, args.config, per_gpu, world, args.strong),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def _per_gpu_batch(conf, world, strong):
+    if not strong:
+        return conf["batch"]
+    if conf["batch"] % world:
+        raise SystemExit("bench.py --strong: global batch %d does not split over %d GPUs" % (conf["batch"], world))
+    return conf["batch"] // world
+
+
+def legacy_b200(conf, batch, steps=10):
+    """The reference's own kernels recompiled for sm_100 under its UNCHANGED model / loss / optimiser loop on this GPU
+    (oracle/ref_live.py on oracle/_ref, as a subprocess after the timed region): BASELINE.md B2(i), the comparator a
+    GPU kernel rewrite has to beat.  cuDNN off is what the trainer runs (src/deterministic.py:36-38); on is kinder."""
+    out = {}
+    for tag, flag in (("cudnn_off", []), ("cudnn_on", ["--cudnn"])):
+        cmd = [sys.executable, "-m", "oracle.ref_live", "--bench", "--batch", str(batch), "--steps", str(steps), "--warmup", "3",
+               "--points", str(conf["points"]), "--image", str(conf["image"][0]), str(conf["image"][1])] + flag + \
+              (["--nus"] if conf["nus"] else [])
+        try:
+            res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+            line = [l for l in res.stdout.splitlines() if l.startswith("{")]
+            if res.returncode != 0 or not line:
+                out[tag] = {"unavailable": (res.stderr.strip().splitlines() or ["no output"])[-1][:200]}
+            else:
+                r = json.loads(line[-1])
+                out[tag] = {k: r[k] for k in ("pairs_per_s", "ms_per_step", "e2e_pairs_per_s", "e2e_ms_per_step")}
+        except Exception as e:   # noqa: BLE001
+            out[tag] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:160])}
+    out["what"] = ("unchanged src/modellearn_proj_center.py + compute_loss.py + clip_grad_norm_ + Adam, eager, on the "
+                   "reference's CUDA kernels compiled for sm_100 (oracle/_ref), batch %d, %d steps" % (batch, steps))
+    return out
 
 
 def _event_time(fn, flush, reps=25, skip=5):
@@ -216,7 +285,6 @@ def run_ours(args):
     import torch.distributed as dist
     from i2pnet_b200 import _cabi
     from i2pnet_b200.engine import INPUT_KEYS, HostPipeline, TrainStep
-    from i2pnet_b200.synthetic import make_pairs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -232,11 +300,13 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = False   # f32 parity configuration (north_star: 1e-4 relative)
     torch.backends.cudnn.allow_tf32 = False
 
-    eng = TrainStep(BATCH, N_POINTS, IMAGE_HW, device=device, seed=0, use_graph=not args.no_graph,
-                    channels_last_rgb=args.channels_last, cudnn_benchmark=args.cudnn_benchmark,
-                    fused_optimizer=not args.stock_optimizer)
+    conf = CONFIGS[args.config]
+    batch = _per_gpu_batch(conf, world, args.strong)
+    eng = TrainStep(batch, conf["points"], conf["image"], cfg=_cfg_of(conf), device=device, seed=0,
+                    use_graph=not args.no_graph, channels_last_rgb=args.channels_last,
+                    cudnn_benchmark=args.cudnn_benchmark, fused_optimizer=not args.stock_optimizer)
     nb = 4  # distinct batches, cycled
-    host = [make_pairs(BATCH, N_POINTS, IMAGE_HW, seed=100 * rank + i) for i in range(nb)]
+    host = [_pairs(conf, batch, 100 * rank + i) for i in range(nb)]
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     dev_batches = [{k: v.to(device) for k, v in b.items()} for b in host]
     eng.load(dev_batches[0])
@@ -264,6 +334,7 @@ def run_ours(args):
                 if i + 1 < n_steps:
                     pipe.submit(host[(i + 1) % nb])
                 pipe.loss()
+                pipe.out3()
             pipe.drain()
         else:
             for i in range(n_steps):
@@ -290,29 +361,35 @@ def run_ours(args):
     if rank == 0:
         peak = _peaks()
         roof, roof_others = time_hot_kernels(device, peak)
-        value = world * BATCH * args.steps / (ms * 1e-3)
-        e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
+        value = world * batch * args.steps / (ms * 1e-3)
+        e2e = world * batch * args.steps / (ms_e2e * 1e-3)
         h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in INPUT_KEYS)
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            t, cores = cpu_reference_steps(3, 1, BATCH)
-            cpu = {"value": BATCH * len(t) / sum(t), "unit": "pairs/s", "cores": cores, "kind": "port",
-                   "sample": "3 steps of batch %d (the same workload) after 1 warm-up, oracle/model_cpu.py "
-                             "fwd+bwd+clip+Adam" % BATCH}
+        cpu = legacy = None
+        if world == 1 and not args.no_cpu_baseline and not conf["nus"]:
+            cb = min(batch, 8)
+            t, cores = cpu_reference_steps(3, 1, cb, conf=conf)
+            cpu = {"value": cb * len(t) / sum(t), "unit": "pairs/s", "cores": cores, "kind": "port",
+                   "sample": "3 steps of batch %d (of the batch-%d workload) after 1 warm-up, oracle/model_cpu.py "
+                             "fwd+bwd+clip+Adam" % (cb, batch)}
+        if world == 1 and not args.no_legacy:
+            legacy = legacy_b200(conf, batch)
+        config = _config_dict(conf, args.config, batch, world, args.strong)
+        engine = dict({"cuda_graph": not args.no_graph, "optimizer": "torch.optim.Adam" if args.stock_optimizer else "fused clip+Adam (2 launches)",
+                       "side_streams": os.environ.get("I2P_STREAMS", "1") != "0", "rgb_channels_last": args.channels_last,
+                       "cudnn_benchmark": args.cudnn_benchmark, "tf32": False,
+                       "shared_mlp": "tcgen05 3xTF32 split (f32-accurate), mask %d" % _cabi.lib().i2p_get_mlp_tensor_cores(),
+                       "final_loss": loss})
         print(json.dumps({
             "metric": "pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points": N_POINTS, "image": list(IMAGE_HW), "per_gpu_batch": BATCH,
-                       "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "optimizer": "torch.optim.Adam" if args.stock_optimizer else "fused clip+Adam (2 launches)", "side_streams": os.environ.get("I2P_STREAMS", "1") != "0", "rgb_channels_last": args.channels_last, "cudnn_benchmark": args.cudnn_benchmark,
-                       "l2": "256 MB flush write between steps", "tf32": False,
-                       "shared_mlp": "tcgen05 3xTF32 split (f32-accurate), mask %d" % _cabi.lib().i2p_get_mlp_tensor_cores(),
-                       "final_loss": loss},
-            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config, "engine": engine,
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": pipe.d2h_bytes_per_step,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(eng.launches_per_step) * args.steps,
             "gpu_launches_per_step": int(eng.launches_per_step),
             "clocks": clocks, "roofline": roof, "roofline_others": roof_others, "cpu_baseline": cpu,
+            "legacy_b200": legacy,
         }))
     if world > 1:
         # Tear-down: the captured graph holds NCCL kernels, and destroying the communicator underneath it was
@@ -334,7 +411,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of CUDA-graph replay")
+    ap.add_argument("--config", default="kitti_b8", choices=sorted(CONFIGS),
+                    help="kitti_b8: BASELINE configs[1] (default); kitti_b32: north_star's target batch; nus_b16: configs[3]")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the config's batch is the GLOBAL batch, split evenly over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legacy", action="store_true", help="skip the legacy-kernels-on-B200 leg (oracle/ref_live.py)")
     ap.add_argument("--stock-optimizer", action="store_true", help="torch.optim.Adam + clip instead of the fused flat step")
     ap.add_argument("--channels-last", action="store_true", help="NHWC memory format for the RGB conv stack")
     ap.add_argument("--cudnn-benchmark", action="store_true", help="cuDNN algorithm search for the RGB convolutions")

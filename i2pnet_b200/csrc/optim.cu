@@ -14,7 +14,10 @@
 
 namespace i2p {
 
-// state[0] = sum of squares (f64), state[1] = step count t (as f64), state[2] = 1 - b1^t, state[3] = 1 - b2^t
+// state[0] = sum of squares (f64), state[1] = step count t (as f64), state[2] = 1 - b1^t, state[3] = 1 - b2^t,
+// then the arrival ticket (u32 at byte 32) and the learning rate (f32 at byte 48): a launch argument would be frozen
+// into a captured CUDA graph, whereas the reference trainer decays it every epoch (ExponentialLR(0.99),
+// train20v2learn_wandb_proj.py:205, 524) -- replays read the current value from here.
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(long long n, const float *g, double *state, double b1, double b2,
                                                          unsigned *ticket) {
     double acc = 0.0;
@@ -50,8 +53,9 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(long long n, const floa
 }
 
 __global__ void __launch_bounds__(256) adam_step_kernel(long long n, float *p, const float *g, float *m, float *v,
-                                                        const double *state, float lr, float b1, float b2, float eps,
+                                                        const double *state, float lr_arg, float b1, float b2, float eps,
                                                         float wd, float max_norm, float inv_world) {
+    const float lr = lr_arg > 0.f ? lr_arg : *reinterpret_cast<const float *>(reinterpret_cast<const char *>(state) + 48);
     const float total_norm = (float)sqrt(state[0]) * inv_world;
     const float coef = fminf(max_norm / (total_norm + 1e-6f), 1.0f);
     const float gscale = max_norm > 0.f ? inv_world * coef : inv_world;
@@ -72,7 +76,8 @@ __global__ void __launch_bounds__(256) adam_step_kernel(long long n, float *p, c
 
 extern "C" {
 
-int i2p_optim_state_bytes(void) { return 4 * (int)sizeof(double) + 16; }
+int i2p_optim_state_bytes(void) { return 64; }
+int i2p_optim_lr_offset(void) { return 48; }
 
 int i2p_clip_adam_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, void *state,
                        float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, int world,

@@ -16,6 +16,19 @@ def evaluate(model, batches, cfg, device=None, threshold=False):
     device = torch.device(device) if device is not None else next(model.parameters()).device
     evaluator = RteRreEval(threshold=threshold)
     times = []
+    was_training = model.training
+    model.eval()            # evaluation_proj.py:214: dropout off, tracked BatchNorms on their running statistics
+    try:
+        _run(model, batches, cfg, device, evaluator, times)
+    finally:
+        model.train(was_training)
+    rte_mean, rte_sigma, rre_mean, rre_sigma = evaluator.evalSeq()
+    return dict(rte_mean=rte_mean, rte_sigma=rte_sigma, rre_mean=rre_mean, rre_sigma=rre_sigma,
+                recall=evaluator.get_recall(), ms_per_batch=[1e3 * t for t in times],
+                rre=list(evaluator.r_diff_all), rte=list(evaluator.t_diff_all))
+
+
+def _run(model, batches, cfg, device, evaluator, times):
     with torch.no_grad():
         for data in batches:
             if device.type == "cuda":
@@ -29,7 +42,3 @@ def evaluate(model, batches, cfg, device=None, threshold=False):
             times.append(time.perf_counter() - t0)          # includes the host-to-device copies, like the reference's
             gt = torch.cat([data["q_gt"].reshape(-1, 4), data["t_gt"].reshape(-1, 3)], dim=1)
             evaluator.addBatch(pose_to_extrinsic(out3.cpu().numpy()), pose_to_extrinsic(gt.cpu().numpy()))
-    rte_mean, rte_sigma, rre_mean, rre_sigma = evaluator.evalSeq()
-    return dict(rte_mean=rte_mean, rte_sigma=rte_sigma, rre_mean=rre_mean, rre_sigma=rre_sigma,
-                recall=evaluator.get_recall(), ms_per_batch=[1e3 * t for t in times],
-                rre=list(evaluator.r_diff_all), rte=list(evaluator.t_diff_all))

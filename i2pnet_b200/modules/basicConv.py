@@ -77,6 +77,7 @@ class _ConvSplitBackward(Function):
     def forward(ctx, x, w, b, conf):
         ctx.save_for_backward(x, w)
         ctx.conf, ctx.has_bias = conf, b is not None
+        ctx.params = (w, b)
         stride, padding, dilation, groups = conf
         return torch.nn.functional.conv2d(x, w, b, stride, padding, dilation, groups)
 
@@ -86,13 +87,27 @@ class _ConvSplitBackward(Function):
         stride, padding, dilation, groups = ctx.conf
         bias_sizes = [w.shape[0]] if ctx.has_bias else None
         back = torch.ops.aten.convolution_backward
+        from ..engine import grad_sink
+        sink_w = grad_sink(ctx.params[0])
+        sink_b = grad_sink(ctx.params[1]) if ctx.has_bias else None
         with _streams.Fork(gy, x, w) as branch:
             _, gw, gb = back(gy, x, w, bias_sizes, stride, padding, dilation, False, [0, 0], groups,
                              [False, True, ctx.has_bias])
+            if sink_w is not None:
+                # A tensor produced on the side stream must not be handed to autograd: AccumulateGrad runs on THIS node's
+                # stream and would read it without waiting for the branch.  The gradients go straight into the step
+                # engine's flat buffer on the branch's own stream; the engine joins the branch before it reads the buffer.
+                sink_w.add_(gw)
+                if sink_b is not None:
+                    sink_b.add_(gb)
+                gw = gb = None
         gx = None
         if ctx.needs_input_grad[0]:
             gx = back(gy, x, w, bias_sizes, stride, padding, dilation, False, [0, 0], groups, [True, False, False])[0]
-        _streams.defer_or_join(branch, gw, gb)
+        if sink_w is not None:
+            _streams.defer_or_join(branch)
+        else:
+            branch.join(gw, gb)          # no engine: autograd owns the gradients, so they are joined before it sees them
         return gx, gw, gb, None
 
 

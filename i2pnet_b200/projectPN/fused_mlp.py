@@ -63,11 +63,17 @@ class FusedMLPFunction(Function):
                  st[3].data_ptr())
             bnm = trackers[l]
             if bnm is not None:
-                mom = bnm.momentum if bnm.momentum is not None else 0.1
-                var = (1.0 / (st[1] * st[1]) - float(eps[l])).clamp_(min=0.0)       # biased batch variance back from rstd
-                bnm.running_mean.mul_(1.0 - mom).add_(st[0], alpha=mom)
-                bnm.running_var.mul_(1.0 - mom).add_(var, alpha=mom * rows / max(rows - 1, 1))
                 bnm.num_batches_tracked.add_(1)
+                var = (1.0 / (st[1] * st[1]) - float(eps[l])).clamp_(min=0.0)       # biased batch variance back from rstd
+                unbias = rows / max(rows - 1, 1)
+                if bnm.momentum is None:    # nn.BatchNorm: cumulative moving average, factor 1 / num_batches_tracked
+                    f = 1.0 / bnm.num_batches_tracked.to(f32)
+                    bnm.running_mean.add_((st[0] - bnm.running_mean) * f)
+                    bnm.running_var.add_((var * unbias - bnm.running_var) * f)
+                else:
+                    mom = bnm.momentum
+                    bnm.running_mean.mul_(1.0 - mom).add_(st[0], alpha=mom)
+                    bnm.running_var.mul_(1.0 - mom).add_(var, alpha=mom * unbias)
             ys.append(y)
             stats.append(st)
             packs.append(pack)

@@ -263,8 +263,11 @@ int i2p_quat_mul(int B, int N, int na, int nb, int conj_a, int conj_b, const flo
  * param, grad, exp_avg, exp_avg_sq: n f32 each (grad 16-byte aligned).  grad holds the SUM of the ranks' gradients
  * (world = 1: the gradient); it is averaged, clipped to total norm max_norm (max_norm <= 0: no clipping) and given
  * L2 weight decay inside the update and left untouched in memory.  state: i2p_optim_state_bytes() bytes, zero-filled
- * once by the caller; it carries the step count across calls.  Two launches. */
+ * once by the caller; it carries the step count across calls.  Two launches.
+ * lr > 0: that learning rate; lr <= 0: the f32 at byte i2p_optim_lr_offset() of `state` (so that a step captured into
+ * a CUDA graph follows the trainer's per-epoch ExponentialLR decay, train20v2learn_wandb_proj.py:205, 524). */
 int i2p_optim_state_bytes(void);
+int i2p_optim_lr_offset(void);
 int i2p_clip_adam_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, void *state,
                        float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, int world,
                        void *stream);

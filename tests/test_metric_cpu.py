@@ -36,7 +36,10 @@ def pose_distance_to_reference(out3, ref_out3):
 
 def test_evaluation_loop_host_logic(oracle_backend):
     """i2pnet_b200.evaluation.evaluate (evaluation_proj.py's loop) on the reference-initialised model and the golden
-    batch: its RTE / RRE equal cal_rete_once of the golden outputs of the reference model."""
+    batch.  Like evaluation_proj.py:214 it switches the model to eval() (dropout off, the image branch's tracked
+    BatchNorms on their running statistics, which it must not update) and restores the caller's mode: its RTE / RRE
+    equal cal_rete_once of the model's own eval-mode forward; with running statistics equal to the batch's, that of
+    the golden (train-mode) outputs of the reference model."""
     from i2pnet_b200 import metric
     from i2pnet_b200.config_proj_lidarcenter import I2PNetConfig as cfg
     from i2pnet_b200.evaluation import evaluate
@@ -46,7 +49,16 @@ def test_evaluation_loop_host_logic(oracle_backend):
     t = lambda k: torch.from_numpy(g[k])
     batch = dict(rgb=torch.from_numpy(g["rgb_u8"]).float(), lidar=t("lidar"), raw_point_xyz=t("raw_point_xyz"),
                  lidar_feats=t("lidar_feats"), intrinsic=t("intrinsic"), q_gt=t("q_gt"), t_gt=t("t_gt"))
+    assert model.training
+    buffers = {k: v.clone() for k, v in model.named_buffers()}
     res = evaluate(model, [batch], cfg)
-    want_rre, want_rte = metric.cal_rete_once(t("out3"), t("q_gt"), t("t_gt"))          # from the REFERENCE's output
+    assert model.training, "evaluate() must restore the caller's mode"
+    assert all(torch.equal(v, buffers[k]) for k, v in model.named_buffers()), "evaluate() updated running statistics"
+    model.eval()
+    with torch.no_grad():
+        own = model(batch["rgb"], batch["lidar"], batch["raw_point_xyz"], None, batch["intrinsic"], None, None, None,
+                    batch["lidar_feats"], cfg)[0]
+    model.train()
+    want_rre, want_rte = metric.cal_rete_once(own, t("q_gt"), t("t_gt"))
     assert abs(res["rre_mean"] - want_rre) < 1e-3 and abs(res["rte_mean"] - want_rte) < 1e-4
     assert res["recall"] == 1.0 and len(res["ms_per_batch"]) == 1 and len(res["rre"]) == 2

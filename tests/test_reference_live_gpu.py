@@ -1,0 +1,189 @@
+"""GPU: the reference's UNCHANGED Python (oracle/_ref/py, staged by oracle/build_ref.py) run live on the B200.
+
+  * on its own CUDA kernels (oracle/_ref/*.so) as the model-level oracle for the BENCHMARKED configuration: batch 8 and
+    batch 32, against the product's step engine through its CAPTURED CUDA graph -- side streams, deferred weight-gradient
+    joins, flat gradient buffer, fused clip + Adam (src/modellearn_proj_center.py:216-424, compute_loss.py:102-133,
+    train20v2learn_wandb_proj.py:457-483);
+  * on the drop-in extension modules (dropin/, libi2p_b200.so): north_star's "drop in unchanged", including the
+    trainer's loop body and pointnet2/pointnet2_modules.py:10-156.
+
+Bars.  Forward / loss: 1e-4 relative (north_star).  Gradients: relative L2 distance of the whole flat gradient, and per
+parameter tensor against the largest tensor norm -- f32 end-to-end gradients of this network are ill-conditioned
+(DESIGN.md section 4), so the per-tensor relative bar is looser and stated.  Index-only differences between "ref" and
+"dropin" cannot exist (the kernels are bit-exact), so the forward of the unchanged model is required to be IDENTICAL.
+"""
+import pytest
+import torch
+
+from oracle import ref_live
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_live.available("ref"), reason="oracle/_ref not built")]
+
+DEV = "cuda:0"
+
+
+def _f32_mode():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def _silence_dropout(model):
+    for head in (model.l4_head, model.l3_head):
+        head.DP1.p = 0.0
+
+
+def _reference_model(ns, seed=0, cfg=None):
+    torch.manual_seed(seed)
+    model = ns.RegNet_v2(cfg=cfg or ns.cfg).to(DEV)
+    model.train()
+    _silence_dropout(model)
+    g = torch.Generator().manual_seed(5)          # non-trivial BN affine parameters
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "bn" in n or (".1." in n and "RGB" in n) or ".5." in n:
+                p.add_((0.1 * torch.randn(p.shape, generator=g)).to(DEV))
+    return model
+
+
+def _batch(b, seed, **kw):
+    from i2pnet_b200.synthetic import make_pairs
+    return {k: v.to(DEV) for k, v in make_pairs(b, 20480, seed=seed, occupy_centres=(4, 8), **kw).items()}
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("batch", [8, 32])
+def test_captured_step_matches_reference_model_on_reference_kernels(batch):
+    """The benchmarked path (TrainStep's captured graph at the bench's batch size) against the unchanged reference
+    model + Get_loss + clip_grad_norm_ + Adam on the reference's own kernels, same parameters, same batches."""
+    from i2pnet_b200.engine import TrainStep
+    _f32_mode()
+    prev = torch.backends.cudnn.enabled
+    torch.backends.cudnn.enabled = False           # the trainer's set_seed(0), src/deterministic.py:36-38
+    try:
+        ns = ref_live.load("ref")
+        ref = _reference_model(ns)
+        state = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+        eng = TrainStep(batch, device=DEV, seed=1, use_graph=True)
+        _silence_dropout(eng.model)
+        eng.model.load_state_dict(state, strict=True)
+        batches = [_batch(batch, 200 + i) for i in range(3)]
+        eng.load(batches[0])
+        eng.warmup_and_capture(eager_steps=2)
+        for k, v in eng.model.state_dict().items():      # warm-up must leave the training state as loaded
+            assert torch.equal(v, state[k]), "warm-up changed %s" % k
+        opt = ref_live.make_optimizer(ref)
+        ref_losses, my_losses = [], []
+        for i, bt in enumerate(batches):
+            # reference iteration (train20v2learn_wandb_proj.py:457-483)
+            out3_r, out4_r, loss_r = ref_live.forward_loss(ns, ref, bt)
+            opt.zero_grad()
+            loss_r.backward()
+            grads_r = {n: p.grad.detach().clone() for n, p in ref.named_parameters()}
+            torch.nn.utils.clip_grad_norm_(ref.parameters(), 10.0)
+            opt.step()
+            # product: one replay of the captured graph
+            eng.load(bt)
+            eng.step()
+            torch.cuda.synchronize()
+            ref_losses.append(float(loss_r))
+            my_losses.append(float(eng.loss))
+            if i == 0:       # identical parameters: forward 1e-4 (north_star), gradients vs the reference's
+                assert _rel(eng.out3, out3_r.detach()) < 1e-4 and _rel(eng.out4, out4_r.detach()) < 1e-4
+                assert abs(my_losses[0] - ref_losses[0]) < 1e-4 * abs(ref_losses[0])
+                mine = {n: p.grad for n, p in eng.model.named_parameters()}      # views of the flat gradient buffer
+                num = sum(float((mine[n].double() - grads_r[n].double()).pow(2).sum()) for n in grads_r)
+                den = sum(float(grads_r[n].double().pow(2).sum()) for n in grads_r)
+                gmax = max(float(g.norm()) for g in grads_r.values())
+                worst = max((float((mine[n] - grads_r[n]).norm()) / gmax, n) for n in grads_r)
+                print("batch %d: flat-gradient relative L2 error %.3e; worst tensor (vs largest norm) %.3e %s"
+                      % (batch, (num / den) ** 0.5, worst[0], worst[1]))
+                assert (num / den) ** 0.5 < 1e-2, (num / den) ** 0.5
+                assert worst[0] < 1e-2, worst
+        print("losses  reference %s\n        product   %s" % (ref_losses, my_losses))
+        # after Adam steps from identical parameters the trajectories stay together (Adam's first updates are
+        # lr * sign(g): last-bit gradient noise moves near-zero-gradient weights by 1e-3, which the loss barely sees)
+        for a, b in zip(my_losses[1:], ref_losses[1:]):
+            assert abs(a - b) < 2e-2 * abs(b), (my_losses, ref_losses)
+    finally:
+        torch.backends.cudnn.enabled = prev
+
+
+def test_unchanged_reference_model_runs_on_dropin_and_equals_reference_kernels():
+    """src/modellearn_proj_center.py + the trainer's loop body, byte for byte, on dropin/ (libi2p_b200.so): forward
+    IDENTICAL to the same files on the reference's own kernels, gradients equal up to atomic summation order."""
+    _f32_mode()
+    prev = torch.backends.cudnn.enabled
+    torch.backends.cudnn.enabled = False
+    try:
+        from i2pnet_b200 import _cabi
+        ns_r, ns_d = ref_live.load("ref"), ref_live.load("dropin")
+        assert ns_d.extension.__file__.endswith("dropin/pointnet2/pointnet2_cuda.py")
+        assert ns_r.extension.__file__.endswith("_ref/pointnet2_cuda.so")
+        ref = _reference_model(ns_r)
+        mine = _reference_model(ns_d)
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        bt = _batch(4, 300)
+        before = _cabi.launch_count()
+        o3d, o4d, ld = ref_live.forward_loss(ns_d, mine, bt)
+        ld.backward()
+        launches = _cabi.launch_count() - before
+        o3r, o4r, lr_ = ref_live.forward_loss(ns_r, ref, bt)
+        lr_.backward()
+        assert launches >= 9 + 2, launches          # 9 window selects + the cost volume's grouping (fwd + grad)
+        assert torch.equal(o3d, o3r) and torch.equal(o4d, o4r) and torch.equal(ld, lr_)
+        gmax = max(float(p.grad.norm()) for p in ref.parameters())
+        for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
+            assert float((a.grad - b.grad).norm()) <= 1e-4 * gmax, n
+        # the trainer's loop body, two iterations (forward, zero_grad, loss.item(), backward, clip, Adam)
+        opt = ref_live.make_optimizer(mine)
+        losses = [ref_live.train_iteration(ns_d, mine, opt, _batch(4, 301 + i))[1] for i in range(2)]
+        assert all(v == v and v > 0 for v in losses), losses
+    finally:
+        torch.backends.cudnn.enabled = prev
+
+
+def test_unchanged_iter_model_on_dropin_equals_reference_kernels():
+    """src/modellearn_proj_center_iter.py (six level-3 refinements, inference) on dropin/ vs the reference kernels."""
+    _f32_mode()
+    ns_r, ns_d = ref_live.load("ref"), ref_live.load("dropin")
+    torch.manual_seed(2)
+    ref = ns_r.RegNet_v2_iter(cfg=ns_r.cfg).to(DEV).train()
+    mine = ns_d.RegNet_v2_iter(cfg=ns_d.cfg).to(DEV).train()
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    for m in (ref, mine):
+        _silence_dropout(m)
+    bt = _batch(2, 310)
+    with torch.no_grad():
+        a = mine(bt["rgb"], bt["lidar"], bt["raw_point_xyz"], None, bt["intrinsic"], None, None, None, bt["lidar_feats"], ns_d.cfg)
+        b = ref(bt["rgb"], bt["lidar"], bt["raw_point_xyz"], None, bt["intrinsic"], None, None, None, bt["lidar_feats"], ns_r.cfg)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_pointnet2_modules_unchanged_on_dropin():
+    """pointnet2/pointnet2_modules.py:10-156 (PointnetSAModuleMSG / PointnetSAModule / PointnetFPModule) -- the only
+    route to ball_query, three_nn, three_interpolate and gather_operation -- unchanged on dropin/: identical forward,
+    matching gradients."""
+    _f32_mode()
+    ns_r, ns_d = ref_live.load("ref"), ref_live.load("dropin")
+    gen = torch.Generator().manual_seed(9)
+    xyz = ((torch.rand(2, 4096, 3, generator=gen) - 0.5) * 40).to(DEV)
+    feat = torch.randn(2, 6, 4096, generator=gen).to(DEV)
+    outs = {}
+    for tag, ns in (("ref", ns_r), ("dropin", ns_d)):
+        M = ns.pointnet2_modules
+        torch.manual_seed(4)
+        sa = M.PointnetSAModuleMSG(npoint=512, radii=[2.0, 4.0], nsamples=[16, 32], mlps=[[6, 16, 32], [6, 16, 32]], use_xyz=True).to(DEV)
+        sa2 = M.PointnetSAModule(npoint=128, radius=8.0, nsample=16, mlp=[64, 64], use_xyz=True).to(DEV)
+        fp = M.PointnetFPModule(mlp=[64 + 64, 32]).to(DEV)
+        f = feat.clone().requires_grad_(True)
+        x1, f1 = sa(xyz, f)
+        x2, f2 = sa2(x1, f1)
+        up = fp(x1, x2, f1, f2)
+        up.square().mean().backward()
+        outs[tag] = (x1, f1, x2, f2, up, f.grad)
+    for a, b in zip(outs["dropin"][:5], outs["ref"][:5]):
+        assert torch.equal(a, b)
+    assert _rel(outs["dropin"][5], outs["ref"][5]) < 1e-5
