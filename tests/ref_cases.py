@@ -115,6 +115,31 @@ def all_cases():
     return c
 
 
+def big_cases():
+    """BASELINE configs[4] sizes (point-count sweep 32k ... 131k, M = N / 4): too slow for the CPU oracle and too big
+    for a committed fixture, so they are checked LIVE against the reference's own kernels on the GPU box only."""
+    rng = np.random.Generator(np.random.PCG64(4242))
+    c = {}
+    for n in (32768, 65536, 131072):
+        tag = "%dk" % (n // 1024)
+        m = n // 4
+        xyz = _cloud(rng, 2, n)
+        c["fps_" + tag] = dict(op="fps", xyz=xyz, m=m)
+        c["fps_ties_" + tag] = dict(op="fps", xyz=_cloud(rng, 1, n, quant=0.5, dup=0.05), m=m // 4)
+        q = np.ascontiguousarray(xyz[:, rng.permutation(n)[:m]])
+        c["ball_" + tag] = dict(op="ball_query", xyz=xyz, new_xyz=q, radius=1.0, nsample=32)
+        c["ball_ties_" + tag] = dict(op="ball_query", xyz=_cloud(rng, 1, n, quant=0.5), new_xyz=np.ascontiguousarray(q[:1, :m // 2]),
+                                     radius=1.5, nsample=16)
+        c["nn3_" + tag] = dict(op="three_nn", unknown=xyz, known=q)
+        w = rng.uniform(0.1, 1.0, (2, m, 3)).astype(np.float32)
+        c["group_" + tag] = dict(op="group", points=rng.standard_normal((2, 16, n)).astype(np.float32),
+                                 idx=rng.integers(0, n, (2, m, 16)).astype(np.int32),
+                                 grad_out=rng.standard_normal((2, 16, m, 16)).astype(np.float32),
+                                 idx3=rng.integers(0, n, (2, m, 3)).astype(np.int32), weight=(w / w.sum(-1, keepdims=True)),
+                                 grad3=rng.standard_normal((2, 16, m)).astype(np.float32))
+    return c
+
+
 # ----------------------------------------------------------------------------------------------
 # runners
 # ----------------------------------------------------------------------------------------------

@@ -46,6 +46,20 @@ def test_oracle_matches_reference_kernel(name, dev, reference_ext):
     ref_cases.compare(case, ref_cases.run_oracle(case), want, "oracle vs reference CUDA kernel")
 
 
+BIG = ref_cases.big_cases   # built lazily: ~100 MB of inputs
+
+
+@pytest.mark.parametrize("name", ["%s_%dk" % (op, n) for n in (32, 64, 128) for op in ("fps", "fps_ties", "ball", "ball_ties", "nn3", "group")])
+def test_sweep_size_kernel_matches_reference_kernel(name, dev, reference_ext):
+    """Exact indices at BASELINE configs[4]'s sizes (N = 32k, 65k, 131k; M = N / 4), against the reference's own kernels."""
+    global BIG
+    if callable(BIG):
+        BIG = BIG()
+    case = BIG[name]
+    want = ref_cases.run_reference(case, *reference_ext, dev)
+    ref_cases.compare(case, ref_cases.run_product(case, dev), want, "sm_100a kernel vs reference CUDA kernel (sweep size)")
+
+
 def _sorted_sets(idx):
     return np.sort(idx, axis=-1)
 

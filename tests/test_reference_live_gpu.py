@@ -82,6 +82,16 @@ def test_captured_step_matches_reference_model_on_reference_kernels(batch):
             opt.zero_grad()
             loss_r.backward()
             grads_r = {n: p.grad.detach().clone() for n, p in ref.named_parameters()}
+            if i == 0:
+                # the reference's distance to ITSELF under a different-but-equivalent evaluation (its library
+                # convolutions through cuDNN instead of ATen's native kernels): the noise floor of f32 gradients here
+                torch.backends.cudnn.enabled = True
+                opt.zero_grad()
+                ref_live.forward_loss(ns, ref, bt)[2].backward()
+                grads_alt = {n: p.grad.detach().clone() for n, p in ref.named_parameters()}
+                torch.backends.cudnn.enabled = False
+                for n, p in ref.named_parameters():
+                    p.grad.copy_(grads_r[n])
             torch.nn.utils.clip_grad_norm_(ref.parameters(), 10.0)
             opt.step()
             # product: one replay of the captured graph
@@ -94,19 +104,25 @@ def test_captured_step_matches_reference_model_on_reference_kernels(batch):
                 assert _rel(eng.out3, out3_r.detach()) < 1e-4 and _rel(eng.out4, out4_r.detach()) < 1e-4
                 assert abs(my_losses[0] - ref_losses[0]) < 1e-4 * abs(ref_losses[0])
                 mine = {n: p.grad for n, p in eng.model.named_parameters()}      # views of the flat gradient buffer
-                num = sum(float((mine[n].double() - grads_r[n].double()).pow(2).sum()) for n in grads_r)
-                den = sum(float(grads_r[n].double().pow(2).sum()) for n in grads_r)
-                gmax = max(float(g.norm()) for g in grads_r.values())
-                worst = max((float((mine[n] - grads_r[n]).norm()) / gmax, n) for n in grads_r)
-                print("batch %d: flat-gradient relative L2 error %.3e; worst tensor (vs largest norm) %.3e %s"
-                      % (batch, (num / den) ** 0.5, worst[0], worst[1]))
-                assert (num / den) ** 0.5 < 1e-2, (num / den) ** 0.5
-                assert worst[0] < 1e-2, worst
+
+                def rel_l2(x, y, pick):
+                    names = [n for n in y if pick(n)]
+                    num = sum(float((x[n].double() - y[n].double()).pow(2).sum()) for n in names)
+                    return (num / sum(float(y[n].double().pow(2).sum()) for n in names)) ** 0.5
+                rgb, rest = (lambda n: n.startswith("RGB_net")), (lambda n: not n.startswith("RGB_net"))
+                err = {k: (rel_l2(mine, grads_r, f), rel_l2(grads_alt, grads_r, f)) for k, f in (("image", rgb), ("points", rest))}
+                print("batch %d: relative L2 gradient error (product vs reference / reference vs itself through cuDNN): %s"
+                      % (batch, {k: "%.2e / %.2e" % v for k, v in err.items()}))
+                # The image branch's 15 overlapping max-pools route gradients through arg-max positions that flip on
+                # 1e-6 forward differences: its bar is the reference's own distance to itself (x3).  The point branch /
+                # cost volumes / heads see the image branch only through RF3 and are held to an absolute bar.
+                assert err["image"][0] < 3 * err["image"][1] + 1e-3, err
+                assert err["points"][0] < max(2e-3, 3 * err["points"][1]), err
         print("losses  reference %s\n        product   %s" % (ref_losses, my_losses))
         # after Adam steps from identical parameters the trajectories stay together (Adam's first updates are
         # lr * sign(g): last-bit gradient noise moves near-zero-gradient weights by 1e-3, which the loss barely sees)
         for a, b in zip(my_losses[1:], ref_losses[1:]):
-            assert abs(a - b) < 2e-2 * abs(b), (my_losses, ref_losses)
+            assert abs(a - b) < 5e-3 * abs(b), (my_losses, ref_losses)      # measured: 2e-4 ... 1.6e-3
     finally:
         torch.backends.cudnn.enabled = prev
 
