@@ -67,6 +67,9 @@ _SIGNATURES = {
     "i2p_rgb_bn_from_running": [_int, _vp, _vp, _flt, _vp, _vp, _vp, _vp, _vp],
     "i2p_rgb_bn_act_pool_fwd": [_int] * 5 + [_vp, _vp, _flt, _vp, _vp],
     "i2p_rgb_bn_act_pool_bwd": [_int] * 6 + [_vp, _vp, _flt] + [_vp] * 6,
+    "i2p_conv3x3_pack": [_int, _int, _int, _vp, _vp, _vp],
+    "i2p_conv3x3_tc": [_int] * 5 + [_vp] * 6,
+    "i2p_conv3x3_wgrad": [_int] * 5 + [_vp] * 4,
     "i2p_pw_linear_bwd_dw": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 4 + [_flt, _vp, _vp],
 }
 
@@ -74,7 +77,7 @@ _SIGNATURES = {
 def exported_symbols():
     """Every entry point include/i2p_b200.h declares."""
     return sorted(list(_SIGNATURES) + ["i2p_last_error", "i2p_abi_version", "i2p_launch_count", "i2p_pw_num_tiles",
-                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out", "i2p_rgb_s12_slots", "i2p_pw_tc_supported", "i2p_pw_pack_floats", "i2p_optim_state_bytes", "i2p_optim_lr_offset"])
+                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out", "i2p_rgb_s12_slots", "i2p_pw_tc_supported", "i2p_pw_pack_floats", "i2p_optim_state_bytes", "i2p_optim_lr_offset", "i2p_conv3x3_pack_floats", "i2p_conv3x3_tiles"])
 
 
 def lib():
@@ -100,6 +103,10 @@ def lib():
         L.i2p_pw_pack_floats.restype = _ll
         L.i2p_optim_state_bytes.restype = _int
         L.i2p_optim_lr_offset.restype = _int
+        L.i2p_conv3x3_pack_floats.argtypes = [_int] * 3
+        L.i2p_conv3x3_pack_floats.restype = _ll
+        L.i2p_conv3x3_tiles.argtypes = [_int, _int]
+        L.i2p_conv3x3_tiles.restype = _int
         L.i2p_rgb_num_chunks.argtypes = [_int]
         L.i2p_rgb_num_chunks.restype = _int
         L.i2p_rgb_s12_slots.restype = _int

@@ -12,8 +12,8 @@ from .. import _cabi
 from .. import streams as _streams
 from .._cabi import _ptr, call, f32
 
-USE_FUSED_RGB_TAIL = True   # False: nn.BatchNorm2d -> nn.LeakyReLU -> nn.MaxPool2d through ATen / cuDNN
-SPLIT_CONV_BACKWARD = os.environ.get("I2P_SPLIT_WGRAD", "1") != "0"  # weight gradients of the 3x3 convolutions on a side stream (see _ConvSplitBackward)
+USE_FUSED_RGB_TAIL = True   # False: nn.BatchNorm2d -> nn.LeakyReLU -> nn.MaxPool2d through ATen / cuDNN (A/B, with USE_OWN_CONV off)
+USE_OWN_CONV = os.environ.get("I2P_OWN_CONV", "1") != "0"   # "0": library (cuDNN) convolutions, for A/B measurements only
 
 
 class _BlockTail(Function):
@@ -68,55 +68,102 @@ class _BlockTail(Function):
         return dy, dgb[0], dgb[1], None, None, None
 
 
-class _ConvSplitBackward(Function):
-    """nn.Conv2d (library convolution, cuDNN) whose backward issues the weight gradient on a side stream: only the data
-    gradient is on the dependent chain of the image branch, the weight gradients are needed by the optimiser alone
-    (streams.defer_or_join: they stay un-joined until the end of the backward pass when a step engine asks for that)."""
+class _ConvBlock(Function):
+    """One pyramid block -- Conv2d(3x3, pad 1) -> BatchNorm2d -> LeakyReLU -> MaxPool2d(3, stride, 1) -- entirely on own
+    kernels (csrc/conv.cu, csrc/rgb.cu):
+      forward : weight pack, implicit-GEMM convolution on the tensor cores with the batch statistics of its output in
+                the epilogue, statistics merge, pooled write;
+      backward: pooling / activation / batch-norm backward -> dy; the data gradient is the same tensor-core kernel on
+                the flipped weights; the weight gradient runs on a side stream (only the optimiser needs it) and
+                accumulates straight into the step engine's flat gradient buffer when there is one (engine.grad_sink)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, conf):
-        ctx.save_for_backward(x, w)
-        ctx.conf, ctx.has_bias = conf, b is not None
+    def forward(ctx, x, w, b, gamma, beta, bn, slope, stride):
+        dev = x.device
+        B, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        L = _cabi.lib()
+        xp = _ptr(x, f32, "conv input", dev)
+        pack = torch.empty(L.i2p_conv3x3_pack_floats(Cin, Cout, 0), dtype=f32, device=dev)
+        call("i2p_conv3x3_pack", dev, Cin, Cout, 0, _ptr(w, f32, "conv weight", dev), pack.data_ptr())
+        batch_stats = bn.training or not bn.track_running_stats
+        ntiles = B * L.i2p_conv3x3_tiles(H, W)
+        y = torch.empty(B, Cout, H, W, dtype=f32, device=dev)
+        tiles = torch.empty(Cout, ntiles, 3, dtype=f32, device=dev) if batch_stats else None
+        call("i2p_conv3x3_tc", dev, B, Cin, Cout, H, W, xp, pack.data_ptr(), _ptr(b, f32, "conv bias", dev) if b is not None else None,
+             y.data_ptr(), tiles.data_ptr() if batch_stats else None)
+        stats = torch.empty(4, Cout, dtype=f32, device=dev)
+        s12 = torch.empty(L.i2p_rgb_s12_slots(), Cout, dtype=torch.float64, device=dev)
+        if batch_stats:
+            track = bn.track_running_stats and bn.running_mean is not None
+            if track and bn.momentum is None:
+                raise _cabi.I2PError("BatchNorm2d(momentum=None) is not covered by the fused RGB block")
+            call("i2p_rgb_bn_finalize", dev, Cout, ntiles, tiles.data_ptr(), _ptr(gamma, f32, "bn weight", dev),
+                 _ptr(beta, f32, "bn bias", dev), float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1),
+                 bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                 bn.num_batches_tracked.data_ptr() if track else None, stats.data_ptr(), s12.data_ptr())
+        else:
+            call("i2p_rgb_bn_from_running", dev, Cout, _ptr(gamma, f32, "bn weight", dev), _ptr(beta, f32, "bn bias", dev),
+                 float(bn.eps), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), stats.data_ptr(), s12.data_ptr())
+        Ho, Wo = L.i2p_rgb_pool_out(H, stride), L.i2p_rgb_pool_out(W, stride)
+        out = torch.empty(B, Cout, Ho, Wo, dtype=f32, device=dev)
+        call("i2p_rgb_bn_act_pool_fwd", dev, B, Cout, H, W, stride, y.data_ptr(), stats.data_ptr(), float(slope), out.data_ptr())
+        ctx.save_for_backward(x, w, y, stats, s12)
+        ctx.meta = (stride, float(slope), bool(batch_stats), b is not None)
         ctx.params = (w, b)
-        stride, padding, dilation, groups = conf
-        return torch.nn.functional.conv2d(x, w, b, stride, padding, dilation, groups)
+        ctx.used = False
+        return out
 
     @staticmethod
-    def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        stride, padding, dilation, groups = ctx.conf
-        bias_sizes = [w.shape[0]] if ctx.has_bias else None
-        back = torch.ops.aten.convolution_backward
+    def backward(ctx, dout):
         from ..engine import grad_sink
+        x, w, y, stats, s12 = ctx.saved_tensors
+        stride, slope, batch_stats, has_bias = ctx.meta
+        dev = y.device
+        B, Cout, H, W = y.shape
+        Cin = x.shape[1]
+        L = _cabi.lib()
+        if ctx.used:          # a second backward through the same graph: the sums start from zero again
+            s12.zero_()
+        ctx.used = True
+        dout = dout.contiguous()
+        dy = torch.empty_like(y)
+        dgb = torch.empty(2, Cout, dtype=f32, device=dev)
+        call("i2p_rgb_bn_act_pool_bwd", dev, B, Cout, H, W, stride, int(batch_stats), y.data_ptr(), stats.data_ptr(), slope,
+             _ptr(dout, f32, "grad_output", dev), s12.data_ptr(), dy.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr())
+        # weight gradient: nobody but the optimiser reads it -> side stream, joined at the end of the backward pass
         sink_w = grad_sink(ctx.params[0])
-        sink_b = grad_sink(ctx.params[1]) if ctx.has_bias else None
-        with _streams.Fork(gy, x, w) as branch:
-            _, gw, gb = back(gy, x, w, bias_sizes, stride, padding, dilation, False, [0, 0], groups,
-                             [False, True, ctx.has_bias])
-            if sink_w is not None:
-                # A tensor produced on the side stream must not be handed to autograd: AccumulateGrad runs on THIS node's
-                # stream and would read it without waiting for the branch.  The gradients go straight into the step
-                # engine's flat buffer on the branch's own stream; the engine joins the branch before it reads the buffer.
-                sink_w.add_(gw)
-                if sink_b is not None:
-                    sink_b.add_(gb)
-                gw = gb = None
+        gw = gb = None
+        with _streams.Fork(dy, x) as branch:
+            if sink_w is None:
+                gw = torch.zeros_like(w)
+            call("i2p_conv3x3_wgrad", dev, B, Cin, Cout, H, W, x.data_ptr(), dy.data_ptr(),
+                 (sink_w if sink_w is not None else gw).data_ptr())
+        if sink_w is not None:
+            _streams.defer_or_join(branch)      # no tensor of the branch is handed to autograd: the sink received it
+        else:
+            branch.join(gw)
+            if has_bias:                          # a bias in front of a batch-norm: sum(dy) over (B, H, W), ~0 by construction
+                gb = dy.sum(dim=(0, 2, 3)) if not batch_stats else torch.zeros(Cout, dtype=f32, device=dev)
+        if sink_w is not None and has_bias and not batch_stats:
+            grad_sink(ctx.params[1]).add_(dy.sum(dim=(0, 2, 3)))
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = back(gy, x, w, bias_sizes, stride, padding, dilation, False, [0, 0], groups, [True, False, False])[0]
-        if sink_w is not None:
-            _streams.defer_or_join(branch)
-        else:
-            branch.join(gw, gb)          # no engine: autograd owns the gradients, so they are joined before it sees them
-        return gx, gw, gb, None
+            pack = torch.empty(L.i2p_conv3x3_pack_floats(Cin, Cout, 1), dtype=f32, device=dev)
+            call("i2p_conv3x3_pack", dev, Cin, Cout, 1, w.data_ptr(), pack.data_ptr())
+            gx = torch.empty_like(x)
+            call("i2p_conv3x3_tc", dev, B, Cout, Cin, H, W, dy.data_ptr(), pack.data_ptr(), None, gx.data_ptr(), None)
+        return gx, gw, gb, dgb[0], dgb[1], None, None, None
 
 
-def _conv(conv, x):
-    if (SPLIT_CONV_BACKWARD and x.is_cuda and torch.is_grad_enabled() and conv.padding_mode == "zeros"
-            and not isinstance(conv.padding, str)):
-        return _ConvSplitBackward.apply(x, conv.weight, conv.bias, (list(conv.stride), list(conv.padding), list(conv.dilation),
-                                                                    conv.groups))
-    return conv(x)
+def _conv_block_supported(x, conv, bn, act, pool):
+    def one(v):
+        return v if isinstance(v, int) else (v[0] if v[0] == v[1] else None)
+    return (x.dtype == f32 and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros" and bn.affine
+            and isinstance(act, nn.LeakyReLU) and one(pool.kernel_size) == 3 and one(pool.padding) == 1
+            and one(pool.stride) in (1, 2) and one(pool.dilation) == 1 and not pool.ceil_mode
+            and (bn.training or bn.track_running_stats))
 
 
 def _fusable(y, bn, act, pool):
@@ -129,14 +176,21 @@ def _fusable(y, bn, act, pool):
 
 
 class _Pyramid(nn.Sequential):
-    """The Sequential the reference builds (same slots, same state_dict keys); on CUDA the three
-    element-wise slots of every block run as one fused operator behind the library convolution."""
+    """The Sequential the reference builds (same slots, same state_dict keys).  On CUDA every block runs as ONE fused
+    operator on own kernels (_ConvBlock); a block configuration those kernels do not cover raises -- there is no
+    library fallback on the device.  CPU tensors (host-logic tests only) take the reference's module-by-module form."""
 
     def forward(self, x):
         mods = list(self)
         for i in range(0, len(mods), 4):
             conv, bn, act, pool = mods[i:i + 4]
-            y = _conv(conv, x)
+            if x.is_cuda and USE_OWN_CONV:
+                if not _conv_block_supported(x, conv, bn, act, pool):
+                    raise _cabi.I2PError("RGB pyramid block %d: configuration not covered by the sm_100a kernels" % (i // 4))
+                stride = pool.stride if isinstance(pool.stride, int) else pool.stride[0]
+                x = _ConvBlock.apply(x.contiguous(), conv.weight, conv.bias, bn.weight, bn.bias, bn, act.negative_slope, stride)
+                continue
+            y = conv(x)          # A/B measurements (USE_OWN_CONV = False: library convolution) and CPU host logic
             if _fusable(y, bn, act, pool):
                 stride = pool.stride if isinstance(pool.stride, int) else pool.stride[0]
                 x = _BlockTail.apply(y, bn.weight, bn.bias, bn, act.negative_slope, stride)

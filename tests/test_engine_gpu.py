@@ -76,15 +76,15 @@ def test_warmup_and_capture_leaves_the_training_state_as_loaded():
 
 def test_side_stream_weight_gradients_land_in_the_flat_buffer_under_replay():
     """The image branch's weight gradients are issued on a side stream and accumulate straight into the flat gradient
-    buffer (engine.grad_sink): under graph replay they must equal the un-split path's (same kernels, same inputs)."""
+    buffer (engine.grad_sink): under graph replay they must equal what the single-stream step computes."""
+    from i2pnet_b200 import streams
     from i2pnet_b200.engine import TrainStep
-    from i2pnet_b200.modules import basicConv
     _f32()
     bt = _batch(4, 72)
     grads = {}
-    for split in (True, False):
-        prev = basicConv.SPLIT_CONV_BACKWARD
-        basicConv.SPLIT_CONV_BACKWARD = split
+    for side in (True, False):
+        prev = streams.ENABLED
+        streams.ENABLED = side
         try:
             eng = TrainStep(4, device=DEV, seed=0, use_graph=True)
             eng.set_lr(0.0)
@@ -93,9 +93,9 @@ def test_side_stream_weight_gradients_land_in_the_flat_buffer_under_replay():
             for _ in range(3):
                 eng.step()
             torch.cuda.synchronize()
-            grads[split] = {n: p.grad.detach().clone() for n, p in eng.model.named_parameters() if n.startswith("RGB_net")}
+            grads[side] = {n: p.grad.detach().clone() for n, p in eng.model.named_parameters() if n.startswith("RGB_net")}
         finally:
-            basicConv.SPLIT_CONV_BACKWARD = prev
+            streams.ENABLED = prev
     gmax = max(float(g.norm()) for g in grads[False].values())
     for n, g in grads[False].items():
         assert float((grads[True][n] - g).norm()) <= 2e-3 * max(float(g.norm()), 1e-3 * gmax), n
