@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) pack_kernel(int cin, int cout, int dgrad,
 
 struct Args {
     int B, ki, no, H, W, Wp, tiles, nchunks;
+    float inv_wp;
     const float *x;        // (B, ki, H, W)
     const float *wpack;
     const float *bias;     // (no) or null
@@ -105,12 +106,18 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NC]) {
     for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Persistent: a CTA owns one n-tile (BN output channels) and loops over (image, 128-position tile) work items.  Per
+// item: [chunk loop: operand loads -> (tensor core done with the stage) -> split + store -> MMAs], then the global loads
+// of the NEXT item's first chunk are issued into registers, and only then the epilogue of this item runs (wait for the
+// MMAs, TMEM -> registers, stores, statistics): the next item's memory latency hides behind it.  TMEM, the barriers and
+// -- for layers of at most 16 input channels -- the weights are set up once per CTA.
 template <int CK, int BN>
-__global__ void __launch_bounds__(THREADS, BN == 16 ? 3 : 2) conv3x3_tc_kernel(const Args a) {
+__global__ void __launch_bounds__(THREADS, 2) conv3x3_tc_kernel(const Args a) {
     constexpr int KG = CK / 4;                                   // channel-group planes per chunk
     constexpr uint32_t A_HALF = KG * PLANE_BYTES;                // hi (or lo) planes of the activation tile
     constexpr uint32_t B_HALF = 9 * KG * BN * 16;                // hi (or lo) weights of one chunk
     constexpr int NC = BN / 2;                                   // accumulator columns per thread in the epilogue
+    constexpr int ITEMS = (KG * SLOTS + THREADS - 1) / THREADS;
     extern __shared__ __align__(128) unsigned char smem[];       // A hi | A lo | B hi | B lo
     __shared__ uint64_t mma_bar, b_bar;
     __shared__ uint32_t tmem_slot;
@@ -118,9 +125,9 @@ __global__ void __launch_bounds__(THREADS, BN == 16 ? 3 : 2) conv3x3_tc_kernel(c
     __shared__ int red_cnt[4];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x, nt = blockIdx.y, b = blockIdx.z;
-    const int i0 = tile * BM, n0 = nt * BN;
+    const int nt = blockIdx.y, n0 = nt * BN;
     const int H = a.H, W = a.W, Wp = a.Wp;
+    const int nwork = a.B * a.tiles;
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 4 * BN);
     if (tid == 0) {
@@ -136,208 +143,265 @@ __global__ void __launch_bounds__(THREADS, BN == 16 ? 3 : 2) conv3x3_tc_kernel(c
     const uint32_t sB = sbase + 2 * A_HALF;
     const float *wblk = a.wpack + (size_t)nt * a.nchunks * (2 * B_HALF / 4);
     const size_t plane = (size_t)H * W;
-    const float *xb = a.x + (size_t)b * a.ki * plane;
+    uint32_t mma_commits = 0, b_loads = 0;     // phase counters of the two barriers (uniform across the CTA)
 
-    for (int c = 0; c < a.nchunks; ++c) {
-        if (c >= 1) umma::mbar_wait(&mma_bar, (uint32_t)(c - 1) & 1u);     // the tensor core is done with the stage
-        if (tid == 0) {     // this chunk's weights: one bulk copy, landing through the async proxy
-            umma::mbar_expect_tx(&b_bar, 2 * B_HALF);
-            umma::bulk_g2s(sB, wblk + (size_t)c * (2 * B_HALF / 4), 2 * B_HALF, &b_bar);
-        }
-        // ---- stage the activation bands of channels c * CK .. + CK - 1: item = (plane g, band, slot)
+    // operand loads of (work item T, chunk c): item = (plane g, band, slot); lanes run along the positions of one band
+    // and plane (coalesced plane reads); all of a thread's loads are in flight before the first is consumed
+    float4 ld[ITEMS];
+    auto fetch = [&](int T, int c) {
+        const int b = T / a.tiles, i0 = (T - b * a.tiles) * BM;
+        const float *xb = a.x + (size_t)b * a.ki * plane;
         const int ch0 = c * CK;
-        for (int it = tid; it < KG * SLOTS; it += THREADS) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int it = tid + i * THREADS;
             const int g = it / SLOTS, s = it - g * SLOTS;          // slot inside the plane: band * BAND + position
             const int band = s / BAND, pos = s - band * BAND;
             // flat padded index of this slot, shifted by two rows so that it is never negative
             const int qq = i0 + (band + 1) * Wp + pos - 1;
-            const int yy = qq / Wp - 2, xx = qq - (yy + 2) * Wp;
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-            if (yy >= 0 && yy < H && xx < W) {
+            const int yy2 = (int)(((float)qq + 0.5f) * a.inv_wp);   // exact: the quotient's fraction is >= 0.5 / Wp away from an integer
+            const int yy = yy2 - 2, xx = qq - yy2 * Wp;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it < KG * SLOTS && yy >= 0 && yy < H && xx < W) {
                 const int ch = ch0 + g * 4;
                 const float *p = xb + (size_t)ch * plane + (size_t)yy * W + xx;
-                if (ch < a.ki) v0 = __ldg(p);
-                if (ch + 1 < a.ki) v1 = __ldg(p + plane);
-                if (ch + 2 < a.ki) v2 = __ldg(p + 2 * plane);
-                if (ch + 3 < a.ki) v3 = __ldg(p + 3 * plane);
+                if (ch < a.ki) v.x = __ldg(p);
+                if (ch + 1 < a.ki) v.y = __ldg(p + plane);
+                if (ch + 2 < a.ki) v.z = __ldg(p + 2 * plane);
+                if (ch + 3 < a.ki) v.w = __ldg(p + 3 * plane);
             }
-            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-            umma::split_tf32(v0, h0, l0);
-            umma::split_tf32(v1, h1, l1);
-            umma::split_tf32(v2, h2, l2);
-            umma::split_tf32(v3, h3, l3);
-            unsigned char *dst = smem + (size_t)g * PLANE_BYTES + (size_t)s * 16;
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(h0, h1, h2, h3);
-            *reinterpret_cast<uint4 *>(dst + A_HALF) = make_uint4(l0, l1, l2, l3);
+            ld[i] = v;
         }
-        umma::fence_smem_to_async();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            umma::mbar_wait(&b_bar, (uint32_t)c & 1u);
-            constexpr uint32_t id = idesc(BN);
+    };
+    auto store = [&]() {     // split into tf32 (hi, lo) and store: conflict-free 128-bit shared stores
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                const uint32_t shift = (uint32_t)((tap / 3) * BAND + (tap % 3)) * 16u;     // band dy + 1, position dx + 1
-#pragma unroll
-                for (int j = 0; j < CK / 8; ++j) {
-                    const uint32_t ao = sbase + shift + (uint32_t)(2 * j) * PLANE_BYTES;
-                    const uint32_t bo = sB + (uint32_t)(tap * KG + 2 * j) * (BN * 16);
-                    const uint64_t ah = umma::smem_desc(ao, PLANE_BYTES, 128), al = umma::smem_desc(ao + A_HALF, PLANE_BYTES, 128);
-                    const uint64_t bh = umma::smem_desc(bo, BN * 16, 128), bl = umma::smem_desc(bo + B_HALF, BN * 16, 128);
-                    // Four accumulators: the tensor core adds into the accumulator with truncation, a bias that grows with
-                    // the number of accumulation steps times |accumulator| (measured 4e-6 of the output at K = 576 with
-                    // one accumulator and same-signed products, i.e. post-activation inputs).  The large hi*hi terms go to
-                    // one accumulator per kernel row (K / 24 steps each), the 2^-11-sized correction terms to a fourth; the
-                    // epilogue adds the four in f32 with round-to-nearest.
-                    umma::mma_tf32(tmem_d + (uint32_t)((tap / 3) * BN), ah, bh, id, !(c == 0 && tap % 3 == 0 && j == 0));
-                    umma::mma_tf32(tmem_d + 3 * BN, al, bh, id, !(c == 0 && tap == 0 && j == 0));
-                    umma::mma_tf32(tmem_d + 3 * BN, ah, bl, id, true);
-                }
+        for (int i = 0; i < ITEMS; ++i) {
+            const int it = tid + i * THREADS;
+            if (it < KG * SLOTS) {
+                const int g = it / SLOTS, s = it - g * SLOTS;
+                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                umma::split_tf32(ld[i].x, h0, l0);
+                umma::split_tf32(ld[i].y, h1, l1);
+                umma::split_tf32(ld[i].z, h2, l2);
+                umma::split_tf32(ld[i].w, h3, l3);
+                unsigned char *dst = smem + (size_t)g * PLANE_BYTES + (size_t)s * 16;
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(h0, h1, h2, h3);
+                *reinterpret_cast<uint4 *>(dst + A_HALF) = make_uint4(l0, l1, l2, l3);
             }
-            umma::commit(&mma_bar);
         }
-    }
-    umma::mbar_wait(&mma_bar, (uint32_t)(a.nchunks - 1) & 1u);
-    umma::fence_after_sync();
+    };
 
-    // ---- epilogue: lane = position i0 + row; warps 0-3 take the first half of the channels, 4-7 the second
-    const int row = (warp & 3) * 32 + lane;
-    const int cbase = (warp >> 2) * NC;
-    const int q = i0 + row;
-    const int yy = q / Wp, xx = q - yy * Wp;
-    const bool valid = yy < H && xx < W;
-    float v[NC];
-    {
-        float u0[NC], u1[NC], u2[NC];
-        const uint32_t t0 = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cbase;
-        tmem_ld<NC>(t0, v);
-        tmem_ld<NC>(t0 + BN, u0);
-        tmem_ld<NC>(t0 + 2 * BN, u1);
-        tmem_ld<NC>(t0 + 3 * BN, u2);
+    int T = blockIdx.x;
+    if (T < nwork) fetch(T, 0);
+    for (; T < nwork; T += gridDim.x) {
+        const int b = T / a.tiles, tile = T - b * a.tiles, i0 = tile * BM;
+        for (int c = 0; c < a.nchunks; ++c) {
+            if (c >= 1) {
+                fetch(T, c);
+                umma::mbar_wait(&mma_bar, (mma_commits - 1) & 1u);          // the tensor core is done with the stage
+            }   // (c == 0: the previous item's epilogue has waited for its last MMAs)
+            const bool load_b = a.nchunks > 1 || b_loads == 0;
+            if (load_b && tid == 0) {   // this chunk's weights: one bulk copy, landing through the async proxy
+                umma::mbar_expect_tx(&b_bar, 2 * B_HALF);
+                umma::bulk_g2s(sB, wblk + (size_t)c * (2 * B_HALF / 4), 2 * B_HALF, &b_bar);
+            }
+            store();
+            umma::fence_smem_to_async();
+            umma::fence_before_sync();       // (orders the previous item's tcgen05.ld before the MMAs that overwrite TMEM)
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after_sync();
+                if (load_b) umma::mbar_wait(&b_bar, b_loads & 1u);
+                constexpr uint32_t id = idesc(BN);
 #pragma unroll
-        for (int j = 0; j < NC; ++j) v[j] = (v[j] + u0[j]) + (u1[j] + u2[j]);
-    }
-    float *yb = a.y + ((size_t)b * a.no) * plane + (size_t)yy * W + xx;
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t shift = (uint32_t)((tap / 3) * BAND + (tap % 3)) * 16u;     // band dy + 1, position dx + 1
 #pragma unroll
-    for (int j = 0; j < NC; ++j) {
-        const int n = n0 + cbase + j;
-        if (a.bias != nullptr && n < a.no) v[j] += __ldg(a.bias + n);
-        if (valid && n < a.no) yb[(size_t)n * plane] = v[j];
+                    for (int j = 0; j < CK / 8; ++j) {
+                        const uint32_t ao = sbase + shift + (uint32_t)(2 * j) * PLANE_BYTES;
+                        const uint32_t bo = sB + (uint32_t)(tap * KG + 2 * j) * (BN * 16);
+                        const uint64_t ah = umma::smem_desc(ao, PLANE_BYTES, 128), al = umma::smem_desc(ao + A_HALF, PLANE_BYTES, 128);
+                        const uint64_t bh = umma::smem_desc(bo, BN * 16, 128), bl = umma::smem_desc(bo + B_HALF, BN * 16, 128);
+                        // Four accumulators: the tensor core adds into the accumulator with truncation, a bias that grows with
+                        // the number of accumulation steps times |accumulator| (measured 4e-6 of the output at K = 576 with
+                        // one accumulator and same-signed products, i.e. post-activation inputs).  The large hi*hi terms go to
+                        // one accumulator per kernel row (K / 24 steps each), the 2^-11-sized correction terms to a fourth; the
+                        // epilogue adds the four in f32 with round-to-nearest.
+                        umma::mma_tf32(tmem_d + (uint32_t)((tap / 3) * BN), ah, bh, id, !(c == 0 && tap % 3 == 0 && j == 0));
+                        umma::mma_tf32(tmem_d + 3 * BN, al, bh, id, !(c == 0 && tap == 0 && j == 0));
+                        umma::mma_tf32(tmem_d + 3 * BN, ah, bl, id, true);
+                    }
+                }
+                umma::commit(&mma_bar);
+            }
+            ++mma_commits;
+            if (load_b) ++b_loads;
+        }
+        if (T + (int)gridDim.x < nwork) fetch(T + gridDim.x, 0);     // next item's loads fly during this item's epilogue
+        umma::mbar_wait(&mma_bar, (mma_commits - 1) & 1u);
+        umma::fence_after_sync();
+
+        // ---- epilogue: lane = position i0 + row; warps 0-3 take the first half of the channels, 4-7 the second
+        const int row = (warp & 3) * 32 + lane;
+        const int cbase = (warp >> 2) * NC;
+        const int q = i0 + row;
+        const int yy = q / Wp, xx = q - yy * Wp;
+        const bool valid = yy < H && xx < W;
+        float v[NC];
+        {
+            float u0[NC], u1[NC], u2[NC];
+            const uint32_t t0 = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cbase;
+            tmem_ld<NC>(t0, v);
+            tmem_ld<NC>(t0 + BN, u0);
+            tmem_ld<NC>(t0 + 2 * BN, u1);
+            tmem_ld<NC>(t0 + 3 * BN, u2);
+#pragma unroll
+            for (int j = 0; j < NC; ++j) v[j] = (v[j] + u0[j]) + (u1[j] + u2[j]);
+        }
+        float *yb = a.y + ((size_t)b * a.no) * plane + (size_t)yy * W + xx;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const int n = n0 + cbase + j;
+            if (a.bias != nullptr && n < a.no) v[j] += __ldg(a.bias + n);
+            if (valid && n < a.no) yb[(size_t)n * plane] = v[j];
+        }
+        if (a.tile_stats != nullptr) {
+            // (count, mean, M2) of the tile's valid positions per channel: warp sums -> CTA mean -> warp sums of squares
+            const unsigned vmask = __ballot_sync(FULL, valid);
+            if (lane == 0 && warp < 4) red_cnt[warp] = __popc(vmask);
+            float s[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                s[j] = valid ? v[j] : 0.f;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s[j] += __shfl_xor_sync(FULL, s[j], off);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) red_sum[warp & 3][cbase + j] = s[j];
+            }
+            __syncthreads();
+            const float cnt = (float)(red_cnt[0] + red_cnt[1] + red_cnt[2] + red_cnt[3]);
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const float mean = cnt > 0.f ? (red_sum[0][cbase + j] + red_sum[1][cbase + j] + red_sum[2][cbase + j] + red_sum[3][cbase + j]) / cnt : 0.f;
+                const float d = valid ? v[j] - mean : 0.f;
+                float m2 = d * d;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(FULL, m2, off);
+                s[j] = m2;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) red_m2[warp & 3][cbase + j] = s[j];
+            }
+            __syncthreads();
+            if (tid < BN && n0 + tid < a.no) {
+                const float mean = cnt > 0.f ? (red_sum[0][tid] + red_sum[1][tid] + red_sum[2][tid] + red_sum[3][tid]) / cnt : 0.f;
+                float *ts = a.tile_stats + ((size_t)(n0 + tid) * ((size_t)a.B * a.tiles) + (size_t)b * a.tiles + tile) * 3;
+                ts[0] = cnt;
+                ts[1] = mean;
+                ts[2] = red_m2[0][tid] + red_m2[1][tid] + red_m2[2][tid] + red_m2[3][tid];
+            }
+            // (red_* are rewritten only after the next item's staging barrier)
+        }
     }
     umma::fence_before_sync();
-    if (a.tile_stats != nullptr) {
-        // (count, mean, M2) of the tile's valid positions per channel: warp sums -> CTA mean -> warp sums of squares
-        const unsigned vmask = __ballot_sync(FULL, valid);
-        if (lane == 0 && warp < 4) red_cnt[warp] = __popc(vmask);
-        float s[NC];
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {
-            s[j] = valid ? v[j] : 0.f;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s[j] += __shfl_xor_sync(FULL, s[j], off);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < NC; ++j) red_sum[warp & 3][cbase + j] = s[j];
-        }
-        __syncthreads();
-        const float cnt = (float)(red_cnt[0] + red_cnt[1] + red_cnt[2] + red_cnt[3]);
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {
-            const float mean = cnt > 0.f ? (red_sum[0][cbase + j] + red_sum[1][cbase + j] + red_sum[2][cbase + j] + red_sum[3][cbase + j]) / cnt : 0.f;
-            const float d = valid ? v[j] - mean : 0.f;
-            float m2 = d * d;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(FULL, m2, off);
-            s[j] = m2;
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < NC; ++j) red_m2[warp & 3][cbase + j] = s[j];
-        }
-        __syncthreads();
-        if (tid < BN && n0 + tid < a.no) {
-            const float mean = cnt > 0.f ? (red_sum[0][tid] + red_sum[1][tid] + red_sum[2][tid] + red_sum[3][tid]) / cnt : 0.f;
-            float *ts = a.tile_stats + ((size_t)(n0 + tid) * ((size_t)a.B * a.tiles) + (size_t)b * a.tiles + tile) * 3;
-            ts[0] = cnt;
-            ts[1] = mean;
-            ts[2] = red_m2[0][tid] + red_m2[1][tid] + red_m2[2][tid] + red_m2[3][tid];
-        }
-    } else {
-        __syncthreads();
-    }
+    __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem_d, 4 * BN);
 }
 
 // ---------------------------------------------------------------------------------------------
 // weight gradient: dW[co][ci][ky][kx] += sum_{b, y, x} dY[b][co][y][x] * X[b][ci][y + ky - 1][x + kx - 1]
-// One CTA = one image tile of TR rows x TW columns (about 512 positions) and one (16 output channels) x (CI input
-// channels, 16 or 4) sub-problem.  x (with a one-position halo, zero outside the image) and dY are staged in shared
-// memory position-major ([position][channel], 20-float records: conflict-free 128-bit stores from the plane-major
-// loads and conflict-free 128-bit loads below).  A thread owns a 4 x 4 block of (co, ci) pairs with all nine taps in
-// registers (144 accumulators) and every 16th position of its rows: per position one LDS.128 of dY and nine of x feed
-// 144 FMAs.  The 16 position-partitions of a block are the lanes of a half-warp: shuffle reduction, then one
-// red.global.add per element and CTA.
+//
+// Persistent CTAs, one (16 output channels) x (CI input channels: 16, or 4 for the three-channel first layer)
+// sub-problem each, looping over image tiles of RL rows x TW columns.  A thread owns a 4 x 4 block of (co, ci) pairs
+// with all nine taps in registers (144 accumulators, kept across tiles) and ONE ROW of the tile: it sweeps the row's TW
+// columns with a 3 x 3 window per input channel in registers, so that a position costs 12 new x values + 4 dY values
+// from shared memory for 144 FMAs.  Tiles are staged plane-major ([channel][row][column], exactly the global layout) by
+// 16-byte cp.async with zero fill outside the image (the column origin of the x tile is 4 to the left of the tile, so
+// every copy is an aligned quad that is entirely inside or outside), double-buffered: tile t + 1 streams in while tile t
+// is being reduced.  Row pitches are 4 (mod 8) floats: the lanes of a warp (= rows) hit 8 different banks.
+// One shuffle reduction over the row-lanes and one red.global.add per element at the very end.
 // ---------------------------------------------------------------------------------------------
 struct WArgs {
-    int B, cin, cout, H, W, TR, TW, tiles_x, tiles_y;
+    int B, cin, cout, H, W, tiles_x, tiles_y, ntiles, vec;
     const float *x, *dy;
     float *dw;
 };
 
-template <int CI>      // input channels per CTA: 16, or 4 for the three-channel first layer
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void *src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int CI, int TW>
+struct WGeom {
+    static constexpr int CIB = CI / 4, NBLK = 4 * CIB, RL = THREADS / NBLK;      // row-lanes = rows of a tile
+    static constexpr int XC = TW + 8;                                             // staged x columns: origin x0 - 4
+    static constexpr int XP = XC + ((4 - XC % 8) + 8) % 8, DP = TW + ((4 - TW % 8) + 8) % 8;   // pitches = 4 (mod 8)
+    static constexpr int X_FLOATS = CI * (RL + 2) * XP, D_FLOATS = 16 * RL * DP;
+    static constexpr int BYTES = 2 * (X_FLOATS + D_FLOATS) * 4;
+};
+
+template <int CI, int TW>
 __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const WArgs a) {
-    constexpr int XS = CI == 16 ? 20 : 4;        // floats per staged x position
-    constexpr int DS = 20;                       // floats per staged dY position (16 channels + 4 padding)
-    constexpr int CIB = CI / 4, NBLK = 4 * CIB;  // 4 x 4 register blocks: 4 along co, CIB along ci
-    constexpr int GROUPS = THREADS / (16 * NBLK);
+    using G = WGeom<CI, TW>;
+    constexpr int CIB = G::CIB, NBLK = G::NBLK, RL = G::RL, XP = G::XP, DP = G::DP;
     extern __shared__ __align__(16) float sm[];
-    const int TR = a.TR, TW = a.TW, XW = TW + 2;
-    float *xs = sm;                                   // (TR + 2) x XW x XS
-    float *ds = sm + (size_t)(TR + 2) * XW * XS;      // TR x TW x DS
     const int tid = threadIdx.x;
-    const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
-    const int cig = blockIdx.y % ((a.cin + CI - 1) / CI), cog = blockIdx.y / ((a.cin + CI - 1) / CI);
-    const int b = blockIdx.z;
-    const int y0 = ty * TR, x0 = tx * TW, ci0 = cig * CI, co0 = cog * 16;
+    const int ncig = (a.cin + CI - 1) / CI;
+    const int cig = blockIdx.y % ncig, cog = blockIdx.y / ncig;
+    const int ci0 = cig * CI, co0 = cog * 16;
     const size_t plane = (size_t)a.H * a.W;
-    const float *xb = a.x + (size_t)b * a.cin * plane, *dyb = a.dy + (size_t)b * a.cout * plane;
+    const int per_image = a.tiles_x * a.tiles_y;
 
-    // ---- stage x: item = (4-channel group, position); lanes run along x (coalesced plane reads)
-    for (int it = tid; it < CIB * (TR + 2) * XW; it += THREADS) {
-        const int g = it / ((TR + 2) * XW), p = it - g * ((TR + 2) * XW);
-        const int r = p / XW, cx = p - r * XW;
-        const int yy = y0 + r - 1, xx = x0 + cx - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
-            const int ch = ci0 + g * 4;
-            const float *src = xb + (size_t)ch * plane + (size_t)yy * a.W + xx;
-            if (ch < a.cin) v.x = __ldg(src);
-            if (ch + 1 < a.cin) v.y = __ldg(src + plane);
-            if (ch + 2 < a.cin) v.z = __ldg(src + 2 * plane);
-            if (ch + 3 < a.cin) v.w = __ldg(src + 3 * plane);
+    auto stage = [&](int t, int buf) {
+        float *xs = sm + (size_t)buf * (G::X_FLOATS + G::D_FLOATS), *ds = xs + G::X_FLOATS;
+        const int b = t / per_image, r_ = t - b * per_image;
+        const int ty = r_ / a.tiles_x, tx = r_ - ty * a.tiles_x;
+        const int y0 = ty * RL, x0 = tx * TW;
+        const float *xb = a.x + (size_t)b * a.cin * plane, *dyb = a.dy + (size_t)b * a.cout * plane;
+        if (a.vec) {
+            constexpr int XQ = G::XC / 4, DQ = TW / 4;
+            for (int it = tid; it < CI * (RL + 2) * XQ; it += THREADS) {
+                const int q = it % XQ, r = (it / XQ) % (RL + 2), ch = it / (XQ * (RL + 2));
+                const int yy = y0 + r - 1, xx = x0 - 4 + 4 * q;
+                const bool ok = ci0 + ch < a.cin && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+                const float *src = ok ? xb + (size_t)(ci0 + ch) * plane + (size_t)yy * a.W + xx : a.x;
+                cp_async16_zfill(umma::smem_u32(xs + (ch * (RL + 2) + r) * XP + 4 * q), src, ok);
+            }
+            for (int it = tid; it < 16 * RL * DQ; it += THREADS) {
+                const int q = it % DQ, r = (it / DQ) % RL, ch = it / (DQ * RL);
+                const int yy = y0 + r, xx = x0 + 4 * q;
+                const bool ok = co0 + ch < a.cout && yy < a.H && xx < a.W;
+                const float *src = ok ? dyb + (size_t)(co0 + ch) * plane + (size_t)yy * a.W + xx : a.dy;
+                cp_async16_zfill(umma::smem_u32(ds + (ch * RL + r) * DP + 4 * q), src, ok);
+            }
+        } else {       // any width / alignment: element-wise copies
+            for (int it = tid; it < CI * (RL + 2) * G::XC; it += THREADS) {
+                const int c = it % G::XC, r = (it / G::XC) % (RL + 2), ch = it / (G::XC * (RL + 2));
+                const int yy = y0 + r - 1, xx = x0 - 4 + c;
+                const bool ok = ci0 + ch < a.cin && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+                const float *src = ok ? xb + (size_t)(ci0 + ch) * plane + (size_t)yy * a.W + xx : a.x;
+                cp_async4_zfill(umma::smem_u32(xs + (ch * (RL + 2) + r) * XP + c), src, ok);
+            }
+            for (int it = tid; it < 16 * RL * TW; it += THREADS) {
+                const int c = it % TW, r = (it / TW) % RL, ch = it / (TW * RL);
+                const int yy = y0 + r, xx = x0 + c;
+                const bool ok = co0 + ch < a.cout && yy < a.H && xx < a.W;
+                const float *src = ok ? dyb + (size_t)(co0 + ch) * plane + (size_t)yy * a.W + xx : a.dy;
+                cp_async4_zfill(umma::smem_u32(ds + (ch * RL + r) * DP + c), src, ok);
+            }
         }
-        *reinterpret_cast<float4 *>(xs + (size_t)p * XS + g * 4) = v;
-    }
-    for (int it = tid; it < 4 * TR * TW; it += THREADS) {
-        const int g = it / (TR * TW), p = it - g * (TR * TW);
-        const int r = p / TW, cx = p - r * TW;
-        const int yy = y0 + r, xx = x0 + cx;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (yy < a.H && xx < a.W) {
-            const int ch = co0 + g * 4;
-            const float *src = dyb + (size_t)ch * plane + (size_t)yy * a.W + xx;
-            if (ch < a.cout) v.x = __ldg(src);
-            if (ch + 1 < a.cout) v.y = __ldg(src + plane);
-            if (ch + 2 < a.cout) v.z = __ldg(src + 2 * plane);
-            if (ch + 3 < a.cout) v.w = __ldg(src + 3 * plane);
-        }
-        *reinterpret_cast<float4 *>(ds + (size_t)p * DS + g * 4) = v;
-    }
-    __syncthreads();
+    };
 
-    const int part = tid & 15, blk = (tid >> 4) % NBLK, grp = tid / (16 * NBLK);
+    const int row = tid % RL, blk = tid / RL;
     const int cob = blk / CIB, cib = blk - cob * CIB;
     float acc[4][4][9];
 #pragma unroll
@@ -347,34 +411,64 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const WArgs a) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) acc[i][j][t] = 0.f;
 
-    for (int r = grp; r < TR; r += GROUPS) {
-        for (int cx = part; cx < TW; cx += 16) {
-            const float4 d = *reinterpret_cast<const float4 *>(ds + (size_t)(r * TW + cx) * DS + cob * 4);
-            const float dv[4] = {d.x, d.y, d.z, d.w};
+    int t = blockIdx.x, it_ = 0;
+    if (t < a.ntiles) stage(t, 0);
+    cp_async_commit();
+    for (; t < a.ntiles; t += gridDim.x, ++it_) {
+        const int buf = it_ & 1;
+        if (t + (int)gridDim.x < a.ntiles) stage(t + gridDim.x, buf ^ 1);     // the other buffer was released by the barrier below
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const float *xs = sm + (size_t)buf * (G::X_FLOATS + G::D_FLOATS), *ds = xs + G::X_FLOATS;
+        // rows beyond the image hold zeros in both operands: no need to mask the sweep
+        const float *xr = xs + ((cib * 4) * (RL + 2) + row) * XP;       // channel cib*4, tile row `row` - 1 (the window's top)
+        const float *dr = ds + ((cob * 4) * RL + row) * DP;
+        float w[4][3][3];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float4 xv = *reinterpret_cast<const float4 *>(xs + (size_t)((r + t / 3) * XW + cx + t % 3) * XS + cib * 4);
-                const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j][t] = __fmaf_rn(dv[i], xa[j], acc[i][j][t]);
+            for (int ky = 0; ky < 3; ++ky) {
+                w[j][ky][1] = xr[(j * (RL + 2) + ky) * XP + 3];          // column x0 - 1
+                w[j][ky][2] = xr[(j * (RL + 2) + ky) * XP + 4];          // column x0
             }
+#pragma unroll 4
+        for (int c = 0; c < TW; ++c) {
+            float d[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = dr[i * RL * DP + c];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    w[j][ky][0] = w[j][ky][1];
+                    w[j][ky][1] = w[j][ky][2];
+                    w[j][ky][2] = xr[(j * (RL + 2) + ky) * XP + c + 5];
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) acc[i][j][k] = __fmaf_rn(d[i], w[j][k / 3][k % 3], acc[i][j][k]);
         }
+        __syncthreads();
     }
-    // ---- reduce the 16 position-partitions (lanes of a half-warp), then one atomic per element
+    cp_async_wait<0>();
+    // ---- reduce over the row-lanes of a block that share a warp, then one atomic per element and warp
+    constexpr int LANES = RL < 32 ? RL : 32;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                float s = acc[i][j][t];
+            for (int k = 0; k < 9; ++k) {
+                float v = acc[i][j][k];
 #pragma unroll
-                for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
-                acc[i][j][t] = s;
+                for (int off = LANES / 2; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+                acc[i][j][k] = v;
             }
-    if (part == 0) {
+    if (tid % LANES == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int co = co0 + cob * 4 + i;
@@ -383,7 +477,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const WArgs a) {
                 const int ci = ci0 + cib * 4 + j;
                 if (co < a.cout && ci < a.cin) {
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) atomicAdd(a.dw + ((size_t)co * a.cin + ci) * 9 + t, acc[i][j][t]);
+                    for (int k = 0; k < 9; ++k) atomicAdd(a.dw + ((size_t)co * a.cin + ci) * 9 + k, acc[i][j][k]);
                 }
             }
         }
@@ -424,14 +518,25 @@ int i2p_conv3x3_tc(int B, int ki, int no, int H, int W, const float *x, const fl
                    float *tile_stats, void *stream) {
     using namespace i2p;
     I2P_REQUIRE(B >= 1 && B <= 65535 && ki >= 1 && no >= 1 && H >= 1 && W >= 1, "conv3x3_tc: bad sizes");
-    I2P_REQUIRE((long long)(H + 3) * (W + conv::PAD) < (1LL << 30), "conv3x3_tc: image too large");
+    I2P_REQUIRE((long long)(H + 3) * (W + conv::PAD) < (1LL << 20), "conv3x3_tc: image too large (flat padded index must stay below 2^20)");
     I2P_REQUIRE((reinterpret_cast<uintptr_t>(wpack) & 15) == 0, "conv3x3_tc: wpack must be 16-byte aligned");
     conv::Args a;
     a.B = B; a.ki = ki; a.no = no; a.H = H; a.W = W; a.Wp = W + conv::PAD;
+    a.inv_wp = 1.0f / (float)a.Wp;
     a.tiles = i2p_conv3x3_tiles(H, W);
     a.nchunks = conv::chunks_of(ki);
     a.x = x; a.wpack = wpack; a.bias = bias; a.y = y; a.tile_stats = tile_stats;
-    dim3 grid(a.tiles, conv::ntiles_of(no), B);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int nn = conv::ntiles_of(no);
+    long long gx = (2LL * sms + nn - 1) / nn;          // two resident CTAs per SM over all n-tiles
+    if (gx > (long long)a.tiles * B) gx = (long long)a.tiles * B;
+    dim3 grid((unsigned)gx, nn);
     cudaStream_t s = as_stream(stream);
 #define I2P_CONV(CK_, BN_)                                                                                          \
     do {                                                                                                            \
@@ -452,27 +557,34 @@ int i2p_conv3x3_wgrad(int B, int cin, int cout, int H, int W, const float *x, co
     I2P_REQUIRE(B >= 1 && B <= 65535 && cin >= 1 && cout >= 1 && H >= 1 && W >= 1, "conv3x3_wgrad: bad sizes");
     conv::WArgs a;
     a.B = B; a.cin = cin; a.cout = cout; a.H = H; a.W = W;
-    a.TW = W < 128 ? W : 128;
-    a.TR = 512 / a.TW;
-    if (a.TR > H) a.TR = H;
-    if (a.TR < 1) a.TR = 1;
-    a.tiles_x = ceil_div(W, a.TW);
-    a.tiles_y = ceil_div(H, a.TR);
     a.x = x; a.dy = dy; a.dw = dw;
-    const int ci_t = cin <= 4 ? 4 : 16;
-    dim3 grid(a.tiles_x * a.tiles_y, ceil_div(cin, ci_t) * ceil_div(cout, 16), B);
-    const int xs = ci_t == 16 ? 20 : 4;
-    const int bytes = ((a.TR + 2) * (a.TW + 2) * xs + a.TR * a.TW * 20) * 4;
+    a.vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(dy) % 16 == 0);
     cudaStream_t s = as_stream(stream);
-    if (ci_t == 16) {
-        static bool once = false;
-        if (!once) { conv::allow_smem(conv::wgrad_kernel<16>, 128 * 1024); once = true; }
-        conv::wgrad_kernel<16><<<grid, conv::THREADS, bytes, s>>>(a);
-    } else {
-        static bool once = false;
-        if (!once) { conv::allow_smem(conv::wgrad_kernel<4>, 128 * 1024); once = true; }
-        conv::wgrad_kernel<4><<<grid, conv::THREADS, bytes, s>>>(a);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
     }
+#define I2P_WGRAD(CI_, TW_)                                                                                    \
+    do {                                                                                                       \
+        using G = conv::WGeom<CI_, TW_>;                                                                       \
+        static bool once = false;                                                                              \
+        if (!once) { conv::allow_smem(conv::wgrad_kernel<CI_, TW_>, G::BYTES); once = true; }                  \
+        a.tiles_x = ceil_div(W, TW_);                                                                          \
+        a.tiles_y = ceil_div(H, G::RL);                                                                        \
+        a.ntiles = a.tiles_x * a.tiles_y * B;                                                                  \
+        const int groups = ceil_div(cin, CI_) * ceil_div(cout, 16);                                            \
+        int gx = sms / groups;                                                                                 \
+        if (gx < 1) gx = 1;                                                                                    \
+        if (gx > a.ntiles) gx = a.ntiles;                                                                      \
+        dim3 grid(gx, groups);                                                                                 \
+        conv::wgrad_kernel<CI_, TW_><<<grid, conv::THREADS, G::BYTES, s>>>(a);                                 \
+    } while (0)
+    if (cin <= 4) I2P_WGRAD(4, 8);
+    else I2P_WGRAD(16, 32);
+#undef I2P_WGRAD
     return check_launch("conv3x3_wgrad");
 }
 }

@@ -156,6 +156,30 @@ def main():
             for k, v in sorted(names.items(), key=lambda kv: -kv[1][0])[:60]:
                 fh.write("| %.1f %% | %.1f | %.1f | `%s` |\n" % (100 * v[0] / total, v[0] / reps, v[1] / reps, k[:120]))
         print("wrote", out)
+    elif what == "timeline":
+        # one replay of the captured step as a time-ordered kernel list (start offset, duration, stream, name): the input
+        # of the critical-path analysis (which stream is busy when, where the step waits)
+        from torch.profiler import ProfilerActivity, profile
+        batch = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+        eng2 = TrainStep(batch, device=dev, use_graph=True)
+        eng2.load({k: v.to(dev) for k, v in make_pairs(batch, seed=0).items()})
+        eng2.warmup_and_capture(eager_steps=3)
+        for _ in range(3):
+            eng2.step()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            eng2.step()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.elapsed_us() > 0]
+        evs.sort(key=lambda e: e.time_range.start)
+        t0 = evs[0].time_range.start
+        out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/timeline.csv"
+        with open(out, "w") as fh:
+            fh.write("start_us,dur_us,stream,name\n")
+            for e in evs:
+                fh.write("%.2f,%.2f,%s,\"%s\"\n" % (e.time_range.start - t0, e.time_range.elapsed_us(),
+                                                   getattr(e, "device_resource_id", None), e.name[:100].replace('"', "'")))
+        print("wrote", out, len(evs), "kernels, span %.1f us" % (evs[-1].time_range.end - t0))
     elif what == "marked":
         marked_step(eng, sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/markers.json")
     else:  # forward only

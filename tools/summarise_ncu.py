@@ -14,7 +14,7 @@ import re
 import sys
 from collections import OrderedDict
 
-OWN = ("i2p::", "tc::")
+OWN = ("i2p::", "tc::", "conv::")
 
 
 def _rows(path):
