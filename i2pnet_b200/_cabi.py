@@ -77,7 +77,7 @@ _SIGNATURES = {
 def exported_symbols():
     """Every entry point include/i2p_b200.h declares."""
     return sorted(list(_SIGNATURES) + ["i2p_last_error", "i2p_abi_version", "i2p_launch_count", "i2p_pw_num_tiles",
-                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out", "i2p_rgb_s12_slots", "i2p_pw_tc_supported", "i2p_pw_pack_floats", "i2p_optim_state_bytes", "i2p_optim_lr_offset", "i2p_conv3x3_pack_floats", "i2p_conv3x3_tiles"])
+                   "i2p_set_mlp_tensor_cores", "i2p_get_mlp_tensor_cores", "i2p_rgb_num_chunks", "i2p_rgb_pool_out", "i2p_rgb_s12_slots", "i2p_pw_tc_supported", "i2p_pw_pack_floats", "i2p_optim_state_bytes", "i2p_optim_lr_offset", "i2p_conv3x3_pack_floats", "i2p_conv3x3_tiles", "i2p_conv3x3_stat_slots"])
 
 
 def lib():
@@ -107,6 +107,8 @@ def lib():
         L.i2p_conv3x3_pack_floats.restype = _ll
         L.i2p_conv3x3_tiles.argtypes = [_int, _int]
         L.i2p_conv3x3_tiles.restype = _int
+        L.i2p_conv3x3_stat_slots.argtypes = [_int] * 4
+        L.i2p_conv3x3_stat_slots.restype = _int
         L.i2p_rgb_num_chunks.argtypes = [_int]
         L.i2p_rgb_num_chunks.restype = _int
         L.i2p_rgb_s12_slots.restype = _int

@@ -32,14 +32,14 @@ namespace conv {
 
 constexpr int BM = 128, THREADS = 256;
 constexpr int BAND = BM + 2, SLOTS = 3 * BAND;            // positions per band / per plane
-constexpr uint32_t PLANE_BYTES = SLOTS * 16;              // 6240
+constexpr uint32_t PLANE_BYTES = SLOTS * 16 + 48;         // 6288 = 16 (mod 128): consecutive planes are 4 banks apart (see the staging)
 constexpr int PAD = 4;                                    // Wp = W + PAD
 
 __host__ __device__ constexpr int ck_of(int ki) { return ki < 16 ? 8 : 16; }                 // channels per chunk
 __host__ __device__ constexpr int bn_of(int no) { return no <= 16 ? 16 : 32; }               // output channels per CTA
 __host__ __device__ inline int chunks_of(int ki) { return (ki + ck_of(ki) - 1) / ck_of(ki); }
 __host__ __device__ inline int ntiles_of(int no) { return (no + bn_of(no) - 1) / bn_of(no); }
-// floats of one (n-tile, chunk) weight block: [hi | lo][tap 9][k-group CK/4][n BN][4]
+// floats of one (n-tile, chunk) weight block: [tap 9][k-group CK/4][hi n BN | lo n BN][4]
 __host__ __device__ inline long long block_floats(int ki, int no) { return 2LL * 9 * (ck_of(ki) / 4) * bn_of(no) * 4; }
 
 // W (no_src..): forward  pack[n = co][k = ci][tap] = w[co][ci][tap]            (w is (cout, cin, 3, 3))
@@ -62,10 +62,11 @@ __global__ void __launch_bounds__(256) pack_kernel(int cin, int cout, int dgrad,
         if (n < no && k < ki) v = dgrad ? __ldg(w + ((size_t)k * cin + n) * 9 + (8 - tap)) : __ldg(w + ((size_t)n * cin + k) * 9 + tap);
         uint32_t hi, lo;
         umma::split_tf32(v, hi, lo);
-        float *base = pack + blk * 2 * half;
-        const long long off = e - blk * half;
-        base[off] = __uint_as_float(hi);
-        base[half + off] = __uint_as_float(lo);
+        // [tap][k-group][hi rows 0 .. bn-1 | lo rows 0 .. bn-1][4]: the hi and lo halves of one (tap, k-group) are ONE
+        // K-major operand of 2 bn rows, so that A_hi x [B_hi | B_lo] is a single MMA of N = 2 bn
+        float *base = pack + blk * 2 * half + ((size_t)(tap * kgs + kg) * 2 * bn) * 4;
+        base[nl * 4 + el] = __uint_as_float(hi);
+        base[(bn + nl) * 4 + el] = __uint_as_float(lo);
     }
 }
 
@@ -76,7 +77,7 @@ struct Args {
     const float *wpack;
     const float *bias;     // (no) or null
     float *y;              // (B, no, H, W)
-    float *tile_stats;     // (no, B * tiles, 3) = (count, mean, M2) or null
+    float *tile_stats;     // (no, gridDim.x, 3) = (count, mean, M2) per CTA, or null
 };
 
 __host__ __device__ constexpr uint32_t idesc(int n) {     // kind::tf32, f32 accumulate, K-major A and B, M = 128
@@ -111,17 +112,30 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NC]) {
 // of the NEXT item's first chunk are issued into registers, and only then the epilogue of this item runs (wait for the
 // MMAs, TMEM -> registers, stores, statistics): the next item's memory latency hides behind it.  TMEM, the barriers and
 // -- for layers of at most 16 input channels -- the weights are set up once per CTA.
-template <int CK, int BN>
+//
+// The kernel is bound by instruction issue (ncu, profiles/r2_conv_full.md), so the staging is vectorised (VEC: W % 4 == 0
+// and 16-byte aligned planes): an item is 4 consecutive positions x the 4 channels of one plane = four LDG.128, sixteen
+// splits, eight STS.128.  A quad never straddles a row end (Wp, the tile origin and the quad offset are multiples of 4),
+// so it is entirely inside or outside the image.  Lanes of a quarter-warp hold the KG planes x consecutive quads; planes
+// are 16 (mod 128) bytes apart, so that the eight 16-byte stores of a phase fall into eight different bank groups.
+// The batch statistics are accumulated in registers over ALL items of the CTA as sums shifted by a per-channel reference
+// (the first item's mean, so that the cancellation in M2 = S2 - S1^2 / n stays mild) and reduced once per CTA.
+template <int CK, int BN, bool VEC>
 __global__ void __launch_bounds__(THREADS, 2) conv3x3_tc_kernel(const Args a) {
     constexpr int KG = CK / 4;                                   // channel-group planes per chunk
     constexpr uint32_t A_HALF = KG * PLANE_BYTES;                // hi (or lo) planes of the activation tile
-    constexpr uint32_t B_HALF = 9 * KG * BN * 16;                // hi (or lo) weights of one chunk
+    constexpr uint32_t B_HALF = 9 * KG * BN * 16;                // half the bytes of one chunk's weights (hi and lo interleaved per k-group)
     constexpr int NC = BN / 2;                                   // accumulator columns per thread in the epilogue
-    constexpr int ITEMS = (KG * SLOTS + THREADS - 1) / THREADS;
+    constexpr int SITEMS = (KG * SLOTS + THREADS - 1) / THREADS; // scalar path: items = (plane, slot)
+    constexpr int QPW = 32 / KG;                                 // vector path: quads per warp-item (lanes = KG planes x QPW quads)
+    constexpr int WITEMS = 3 * 32 / QPW;                         // warp-items per chunk: 3 bands x 32 quads
+    constexpr int VROUNDS = (WITEMS + 7) / 8;
+    constexpr int NLD = VEC ? 4 * VROUNDS + 1 : SITEMS;
+    constexpr uint32_t TCOLS = BN == 16 ? 128 : 256;             // six accumulators of BN columns, rounded up to a power of two
     extern __shared__ __align__(128) unsigned char smem[];       // A hi | A lo | B hi | B lo
     __shared__ uint64_t mma_bar, b_bar;
     __shared__ uint32_t tmem_slot;
-    __shared__ float red_sum[4][BN], red_m2[4][BN];
+    __shared__ float red_sum[4][BN], red_m2[4][BN], ref_s[THREADS / 32][NC];
     __shared__ int red_cnt[4];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -129,9 +143,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tc_kernel(const Args a) {
     const int H = a.H, W = a.W, Wp = a.Wp;
     const int nwork = a.B * a.tiles;
 
-    if (warp == 0) umma::tmem_alloc(&tmem_slot, 4 * BN);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, TCOLS);
     if (tid == 0) {
-        umma::mbar_init(&mma_bar, 1);
+        umma::mbar_init(&mma_bar, 3);      // three issuing warps commit per chunk
         umma::mbar_init(&b_bar, 1);
         umma::mbar_fence_init();
     }
@@ -145,51 +159,127 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tc_kernel(const Args a) {
     const size_t plane = (size_t)H * W;
     uint32_t mma_commits = 0, b_loads = 0;     // phase counters of the two barriers (uniform across the CTA)
 
-    // operand loads of (work item T, chunk c): item = (plane g, band, slot); lanes run along the positions of one band
-    // and plane (coalesced plane reads); all of a thread's loads are in flight before the first is consumed
-    float4 ld[ITEMS];
+    // row / column of a flat padded index shifted by two rows (never negative); exact: the quotient's fraction is at
+    // least 0.5 / Wp away from an integer and the float error is below that for indices < 2^20
+    auto rowcol = [&](int qq, int &yy, int &xx) {
+        const int y2 = (int)(((float)qq + 0.5f) * a.inv_wp);
+        yy = y2 - 2;
+        xx = qq - y2 * Wp;
+    };
+
+    float4 ld[NLD];
     auto fetch = [&](int T, int c) {
         const int b = T / a.tiles, i0 = (T - b * a.tiles) * BM;
         const float *xb = a.x + (size_t)b * a.ki * plane;
         const int ch0 = c * CK;
+        if constexpr (VEC) {
+            const int g = lane % KG, kk = lane / KG;
+            const int ch = ch0 + g * 4;
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const int it = tid + i * THREADS;
-            const int g = it / SLOTS, s = it - g * SLOTS;          // slot inside the plane: band * BAND + position
-            const int band = s / BAND, pos = s - band * BAND;
-            // flat padded index of this slot, shifted by two rows so that it is never negative
-            const int qq = i0 + (band + 1) * Wp + pos - 1;
-            const int yy2 = (int)(((float)qq + 0.5f) * a.inv_wp);   // exact: the quotient's fraction is >= 0.5 / Wp away from an integer
-            const int yy = yy2 - 2, xx = qq - yy2 * Wp;
+            for (int r = 0; r < VROUNDS; ++r) {
+                const int wi = warp + 8 * r;                         // warp-item: (band, group of QPW quads)
+                const int band = wi / (32 / QPW), k = (wi % (32 / QPW)) * QPW + kk;
+                int yy, xx;
+                rowcol(i0 + (band + 1) * Wp + 4 * k, yy, xx);
+                const bool ok = wi < WITEMS && yy >= 0 && yy < H && xx < W;
+                const float4 *p = reinterpret_cast<const float4 *>(xb + (size_t)ch * plane + (size_t)yy * W + xx);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                ld[4 * r + 0] = ok && ch < a.ki ? __ldg(p) : z;
+                ld[4 * r + 1] = ok && ch + 1 < a.ki ? __ldg(p + plane / 4) : z;
+                ld[4 * r + 2] = ok && ch + 2 < a.ki ? __ldg(p + 2 * (plane / 4)) : z;
+                ld[4 * r + 3] = ok && ch + 3 < a.ki ? __ldg(p + 3 * (plane / 4)) : z;
+            }
+            // the two halo positions of every band and plane (slot 0 and slot 129): threads 0 .. 6 KG - 1
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (it < KG * SLOTS && yy >= 0 && yy < H && xx < W) {
-                const int ch = ch0 + g * 4;
-                const float *p = xb + (size_t)ch * plane + (size_t)yy * W + xx;
-                if (ch < a.ki) v.x = __ldg(p);
-                if (ch + 1 < a.ki) v.y = __ldg(p + plane);
-                if (ch + 2 < a.ki) v.z = __ldg(p + 2 * plane);
-                if (ch + 3 < a.ki) v.w = __ldg(p + 3 * plane);
+            if (tid < 6 * KG) {
+                const int g2 = tid % KG, e = tid / KG, band = e >> 1, pos = (e & 1) * (BAND - 1);
+                int yy, xx;
+                rowcol(i0 + (band + 1) * Wp + pos - 1, yy, xx);
+                if (yy >= 0 && yy < H && xx < W) {
+                    const int ch2 = ch0 + g2 * 4;
+                    const float *p = xb + (size_t)ch2 * plane + (size_t)yy * W + xx;
+                    if (ch2 < a.ki) v.x = __ldg(p);
+                    if (ch2 + 1 < a.ki) v.y = __ldg(p + plane);
+                    if (ch2 + 2 < a.ki) v.z = __ldg(p + 2 * plane);
+                    if (ch2 + 3 < a.ki) v.w = __ldg(p + 3 * plane);
+                }
             }
-            ld[i] = v;
-        }
-    };
-    auto store = [&]() {     // split into tf32 (hi, lo) and store: conflict-free 128-bit shared stores
+            ld[4 * VROUNDS] = v;
+        } else {
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const int it = tid + i * THREADS;
-            if (it < KG * SLOTS) {
-                const int g = it / SLOTS, s = it - g * SLOTS;
-                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-                umma::split_tf32(ld[i].x, h0, l0);
-                umma::split_tf32(ld[i].y, h1, l1);
-                umma::split_tf32(ld[i].z, h2, l2);
-                umma::split_tf32(ld[i].w, h3, l3);
-                unsigned char *dst = smem + (size_t)g * PLANE_BYTES + (size_t)s * 16;
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(h0, h1, h2, h3);
-                *reinterpret_cast<uint4 *>(dst + A_HALF) = make_uint4(l0, l1, l2, l3);
+            for (int i = 0; i < SITEMS; ++i) {
+                const int it = tid + i * THREADS;
+                const int g = it / SLOTS, s = it - g * SLOTS;          // slot inside the plane: band * BAND + position
+                const int band = s / BAND, pos = s - band * BAND;
+                int yy, xx;
+                rowcol(i0 + (band + 1) * Wp + pos - 1, yy, xx);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (it < KG * SLOTS && yy >= 0 && yy < H && xx < W) {
+                    const int ch = ch0 + g * 4;
+                    const float *p = xb + (size_t)ch * plane + (size_t)yy * W + xx;
+                    if (ch < a.ki) v.x = __ldg(p);
+                    if (ch + 1 < a.ki) v.y = __ldg(p + plane);
+                    if (ch + 2 < a.ki) v.z = __ldg(p + 2 * plane);
+                    if (ch + 3 < a.ki) v.w = __ldg(p + 3 * plane);
+                }
+                ld[i] = v;
             }
         }
     };
+    auto put = [&](unsigned char *dst, float v0, float v1, float v2, float v3) {   // split and store one position's 4 channels
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        umma::split_tf32(v0, h0, l0);
+        umma::split_tf32(v1, h1, l1);
+        umma::split_tf32(v2, h2, l2);
+        umma::split_tf32(v3, h3, l3);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(h0, h1, h2, h3);
+        *reinterpret_cast<uint4 *>(dst + A_HALF) = make_uint4(l0, l1, l2, l3);
+    };
+    auto store = [&]() {
+        if constexpr (VEC) {
+            const int g = lane % KG, kk = lane / KG;
+#pragma unroll
+            for (int r = 0; r < VROUNDS; ++r) {
+                const int wi = warp + 8 * r;
+                if (wi < WITEMS) {
+                    const int band = wi / (32 / QPW), k = (wi % (32 / QPW)) * QPW + kk;
+                    unsigned char *dst = smem + (size_t)g * PLANE_BYTES + (size_t)(band * BAND + 1 + 4 * k) * 16;
+                    const float4 c0 = ld[4 * r], c1 = ld[4 * r + 1], c2 = ld[4 * r + 2], c3 = ld[4 * r + 3];
+                    put(dst, c0.x, c1.x, c2.x, c3.x);
+                    put(dst + 16, c0.y, c1.y, c2.y, c3.y);
+                    put(dst + 32, c0.z, c1.z, c2.z, c3.z);
+                    put(dst + 48, c0.w, c1.w, c2.w, c3.w);
+                }
+            }
+            if (tid < 6 * KG) {
+                const int g2 = tid % KG, e = tid / KG, band = e >> 1, pos = (e & 1) * (BAND - 1);
+                const float4 v = ld[4 * VROUNDS];
+                put(smem + (size_t)g2 * PLANE_BYTES + (size_t)(band * BAND + pos) * 16, v.x, v.y, v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < SITEMS; ++i) {
+                const int it = tid + i * THREADS;
+                if (it < KG * SLOTS) {
+                    const int g = it / SLOTS, s = it - g * SLOTS;
+                    put(smem + (size_t)g * PLANE_BYTES + (size_t)s * 16, ld[i].x, ld[i].y, ld[i].z, ld[i].w);
+                }
+            }
+        }
+    };
+
+    // epilogue constants and the statistics accumulators of this thread's NC channels
+    const int row = (warp & 3) * 32 + lane;
+    const int cbase = (warp >> 2) * NC;
+    float s1[NC], s2[NC];     // sums of (y - ref), (y - ref)^2 over this thread's positions; ref (shared memory): per warp and channel
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s1[j] = s2[j] = 0.f;
+    float *ref = ref_s[warp];
+    if (lane < NC) ref[lane] = 0.f;
+    __syncwarp();
+    const float *bias_p = a.bias != nullptr ? a.bias + n0 + cbase : nullptr;    // (read per item: L1-resident broadcast loads)
+    int my_count = 0;
+    bool have_ref = false;
 
     int T = blockIdx.x;
     if (T < nwork) fetch(T, 0);
@@ -209,30 +299,38 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tc_kernel(const Args a) {
             umma::fence_smem_to_async();
             umma::fence_before_sync();       // (orders the previous item's tcgen05.ld before the MMAs that overwrite TMEM)
             __syncthreads();
-            if (tid == 0) {
-                umma::fence_after_sync();
-                if (load_b) umma::mbar_wait(&b_bar, b_loads & 1u);
-                constexpr uint32_t id = idesc(BN);
+            // MMA issue.  Measured on B200 (tools/micro/mma_rate*.cu): ONE thread needs ~120 cycles per tcgen05.mma whatever
+            // N, kind or layout, but issuers on different warps overlap (2 issuers: 60, 4: ~45 cycles per MMA and SM).  With
+            // N = 16 / 32 an MMA is nowhere near 120 cycles of tensor-core work, so the 54 MMAs of a chunk are issued by
+            // three warps, one kernel row each, into their own accumulators: row r adds its hi*hi terms into accumulator 2r
+            // and its two 2^-11-sized correction terms into accumulator 2r + 1 (the tensor core accumulates with truncation:
+            // keeping the number of accumulation steps per large accumulator small keeps that bias at 2e-7, see the
+            // tests); the epilogue adds the six in f32.  hi*hi and hi*lo share their A operand, so they are ONE MMA of
+            // N = 2 BN over the weight rows [hi | lo]: 36 MMAs per chunk instead of 54.  The barrier expects three commits.
+            if (warp < 3) {
+                if (lane == 0) {
+                    umma::fence_after_sync();
+                    if (load_b) umma::mbar_wait(&b_bar, b_loads & 1u);
+                    const int ky = warp;
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t shift = (uint32_t)((tap / 3) * BAND + (tap % 3)) * 16u;     // band dy + 1, position dx + 1
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int tap = ky * 3 + kx;
+                        const uint32_t shift = (uint32_t)(ky * BAND + kx) * 16u;     // band dy + 1, position dx + 1
 #pragma unroll
-                    for (int j = 0; j < CK / 8; ++j) {
-                        const uint32_t ao = sbase + shift + (uint32_t)(2 * j) * PLANE_BYTES;
-                        const uint32_t bo = sB + (uint32_t)(tap * KG + 2 * j) * (BN * 16);
-                        const uint64_t ah = umma::smem_desc(ao, PLANE_BYTES, 128), al = umma::smem_desc(ao + A_HALF, PLANE_BYTES, 128);
-                        const uint64_t bh = umma::smem_desc(bo, BN * 16, 128), bl = umma::smem_desc(bo + B_HALF, BN * 16, 128);
-                        // Four accumulators: the tensor core adds into the accumulator with truncation, a bias that grows with
-                        // the number of accumulation steps times |accumulator| (measured 4e-6 of the output at K = 576 with
-                        // one accumulator and same-signed products, i.e. post-activation inputs).  The large hi*hi terms go to
-                        // one accumulator per kernel row (K / 24 steps each), the 2^-11-sized correction terms to a fourth; the
-                        // epilogue adds the four in f32 with round-to-nearest.
-                        umma::mma_tf32(tmem_d + (uint32_t)((tap / 3) * BN), ah, bh, id, !(c == 0 && tap % 3 == 0 && j == 0));
-                        umma::mma_tf32(tmem_d + 3 * BN, al, bh, id, !(c == 0 && tap == 0 && j == 0));
-                        umma::mma_tf32(tmem_d + 3 * BN, ah, bl, id, true);
+                        for (int j = 0; j < CK / 8; ++j) {
+                            const uint32_t ao = sbase + shift + (uint32_t)(2 * j) * PLANE_BYTES;
+                            const uint32_t bo = sB + (uint32_t)(tap * KG + 2 * j) * (2 * BN * 16);
+                            const uint64_t ah = umma::smem_desc(ao, PLANE_BYTES, 128), al = umma::smem_desc(ao + A_HALF, PLANE_BYTES, 128);
+                            const uint64_t bd = umma::smem_desc(bo, 2 * BN * 16, 128);     // rows 0 .. BN-1: hi, BN .. 2BN-1: lo
+                            const bool first = c == 0 && kx == 0 && j == 0;
+                            // A_hi x [B_hi | B_lo] -> [main | correction] in one MMA of N = 2 BN; A_lo x B_hi -> correction
+                            umma::mma_tf32(tmem_d + (uint32_t)(2 * ky * BN), ah, bd, idesc(2 * BN), !first);
+                            umma::mma_tf32(tmem_d + (uint32_t)((2 * ky + 1) * BN), al, bd, idesc(BN), true);
+                        }
                     }
+                    umma::commit(&mma_bar);
                 }
-                umma::commit(&mma_bar);
+                __syncwarp();     // the issuing warps stay converged: their other lanes do not run ahead into the barrier spin
             }
             ++mma_commits;
             if (load_b) ++b_loads;
@@ -242,73 +340,100 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tc_kernel(const Args a) {
         umma::fence_after_sync();
 
         // ---- epilogue: lane = position i0 + row; warps 0-3 take the first half of the channels, 4-7 the second
-        const int row = (warp & 3) * 32 + lane;
-        const int cbase = (warp >> 2) * NC;
         const int q = i0 + row;
         const int yy = q / Wp, xx = q - yy * Wp;
         const bool valid = yy < H && xx < W;
-        float v[NC];
-        {
-            float u0[NC], u1[NC], u2[NC];
-            const uint32_t t0 = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cbase;
-            tmem_ld<NC>(t0, v);
-            tmem_ld<NC>(t0 + BN, u0);
-            tmem_ld<NC>(t0 + 2 * BN, u1);
-            tmem_ld<NC>(t0 + 3 * BN, u2);
+        // 8 columns at a time (keeps the live registers of the epilogue small); the six accumulators are added in f32.
+        // Statistics: the first item with valid positions sets the warp's per-channel reference (its mean over the warp's
+        // positions); from then on every valid position adds (y - ref) and (y - ref)^2 to this thread's sums.
+        const uint32_t t0 = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cbase;
+        float *yb = a.y + ((size_t)b * a.no + n0 + cbase) * plane + (size_t)yy * W + xx;
+        const bool stats = a.tile_stats != nullptr;
+        const int nvalid = __popc(__ballot_sync(FULL, valid));
+        const bool set_ref = stats && !have_ref && nvalid > 0;
 #pragma unroll
-            for (int j = 0; j < NC; ++j) v[j] = (v[j] + u0[j]) + (u1[j] + u2[j]);
+        for (int h = 0; h < NC; h += 8) {
+            float acc[8];
+            {
+                uint32_t r[6][8];
+#pragma unroll
+                for (int k = 0; k < 6; ++k)      // six loads in flight, ONE wait (a wait per load costs ~300 cycles each)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                                 : "=r"(r[k][0]), "=r"(r[k][1]), "=r"(r[k][2]), "=r"(r[k][3]), "=r"(r[k][4]), "=r"(r[k][5]),
+                                   "=r"(r[k][6]), "=r"(r[k][7])
+                                 : "r"(t0 + (uint32_t)(k * BN + h)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 8; ++j)      // mains (even blocks) and corrections (odd blocks) separately, then together
+                    acc[j] = ((__uint_as_float(r[0][j]) + __uint_as_float(r[2][j])) + __uint_as_float(r[4][j])) +
+                             ((__uint_as_float(r[1][j]) + __uint_as_float(r[3][j])) + __uint_as_float(r[5][j]));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool in = n0 + cbase + h + j < a.no;
+                const float val = acc[j] + (bias_p != nullptr && in ? __ldg(bias_p + h + j) : 0.f);
+                if (valid && in) yb[(size_t)(h + j) * plane] = val;
+                if (set_ref) {
+                    float m = valid ? val : 0.f;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) m += __shfl_xor_sync(FULL, m, off);
+                    if (lane == 0) ref[h + j] = m / (float)nvalid;
+                    __syncwarp();
+                }
+                if (stats && valid) {
+                    const float d = val - ref[h + j];
+                    s1[h + j] += d;
+                    s2[h + j] = __fmaf_rn(d, d, s2[h + j]);
+                }
+            }
         }
-        float *yb = a.y + ((size_t)b * a.no) * plane + (size_t)yy * W + xx;
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {
-            const int n = n0 + cbase + j;
-            if (a.bias != nullptr && n < a.no) v[j] += __ldg(a.bias + n);
-            if (valid && n < a.no) yb[(size_t)n * plane] = v[j];
-        }
-        if (a.tile_stats != nullptr) {
-            // (count, mean, M2) of the tile's valid positions per channel: warp sums -> CTA mean -> warp sums of squares
-            const unsigned vmask = __ballot_sync(FULL, valid);
-            if (lane == 0 && warp < 4) red_cnt[warp] = __popc(vmask);
-            float s[NC];
-#pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                s[j] = valid ? v[j] : 0.f;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) s[j] += __shfl_xor_sync(FULL, s[j], off);
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int j = 0; j < NC; ++j) red_sum[warp & 3][cbase + j] = s[j];
-            }
-            __syncthreads();
-            const float cnt = (float)(red_cnt[0] + red_cnt[1] + red_cnt[2] + red_cnt[3]);
-#pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                const float mean = cnt > 0.f ? (red_sum[0][cbase + j] + red_sum[1][cbase + j] + red_sum[2][cbase + j] + red_sum[3][cbase + j]) / cnt : 0.f;
-                const float d = valid ? v[j] - mean : 0.f;
-                float m2 = d * d;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(FULL, m2, off);
-                s[j] = m2;
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int j = 0; j < NC; ++j) red_m2[warp & 3][cbase + j] = s[j];
-            }
-            __syncthreads();
-            if (tid < BN && n0 + tid < a.no) {
-                const float mean = cnt > 0.f ? (red_sum[0][tid] + red_sum[1][tid] + red_sum[2][tid] + red_sum[3][tid]) / cnt : 0.f;
-                float *ts = a.tile_stats + ((size_t)(n0 + tid) * ((size_t)a.B * a.tiles) + (size_t)b * a.tiles + tile) * 3;
-                ts[0] = cnt;
-                ts[1] = mean;
-                ts[2] = red_m2[0][tid] + red_m2[1][tid] + red_m2[2][tid] + red_m2[3][tid];
-            }
-            // (red_* are rewritten only after the next item's staging barrier)
-        }
+        if (set_ref) have_ref = true;
+        if (stats && valid) ++my_count;
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem_d, 4 * BN);
+    if (warp == 0) umma::tmem_dealloc(tmem_d, TCOLS);
+
+    if (a.tile_stats != nullptr) {
+        // per warp and channel: n, mean = ref + S1 / n, M2 = S2 - S1^2 / n; the four row-warps of a channel are merged
+        // with Chan's formula: one (count, mean, M2) per CTA and channel
+        int cnt_w = my_count;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) cnt_w += __shfl_xor_sync(FULL, cnt_w, off);
+        const float nw = (float)cnt_w;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            float t1 = s1[j], t2 = s2[j];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                t1 += __shfl_xor_sync(FULL, t1, off);
+                t2 += __shfl_xor_sync(FULL, t2, off);
+            }
+            if (lane == 0) {
+                red_sum[warp & 3][cbase + j] = nw > 0.f ? ref[j] + t1 / nw : 0.f;
+                red_m2[warp & 3][cbase + j] = nw > 0.f ? fmaxf(t2 - t1 * t1 / nw, 0.f) : 0.f;
+            }
+        }
+        if (lane == 0 && warp < 4) red_cnt[warp] = cnt_w;
+        __syncthreads();
+        if (tid < BN && n0 + tid < a.no) {
+            float n = 0.f, mu = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float n2 = (float)red_cnt[w];
+                if (n2 > 0.f) {
+                    const float tot = n + n2, d = red_sum[w][tid] - mu, f = n2 / tot;
+                    mu += d * f;
+                    m2 += red_m2[w][tid] + d * d * n * f;
+                    n = tot;
+                }
+            }
+            float *ts = a.tile_stats + ((size_t)(n0 + tid) * gridDim.x + blockIdx.x) * 3;
+            ts[0] = n;
+            ts[1] = mu;
+            ts[2] = m2;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -503,6 +628,25 @@ long long i2p_conv3x3_pack_floats(int cin, int cout, int dgrad) {
 
 int i2p_conv3x3_tiles(int H, int W) { return (H * (W + i2p::conv::PAD) + i2p::conv::BM - 1) / i2p::conv::BM; }
 
+static int conv_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+/* number of persistent CTAs per n-tile of i2p_conv3x3_tc = number of (count, mean, M2) statistics slots per channel */
+int i2p_conv3x3_stat_slots(int B, int no, int H, int W) {
+    const int nn = i2p::conv::ntiles_of(no);
+    long long gx = (2LL * conv_sms() + nn - 1) / nn;          // two resident CTAs per SM over all n-tiles
+    const long long work = (long long)i2p_conv3x3_tiles(H, W) * B;
+    return (int)(gx > work ? work : gx);
+}
+
 int i2p_conv3x3_pack(int cin, int cout, int dgrad, const float *w, float *pack, void *stream) {
     using namespace i2p;
     I2P_REQUIRE(cin >= 1 && cout >= 1 && w != nullptr && pack != nullptr, "conv3x3_pack: bad arguments");
@@ -526,27 +670,21 @@ int i2p_conv3x3_tc(int B, int ki, int no, int H, int W, const float *x, const fl
     a.tiles = i2p_conv3x3_tiles(H, W);
     a.nchunks = conv::chunks_of(ki);
     a.x = x; a.wpack = wpack; a.bias = bias; a.y = y; a.tile_stats = tile_stats;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
     const int nn = conv::ntiles_of(no);
-    long long gx = (2LL * sms + nn - 1) / nn;          // two resident CTAs per SM over all n-tiles
-    if (gx > (long long)a.tiles * B) gx = (long long)a.tiles * B;
-    dim3 grid((unsigned)gx, nn);
+    dim3 grid((unsigned)i2p_conv3x3_stat_slots(B, no, H, W), nn);
     cudaStream_t s = as_stream(stream);
-#define I2P_CONV(CK_, BN_)                                                                                          \
-    do {                                                                                                            \
-        static bool once = false;                                                                                   \
-        if (!once) { conv::allow_smem(conv::conv3x3_tc_kernel<CK_, BN_>, conv::smem_bytes<CK_, BN_>()); once = true; } \
-        conv::conv3x3_tc_kernel<CK_, BN_><<<grid, conv::THREADS, conv::smem_bytes<CK_, BN_>(), s>>>(a);              \
+    const bool vec = W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+#define I2P_CONV(CK_, BN_, V_)                                                                                            \
+    do {                                                                                                                  \
+        static bool once = false;                                                                                         \
+        if (!once) { conv::allow_smem(conv::conv3x3_tc_kernel<CK_, BN_, V_>, conv::smem_bytes<CK_, BN_>()); once = true; } \
+        conv::conv3x3_tc_kernel<CK_, BN_, V_><<<grid, conv::THREADS, conv::smem_bytes<CK_, BN_>(), s>>>(a);                \
     } while (0)
+#define I2P_CONV_V(CK_, BN_) do { if (vec) I2P_CONV(CK_, BN_, true); else I2P_CONV(CK_, BN_, false); } while (0)
     const int ck = conv::ck_of(ki), bn = conv::bn_of(no);
-    if (ck == 8) { if (bn == 16) I2P_CONV(8, 16); else I2P_CONV(8, 32); }
-    else { if (bn == 16) I2P_CONV(16, 16); else I2P_CONV(16, 32); }
+    if (ck == 8) { if (bn == 16) I2P_CONV_V(8, 16); else I2P_CONV_V(8, 32); }
+    else { if (bn == 16) I2P_CONV_V(16, 16); else I2P_CONV_V(16, 32); }
+#undef I2P_CONV_V
 #undef I2P_CONV
     return check_launch("conv3x3_tc");
 }

@@ -87,7 +87,7 @@ class _ConvBlock(Function):
         pack = torch.empty(L.i2p_conv3x3_pack_floats(Cin, Cout, 0), dtype=f32, device=dev)
         call("i2p_conv3x3_pack", dev, Cin, Cout, 0, _ptr(w, f32, "conv weight", dev), pack.data_ptr())
         batch_stats = bn.training or not bn.track_running_stats
-        ntiles = B * L.i2p_conv3x3_tiles(H, W)
+        ntiles = L.i2p_conv3x3_stat_slots(B, Cout, H, W)     # one statistics slot per persistent CTA
         y = torch.empty(B, Cout, H, W, dtype=f32, device=dev)
         tiles = torch.empty(Cout, ntiles, 3, dtype=f32, device=dev) if batch_stats else None
         call("i2p_conv3x3_tc", dev, B, Cin, Cout, H, W, xp, pack.data_ptr(), _ptr(b, f32, "conv bias", dev) if b is not None else None,

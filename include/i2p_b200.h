@@ -263,11 +263,12 @@ int i2p_quat_mul(int B, int N, int na, int nb, int conj_a, int conj_b, const flo
  * NCHW f32.  i2p_conv3x3_pack lays the (cout, cin, 3, 3) weights out once per step as tf32 (hi | lo) halves in the
  * tensor-core operand layout (dgrad = 1: transposed and flipped, for the data gradient); i2p_conv3x3_tc is the
  * implicit GEMM on tcgen05 (3xTF32, f32-accurate): y (B, no, H, W) = conv(x (B, ki, H, W)) [+ bias], and, when
- * tile_stats (no, B * i2p_conv3x3_tiles(H, W), 3) is given, the (count, mean, M2) of every 128-position tile per
- * output channel (the input of i2p_rgb_bn_finalize).  Data gradient: the same call on dy with the dgrad pack
+ * tile_stats (no, i2p_conv3x3_stat_slots(B, no, H, W), 3) is given, one (count, mean, M2) of y per persistent CTA and
+ * output channel (the input of i2p_rgb_bn_finalize with ntiles = that slot count).  Data gradient: the same call on dy with the dgrad pack
  * (ki = cout, no = cin).  i2p_conv3x3_wgrad ADDS the weight gradient into dw (cout, cin, 3, 3) (f32 FMA, atomics). */
 long long i2p_conv3x3_pack_floats(int cin, int cout, int dgrad);
 int i2p_conv3x3_tiles(int H, int W);
+int i2p_conv3x3_stat_slots(int B, int no, int H, int W);
 int i2p_conv3x3_pack(int cin, int cout, int dgrad, const float *w, float *pack, void *stream);
 int i2p_conv3x3_tc(int B, int ki, int no, int H, int W, const float *x, const float *wpack, const float *bias, float *y,
                    float *tile_stats, void *stream);

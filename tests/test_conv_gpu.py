@@ -30,7 +30,7 @@ def _conv_tc(x, w, bias, dgrad=False, stats=False):
     pack = torch.empty(L.i2p_conv3x3_pack_floats(cin, cout, int(dgrad)), device=x.device)
     _cabi.call("i2p_conv3x3_pack", x.device, cin, cout, int(dgrad), w.data_ptr(), pack.data_ptr())
     y = torch.full((B, no, H, W), float("nan"), device=x.device)
-    tiles = torch.full((no, B * L.i2p_conv3x3_tiles(H, W), 3), float("nan"), device=x.device) if stats else None
+    tiles = torch.full((no, L.i2p_conv3x3_stat_slots(B, no, H, W), 3), float("nan"), device=x.device) if stats else None
     _cabi.call("i2p_conv3x3_tc", x.device, B, ki, no, H, W, x.data_ptr(), pack.data_ptr(),
                bias.data_ptr() if bias is not None else None, y.data_ptr(), tiles.data_ptr() if stats else None)
     return y, tiles

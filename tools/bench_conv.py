@@ -51,7 +51,7 @@ for cin, cout, H, W, n in (SHAPES[:3] + SHAPES[6:7] if PROFILE else SHAPES):
     dy = torch.randn(B, cout, H, W, device=dev)
     dx = torch.empty_like(x)
     dw = torch.zeros_like(w)
-    tiles = torch.empty(cout, B * L.i2p_conv3x3_tiles(H, W), 3, device=dev)
+    tiles = torch.empty(cout, L.i2p_conv3x3_stat_slots(B, cout, H, W), 3, device=dev)
     pf = torch.empty(L.i2p_conv3x3_pack_floats(cin, cout, 0), device=dev)
     pd = torch.empty(L.i2p_conv3x3_pack_floats(cin, cout, 1), device=dev)
     _cabi.call("i2p_conv3x3_pack", dev, cin, cout, 0, w.data_ptr(), pf.data_ptr())
