@@ -67,6 +67,10 @@ _SIGNATURES = {
     "i2p_rgb_bn_from_running": [_int, _vp, _vp, _flt, _vp, _vp, _vp, _vp, _vp],
     "i2p_rgb_bn_act_pool_fwd": [_int] * 5 + [_vp, _vp, _flt, _vp, _vp],
     "i2p_rgb_bn_act_pool_bwd": [_int] * 6 + [_vp, _vp, _flt] + [_vp] * 6,
+    "i2p_pose_head_fwd": [_int] * 4 + [_vp] * 16,
+    "i2p_pose_head_bwd": [_int] * 4 + [_vp] * 20,
+    "i2p_pose_loss_fwd": [_int, _int] + [_vp] * 8,
+    "i2p_pose_loss_bwd": [_int, _int] + [_vp] * 12,
     "i2p_conv3x3_pack": [_int, _int, _int, _vp, _vp, _vp],
     "i2p_conv3x3_tc": [_int] * 5 + [_vp] * 6,
     "i2p_conv3x3_wgrad": [_int] * 5 + [_vp] * 4,

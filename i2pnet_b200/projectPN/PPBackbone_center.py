@@ -30,13 +30,29 @@ from .utils import (FLAG_COPY, FLAG_SHIFT, StrideGrid, check_valid, gather_rows,
 USE_FUSED_MLP = True   # False: the layer-by-layer ATen formulation (kept for A/B parity tests)
 
 
+LIBRARY_FALLBACKS = 0   # how often a CUDA tensor went through the layer-by-layer ATen / cuBLAS formulation (see run_mlp)
+
+
 def run_mlp(convs, x, reduce_k=False):
     """Apply a chain of Conv2d blocks to channels-last x (b, n, k, c); reduce_k: max over the k axis.
-    CUDA tensors take the fused kernels (fused_mlp.py); the layer-by-layer path remains for layer
-    configurations outside the fused kernels' coverage and for the CPU host-logic tests."""
+    CUDA tensors take the fused kernels (fused_mlp.py).  The layer-by-layer formulation is the CPU host-logic path and
+    the explicit A/B switch (USE_FUSED_MLP = False).  A CUDA tensor whose layer configuration the fused kernels do not
+    cover (only: a running-statistics BatchNorm in eval mode, i.e. the small-range model at inference) is COUNTED in
+    LIBRARY_FALLBACKS and warned about once -- the large-range model never gets there (tests/test_model_gpu.py asserts
+    the counter stays 0) -- and raises under I2P_STRICT=1."""
+    global LIBRARY_FALLBACKS
     convs = list(convs)
-    if USE_FUSED_MLP and x.is_cuda and len(convs) > 0 and _fm.fusable(convs):
-        return _fm.fused_mlp(x, convs, reduce_k)
+    if USE_FUSED_MLP and x.is_cuda and len(convs) > 0:
+        if _fm.fusable(convs):
+            return _fm.fused_mlp(x, convs, reduce_k)
+        LIBRARY_FALLBACKS += 1
+        import os
+        import warnings
+        if os.environ.get("I2P_STRICT", "0") == "1":
+            from .. import _cabi
+            raise _cabi.I2PError("shared MLP configuration not covered by the sm_100a kernels (I2P_STRICT=1)")
+        warnings.warn("i2pnet_b200: a shared-MLP chain ran through the ATen / cuBLAS formulation (layer configuration "
+                      "outside the fused kernels' coverage)", RuntimeWarning, stacklevel=2)
     for conv in convs:
         x = conv._forward_layer(x)
     return torch.max(x, dim=2)[0] if reduce_k else x
@@ -468,6 +484,56 @@ class CostVolume(nn.Module):
         self.pi_encoding.set_bn()
 
 
+class _PoseHeadFn(torch.autograd.Function):
+    """PoseHead.forward as one kernel per direction (csrc/head.cu): softmax of the mask over the points, weighted pooling,
+    hidden layer, dropout, the two linear heads, quaternion normalisation.  Parameter gradients accumulate straight into
+    the step engine's flat gradient buffer when there is one."""
+
+    @staticmethod
+    def forward(ctx, pred, mask, w1, b1, wq, bq, wt, bt, drop):
+        from .. import _cabi
+        f32, dev = torch.float32, pred.device
+        pred, mask = pred.contiguous(), mask.contiguous()
+        B, N, C = pred.shape
+        Hd = w1.shape[0]
+        mask_p = torch.empty(B, N, C, dtype=f32, device=dev)
+        pooled = torch.empty(B, C, dtype=f32, device=dev)
+        hidden = torch.empty(B, Hd, dtype=f32, device=dev)
+        q_raw, q, t = (torch.empty(B, 4, dtype=f32, device=dev), torch.empty(B, 4, dtype=f32, device=dev),
+                       torch.empty(B, 3, dtype=f32, device=dev))
+        P = lambda x, n: _cabi._ptr(x, f32, n, dev)
+        _cabi.call("i2p_pose_head_fwd", dev, B, N, C, Hd, P(pred, "prediction"), P(mask, "mask"), P(w1, "hidden weight"),
+                   P(b1, "hidden bias"), P(wq, "quat weight"), P(bq, "quat bias"), P(wt, "trans weight"), P(bt, "trans bias"),
+                   P(drop, "dropout mask") if drop is not None else None, mask_p.data_ptr(), pooled.data_ptr(),
+                   hidden.data_ptr(), q_raw.data_ptr(), q.data_ptr(), t.data_ptr())
+        ctx.save_for_backward(pred, mask_p, pooled, hidden, q_raw, w1, wq, wt, *([drop] if drop is not None else []))
+        ctx.params = (w1, b1, wq, bq, wt, bt)
+        ctx.mark_non_differentiable(mask_p)
+        ctx.set_materialize_grads(False)
+        return q, t, mask_p
+
+    @staticmethod
+    def backward(ctx, dq, dt, _):
+        from .. import _cabi
+        from ..engine import grad_sink
+        saved = ctx.saved_tensors
+        pred, mask_p, pooled, hidden, q_raw, w1, wq, wt = saved[:8]
+        drop = saved[8] if len(saved) > 8 else None
+        f32, dev = torch.float32, pred.device
+        B, N, C = pred.shape
+        Hd = w1.shape[0]
+        dpred, dmask = torch.empty_like(pred), torch.empty_like(pred)
+        sinks = [grad_sink(p) for p in ctx.params]
+        grads = [None if s is not None else torch.zeros_like(p) for s, p in zip(sinks, ctx.params)]
+        tgt = [s if s is not None else g for s, g in zip(sinks, grads)]
+        _cabi.call("i2p_pose_head_bwd", dev, B, N, C, Hd, pred.data_ptr(), mask_p.data_ptr(), pooled.data_ptr(), hidden.data_ptr(),
+                   q_raw.data_ptr(), drop.data_ptr() if drop is not None else None, w1.data_ptr(), wq.data_ptr(), wt.data_ptr(),
+                   _cabi._ptr(dq.contiguous(), f32, "dq", dev) if dq is not None else None,
+                   _cabi._ptr(dt.contiguous(), f32, "dt", dev) if dt is not None else None, dpred.data_ptr(), dmask.data_ptr(),
+                   tgt[0].data_ptr(), tgt[1].data_ptr(), tgt[2].data_ptr(), tgt[3].data_ptr(), tgt[4].data_ptr(), tgt[5].data_ptr())
+        return (dpred, dmask, *grads, None)
+
+
 class PoseHead(nn.Module):
     """Mask-weighted pooling over points -> hidden -> (unit quaternion, translation)."""
 
@@ -484,6 +550,8 @@ class PoseHead(nn.Module):
 
     def forward(self, prediction, mask, xyz, feature, projection_mask):
         """prediction, mask (B,N,C) -> q (B,4), t (B,3), mask_p (B,N,C)"""
+        if prediction.is_cuda and prediction.dtype == torch.float32:
+            return self._forward_fused(prediction, mask, projection_mask)
         if not self.sigmoid:
             if projection_mask is not None:
                 projection_mask = torch.argmax(projection_mask.detach(), dim=-1, keepdim=True).float()
@@ -499,6 +567,25 @@ class PoseHead(nn.Module):
         t = self.trans_head(self.DP2(hidden)).squeeze(1)
         q = q / (torch.sqrt(torch.sum(q * q, dim=-1, keepdim=True) + 1e-10) + 1e-10)
         return q, t, mask_p
+
+
+def _pose_head_fused(self, prediction, mask, projection_mask):
+    """The configuration every shipped config uses (no sigmoid / max head / projection mask / split dropout, plain linear
+    layers); anything else has no kernel and raises -- there is no library fallback on the device."""
+    lin = [m.composed_module for m in (self.hidden_layer, self.quat_head, self.trans_head)]
+    plain = all(isinstance(m[1], nn.Identity) and isinstance(m[2], nn.Identity) and m[0].kernel_size == (1,) for m in lin)
+    if self.sigmoid or self.maxhead or projection_mask is not None or not isinstance(self.DP2, nn.Identity) or not plain:
+        from .. import _cabi
+        raise _cabi.I2PError("PoseHead: this configuration is not covered by the sm_100a pose-head kernel")
+    drop = None
+    if isinstance(self.DP1, nn.Dropout) and self.training and self.DP1.p > 0:
+        B, Hd = prediction.shape[0], lin[0][0].out_channels
+        drop = F.dropout(torch.ones(B, Hd, device=prediction.device), self.DP1.p, True)   # 0 or 1 / (1 - p), graph-safe RNG
+    w = lambda m: m[0].weight      # (out, in, 1): the Parameter itself, so that its gradient sink is found
+    return _PoseHeadFn.apply(prediction, mask, w(lin[0]), lin[0][0].bias, w(lin[1]), lin[1][0].bias, w(lin[2]), lin[2][0].bias, drop)
+
+
+PoseHead._forward_fused = _pose_head_fused
 
 
 class FlowPredictor(nn.Module):

@@ -274,6 +274,25 @@ int i2p_conv3x3_tc(int B, int ki, int no, int H, int W, const float *x, const fl
                    float *tile_stats, void *stream);
 int i2p_conv3x3_wgrad(int B, int cin, int cout, int H, int W, const float *x, const float *dy, float *dw, void *stream);
 
+/* ---- pose head and pose loss (src/projectPN/PPBackbone_center.py:503-560 PoseHead; compute_loss.py:102-133 Get_loss) ----
+ * i2p_pose_head_fwd: mask_p = softmax over the N points of mask (B, N, C) per channel; pooled = sum_n pred * mask_p;
+ * hidden = (W1 pooled + b1) * drop (drop (B, Hd): dropout multipliers or NULL); q_raw = Wq hidden + bq, t = Wt hidden + bt,
+ * q = q_raw / (|q_raw| + 1e-10).  One CTA per sample.  i2p_pose_head_bwd: gradients of all of it from dq (B, 4), dt (B, 3)
+ * (either may be NULL); parameter gradients are ADDED (atomics over the batch) into dw1 (Hd, C), db1, dwq (4, Hd), dbq,
+ * dwt (3, Hd), dbt.  i2p_pose_loss_fwd -> loss3 = (total, rotation part, translation part); l1: L1 translation term. */
+int i2p_pose_head_fwd(int B, int N, int C, int Hd, const float *pred, const float *mask, const float *w1, const float *b1,
+                      const float *wq, const float *bq, const float *wt, const float *bt, const float *drop, float *mask_p,
+                      float *pooled, float *hidden, float *q_raw, float *q, float *t, void *stream);
+int i2p_pose_head_bwd(int B, int N, int C, int Hd, const float *pred, const float *mask_p, const float *pooled,
+                      const float *hidden, const float *q_raw, const float *drop, const float *w1, const float *wq,
+                      const float *wt, const float *dq, const float *dt, float *dpred, float *dmask, float *dw1, float *db1,
+                      float *dwq, float *dbq, float *dwt, float *dbt, void *stream);
+int i2p_pose_loss_fwd(int B, int l1, const float *out3, const float *out4, const float *q_gt, const float *t_gt,
+                      const float *sx, const float *sq, float *loss3, void *stream);
+int i2p_pose_loss_bwd(int B, int l1, const float *out3, const float *out4, const float *q_gt, const float *t_gt,
+                      const float *sx, const float *sq, const float *dloss, float *dout3, float *dout4, float *dsx,
+                      float *dsq, void *stream);
+
 /* ---- optimiser step on flat buffers: replaces torch.nn.utils.clip_grad_norm_(parameters, max_norm) followed by
  * torch.optim.Adam(lr, betas, eps, weight_decay).step() (train20v2learn_wandb_proj.py:198-205, 481-483) -----------
  * param, grad, exp_avg, exp_avg_sq: n f32 each (grad 16-byte aligned).  grad holds the SUM of the ranks' gradients

@@ -12,9 +12,12 @@ pytestmark = pytest.mark.gpu
 def test_model_forward_backward_matches_reference():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False      # true f32 for parity
+    from i2pnet_b200.projectPN import PPBackbone_center as P
     g, state = load_golden_model()
     model = build_model(state, "cuda:0")
+    before = P.LIBRARY_FALLBACKS
     out3, out4, loss, inter = run_model(model, g, "cuda:0")
+    assert P.LIBRARY_FALLBACKS == before, "a shared-MLP chain of the large-range model left the sm_100a kernels"
     # Forward / loss: the north-star 1e-4.  Gradients against a CPU recording: the 15 overlapping
     # 3x3 max-pools and LeakyReLUs of the RGB stack route gradients through arg-max positions that
     # flip on 1e-6 forward differences, so CPU and GPU runs OF THE REFERENCE ITSELF differ by up to
