@@ -168,6 +168,24 @@ __device__ __forceinline__ void issue_chunk_sw(uint32_t tmem_d, uint32_t a_hi, u
     }
 }
 
+// The same with TWO MMAs per k-step instead of three.  One thread needs ~120 cycles to issue a tcgen05.mma whatever its
+// N (tools/micro/mma_rate*.cu), so the count of MMAs, not their size, is what a chunk costs.  The packed weights hold the
+// lo tile right behind the hi tile, both as 8-row SWIZZLE_128B atoms: together they ARE one K-major operand of 2 BN rows.
+// A_hi x [B_hi | B_lo] is therefore a single MMA of N = 2 BN whose columns [0, BN) receive hi*hi and [BN, 2 BN) hi*lo;
+// A_lo x B_hi (N = BN) is accumulated into the second half as well, so the large terms and the 2^-11-sized correction
+// terms also keep separate accumulators (the tensor core accumulates with truncation).  The epilogue adds the halves.
+template <int BN>
+__device__ __forceinline__ void issue_chunk_sw2(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, bool first_chunk) {
+    constexpr uint32_t id_wide = idesc_tf32(2 * BN, false, false), id_half = idesc_tf32(BN, false, false);
+#pragma unroll
+    for (int j = 0; j < BK / 8; ++j) {
+        const uint64_t ah = umma::smem_desc(a_hi + j * 32, 16, 1024, 2), al = umma::smem_desc(a_lo + j * 32, 16, 1024, 2);
+        const uint64_t bb = umma::smem_desc(b_hi + j * 32, 16, 1024, 2);
+        umma::mma_tf32(tmem_d, ah, bb, id_wide, !(first_chunk && j == 0));
+        umma::mma_tf32(tmem_d + BN, al, bb, id_half, true);
+    }
+}
+
 // TMEM allocation + mbarrier set-up shared by the three kernels
 template <int COLS>
 __device__ __forceinline__ uint32_t tc_prologue(uint64_t *bar, uint32_t *slot) {
@@ -183,7 +201,7 @@ __device__ __forceinline__ uint32_t tc_prologue(uint64_t *bar, uint32_t *slot) {
 }
 
 // accumulator (128 lanes x BN columns) -> shared tile[128][BN + 4] (+ per-column addend), conflict-free 128-bit stores
-template <int BN>
+template <int BN, bool WIDE = false>
 __device__ __forceinline__ void tmem_to_tile(uint32_t tmem_d, float *tile, const float *addend, int n0, int nvalid) {
     constexpr int LDT = BN + 4, CQ = BN / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -193,6 +211,12 @@ __device__ __forceinline__ void tmem_to_tile(uint32_t tmem_d, float *tile, const
     for (int c0 = 0; c0 < CQ; c0 += 16) {
         float v[16];
         umma::tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbase + c0), v);
+        if (WIDE) {      // [hi*hi | correction terms]: two accumulators of BN columns
+            float u[16];
+            umma::tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN + cbase + c0), u);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += u[j];
+        }
         if (addend != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -291,7 +315,8 @@ __global__ void __launch_bounds__(THREADS, BN == 128 ? 3 : 4) fwd_kernel(const F
     const int tid = threadIdx.x;
     const int nt = blockIdx.x, n0 = nt * BN, r0 = blockIdx.y * BM;
     if (SW && tid == 0) umma::mbar_init(&b_bar, 1);
-    const uint32_t tmem_d = tc_prologue<BN>(&mma_bar, &tmem_slot);
+    constexpr int TCOLS = SW == 2 ? 2 * BN : BN;      // SW == 2: [hi*hi | correction] accumulators, two MMAs per k-step
+    const uint32_t tmem_d = tc_prologue<TCOLS>(&mma_bar, &tmem_slot);
     unsigned char *smem = SW ? smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
     const uint32_t sbase = umma::smem_u32(smem);
     constexpr uint32_t idesc = idesc_tf32(BN, false, false);
@@ -359,7 +384,8 @@ __global__ void __launch_bounds__(THREADS, BN == 128 ? 3 : 4) fwd_kernel(const F
             const uint32_t sb = sbase + 2 * A_BYTES;
             if (SW) {
                 umma::mbar_wait(&b_bar, (uint32_t)c & 1u);   // the bulk copy of this chunk's weights has landed
-                issue_chunk_sw(tmem_d, sbase, sbase + A_BYTES, sb, sb + B_BYTES, idesc, c == 0);
+                if (SW == 2) issue_chunk_sw2<BN>(tmem_d, sbase, sbase + A_BYTES, sb, c == 0);
+                else issue_chunk_sw(tmem_d, sbase, sbase + A_BYTES, sb, sb + B_BYTES, idesc, c == 0);
             } else {
                 issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, 2 * A_LBO, sb, sb + B_BYTES, B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
             }
@@ -373,10 +399,10 @@ __global__ void __launch_bounds__(THREADS, BN == 128 ? 3 : 4) fwd_kernel(const F
 
     float *tile = reinterpret_cast<float *>(smem);
     constexpr int LDT = BN + 4;
-    tmem_to_tile<BN>(tmem_d, tile, a.bias, n0, a.cout);
+    tmem_to_tile<BN, SW == 2>(tmem_d, tile, a.bias, n0, a.cout);
     umma::fence_before_sync();
     __syncthreads();
-    if ((tid >> 5) == 0) umma::tmem_dealloc(tmem_d, BN);
+    if ((tid >> 5) == 0) umma::tmem_dealloc(tmem_d, TCOLS);
 
     const int vr = min(BM, a.rows - r0);
     store_tile<BN>(tile, a.y, a.cout, r0, vr, n0, a.cout);
@@ -519,7 +545,8 @@ __global__ void __launch_bounds__(THREADS, MAXK ? 2 : 3) dx_kernel(const DxArgs 
     const int nt = blockIdx.x, n0 = nt * BN, r0 = blockIdx.y * BM;
     load_dytab(tab, a.bn, a.s12, a.cout, a.rows);
     if (SW && tid == 0) umma::mbar_init(&b_bar, 1);
-    const uint32_t tmem_d = tc_prologue<BN>(&mma_bar, &tmem_slot);   // (its barrier also publishes the tables)
+    constexpr int TCOLS = SW == 2 ? 2 * BN : BN;
+    const uint32_t tmem_d = tc_prologue<TCOLS>(&mma_bar, &tmem_slot);   // (its barrier also publishes the tables)
     const uint32_t sbase = umma::smem_u32(smem);
     constexpr uint32_t idesc = idesc_tf32(BN, false, false);
     const KMajorCoords co;
@@ -581,7 +608,8 @@ __global__ void __launch_bounds__(THREADS, MAXK ? 2 : 3) dx_kernel(const DxArgs 
             const uint32_t sb = sbase + 2 * A_BYTES;
             if (SW) {
                 umma::mbar_wait(&b_bar, (uint32_t)c & 1u);
-                issue_chunk_sw(tmem_d, sbase, sbase + A_BYTES, sb, sb + B_BYTES, idesc, c == 0);
+                if (SW == 2) issue_chunk_sw2<BN>(tmem_d, sbase, sbase + A_BYTES, sb, c == 0);
+                else issue_chunk_sw(tmem_d, sbase, sbase + A_BYTES, sb, sb + B_BYTES, idesc, c == 0);
             } else {
                 issue_chunk(tmem_d, sbase, sbase + A_BYTES, A_LBO, SBO, 2 * A_LBO, sb, sb + B_BYTES, B_LBO, SBO, 2 * B_LBO, idesc, c == 0);
             }
@@ -595,10 +623,10 @@ __global__ void __launch_bounds__(THREADS, MAXK ? 2 : 3) dx_kernel(const DxArgs 
 
     float *tile = reinterpret_cast<float *>(smem);
     constexpr int LDT = BN + 4;
-    tmem_to_tile<BN>(tmem_d, tile, nullptr, n0, a.cin);
+    tmem_to_tile<BN, SW == 2>(tmem_d, tile, nullptr, n0, a.cin);
     umma::fence_before_sync();
     __syncthreads();
-    if ((tid >> 5) == 0) umma::tmem_dealloc(tmem_d, BN);
+    if ((tid >> 5) == 0) umma::tmem_dealloc(tmem_d, TCOLS);
 
     const int vr = min(BM, a.rows - r0);
     store_tile<BN>(tile, a.dx, a.cin, r0, vr, n0, a.cin);
@@ -804,7 +832,7 @@ static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 // SWIZZLE_128B + bulk-copy variant.  Measured and dropped on the way here: a second register set for the activation
 // operand (prefetch distance 2: 118.8 -> 120.9 us forward) and double-buffered cp.async weights (116.7 vs 120.8 us):
 // the kernels were bound by load/store-unit wavefronts, not by the depth of either pipeline.
-static bool swizzled() { return (i2p_get_mlp_tensor_cores() & 16) != 0; }
+static int swizzled() { const int m = i2p_get_mlp_tensor_cores(); return (m & 16) ? ((m & 64) ? 2 : 1) : 0; }   // bit 64: two MMAs per k-step (issue_chunk_sw2)
 
 }  // namespace tc
 }  // namespace i2p
@@ -855,8 +883,8 @@ int i2p_pw_linear_fwd_tc(int rows, int cin, int cout, const float *x, const floa
         tc::fwd_kernel<BN_, V_, P_><<<grid, tc::THREADS, tc::fwd_smem_bytes<BN_, P_>(), s>>>(a);                \
     } while (0)
 #define I2P_FWD_V(BN_, P_) do { if (vec == 4) I2P_FWD(BN_, 4, P_); else if (vec == 2) I2P_FWD(BN_, 2, P_); else I2P_FWD(BN_, 1, P_); } while (0)
-    if (g.bn_f == 64) { if (bdb) I2P_FWD_V(64, 1); else I2P_FWD_V(64, 0); }
-    else { if (bdb) I2P_FWD_V(128, 1); else I2P_FWD_V(128, 0); }
+    if (g.bn_f == 64) { if (bdb == 2) I2P_FWD_V(64, 2); else if (bdb) I2P_FWD_V(64, 1); else I2P_FWD_V(64, 0); }
+    else { if (bdb == 2) I2P_FWD_V(128, 2); else if (bdb) I2P_FWD_V(128, 1); else I2P_FWD_V(128, 0); }
 #undef I2P_FWD_V
 #undef I2P_FWD
     return check_launch("pw_linear_fwd_tc");
@@ -898,8 +926,8 @@ int i2p_pw_linear_bwd_dx_tc(int rows, int cin, int cout, const float *g_dense, c
         tc::dx_kernel<BN_, P_, M_><<<grid, tc::THREADS, tc::dx_smem_bytes<BN_, P_>(), s>>>(a);                    \
     } while (0)
 #define I2P_DX_M(BN_, P_) do { if (maxk) I2P_DX(BN_, P_, true); else I2P_DX(BN_, P_, false); } while (0)
-    if (g.bn_x == 64) { if (sw) I2P_DX_M(64, 1); else I2P_DX_M(64, 0); }
-    else { if (sw) I2P_DX_M(128, 1); else I2P_DX_M(128, 0); }
+    if (g.bn_x == 64) { if (sw == 2) I2P_DX_M(64, 2); else if (sw) I2P_DX_M(64, 1); else I2P_DX_M(64, 0); }
+    else { if (sw == 2) I2P_DX_M(128, 2); else if (sw) I2P_DX_M(128, 1); else I2P_DX_M(128, 0); }
 #undef I2P_DX_M
 #undef I2P_DX
     return check_launch("pw_linear_bwd_dx_tc");

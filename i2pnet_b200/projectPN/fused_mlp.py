@@ -40,7 +40,7 @@ class FusedMLPFunction(Function):
         inp, in_stats, in_slope = x, None, 1.0
         for l in range(L):
             w, b, gamma, beta = params[4 * l:4 * l + 4]
-            cout, cin = w.shape
+            cout, cin = w.shape[0], w.shape[1]       # (cout, cin, 1, 1): the nn.Conv2d parameter itself
             y = torch.empty(rows, cout, dtype=f32, device=dev)
             tiles = torch.empty(ntiles, cout, 2, dtype=f32, device=dev)
             fwd_tc = bool(tc_mask & 1) and lib.i2p_pw_tc_supported(0, rows, cin, cout)
@@ -93,6 +93,7 @@ class FusedMLPFunction(Function):
                  out.data_ptr())
         ctx.save_for_backward(x, *params, *ys, *stats, *([arg] if arg is not None else []))
         ctx.meta = (L, reduce_k, tuple(slopes))
+        ctx.weights = [params[4 * l] for l in range(L)]      # the Parameter objects (their gradient sinks, engine.grad_sink)
         ctx.packs = packs     # the weights do not change between forward and backward
         return out
 
@@ -143,22 +144,35 @@ class FusedMLPFunction(Function):
         call("i2p_bn_bwd_reduce", dev, rows, c_last, *src(L - 1, g), *bn(L - 1), s12[L - 1].data_ptr())
         grads = [None] * (4 * L)
         dx = None
+        from .. import streams as _streams
+        from ..engine import grad_sink
         for l in range(L - 1, -1, -1):
             w = params[4 * l]
-            cout, cin = w.shape
+            cout, cin = w.shape[0], w.shape[1]
             inp = ys[l - 1] if l > 0 else x
             pst = stats[l - 1] if l > 0 else None
             pscale = _p(pst[2]) if pst is not None else None
             pshift = _p(pst[3]) if pst is not None else None
             pslope = float(slopes[l - 1]) if l > 0 else 1.0
             on_tc = (tc_mask & 32) or not (l == L - 1 and reduce_k)      # bit 32: max-over-K sources on the tensor cores too
-            if on_tc and (tc_mask & 4) and lib.i2p_pw_tc_supported(2, rows, cin, cout):
-                call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
-                     pscale, pshift, pslope, dws[l].data_ptr())
+            # The weight gradient is needed by the optimiser alone, the data gradient by the rest of the backward pass:
+            # dW goes to a side stream (it reads what dX reads), and under a step engine it accumulates straight into
+            # the flat gradient buffer and stays un-joined until the whole backward has been issued (streams.defer_or_join).
+            sink = grad_sink(ctx.weights[l])
+            dw_target = sink if sink is not None else dws[l]
+            with _streams.Fork(grad_out, g if g is not None else grad_out, ys[l], stats[l], s12_all, inp,
+                               *([pst] if pst is not None else []), *([arg] if arg is not None else [])) as branch:
+                if on_tc and (tc_mask & 4) and lib.i2p_pw_tc_supported(2, rows, cin, cout):
+                    call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
+                         pscale, pshift, pslope, dw_target.data_ptr())
+                else:
+                    call("i2p_pw_linear_bwd_dw", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
+                         pscale, pshift, pslope, dw_target.data_ptr())
+            if sink is not None:
+                _streams.defer_or_join(branch)
             else:
-                call("i2p_pw_linear_bwd_dw", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
-                     pscale, pshift, pslope, dws[l].data_ptr())
-            grads[4 * l] = dws[l]
+                branch.join(dws[l])
+            grads[4 * l] = None if sink is not None else dws[l]
             grads[4 * l + 1] = dbs[l]                                       # bias under BN: exactly zero
             if l > 0 or ctx.needs_input_grad[0]:
                 dx = torch.empty(rows, cin, dtype=f32, device=dev)
@@ -196,7 +210,7 @@ def fused_mlp(x, convs, reduce_k=False):
     params, slopes, eps, trackers = [], [], [], []
     for c in convs:
         trackers.append(c.bn_linear if c.bn_linear.track_running_stats and c.bn_linear.running_mean is not None else None)
-        params += [c.conv.weight.view(c.out_channels, c.in_channels), c.conv.bias, c.bn_linear.weight, c.bn_linear.bias]
+        params += [c.conv.weight, c.conv.bias, c.bn_linear.weight, c.bn_linear.bias]
         slopes.append(1.0 if not c.activation_fn else (0.1 if c.leaky_relu else 0.0))
         eps.append(c.bn_linear.eps)
     k = int(lead[-1]) if reduce_k else 0

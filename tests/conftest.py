@@ -23,7 +23,7 @@ def oracle_backend(monkeypatch):
     yield
 
 
-@pytest.fixture(params=[0, 7, 23, 55], ids=["fma", "tcgen05", "tcgen05-sw128", "tcgen05-sw128-maxk"])
+@pytest.fixture(params=[0, 7, 23, 55, 119], ids=["fma", "tcgen05", "tcgen05-sw128", "tcgen05-sw128-maxk", "tcgen05-sw128-maxk-wide"])
 def tensor_cores(request):
     """The shared-MLP kernel families: f32 FMA (mask 0), tcgen05 tf32 with the 3-term hi/lo split for the
     forward, dX and dW GEMMs (mask 7), and the same with SWIZZLE_128B operand tiles + bulk-copied weights
