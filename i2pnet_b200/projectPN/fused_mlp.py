@@ -161,7 +161,7 @@ class FusedMLPFunction(Function):
             sink = grad_sink(ctx.weights[l])
             dw_target = sink if sink is not None else dws[l]
             with _streams.Fork(grad_out, g if g is not None else grad_out, ys[l], stats[l], s12_all, inp,
-                               *([pst] if pst is not None else []), *([arg] if arg is not None else [])) as branch:
+                               *([pst] if pst is not None else []), *([arg] if arg is not None else []), kind="wgrad") as branch:
                 if on_tc and (tc_mask & 4) and lib.i2p_pw_tc_supported(2, rows, cin, cout):
                     call("i2p_pw_linear_bwd_dw_tc", dev, rows, cin, cout, *src(l, g), *bn(l), s12[l].data_ptr(), inp.data_ptr(),
                          pscale, pshift, pslope, dw_target.data_ptr())
