@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(Q_THREADS) ball_query_kernel(int n, int m, flo
 // thousand (N <= 8192 in the operator sweep: 2 warps per SM).  Here a warp owns BQ_QPW queries and its 32 lanes test 32
 // consecutive candidates of the shared tile at once; the lanes inside the radius are compacted in index order with a
 // ballot (rank = popcount of the lower lanes), so the slots fill exactly as the reference's sequential scan fills them.
-// Selected with I2P_BALL_WARP=1 (off by default until measured on the GPU).
+// Default for N <= 32768 (measured, see i2p_ball_query); I2P_BALL_WARP=0 / 1 forces the thread / warp form.
 constexpr int BQ_QPW = 4;
 
 __global__ void __launch_bounds__(Q_THREADS) ball_query_warp_kernel(int n, int m, float radius2, int nsample,
@@ -283,9 +283,12 @@ int i2p_ball_query(int b, int n, int m, float radius, int nsample, const float *
     I2P_REQUIRE(b <= 65535, "ball_query: batch > 65535");
     if (b == 0 || m == 0 || n == 0) return I2P_OK;
     const float radius2 = radius * radius;  // ball_query_gpu.cu:24
-    static int warp_form = -1;   // I2P_BALL_WARP=1: the warp-cooperative kernel
-    if (warp_form < 0) { const char *e = getenv("I2P_BALL_WARP"); warp_form = e ? atoi(e) : 0; }
-    if (warp_form) {
+    // The warp-cooperative kernel fills the GPU when there are few queries and wins up to N = 32k in the operator sweep
+    // (profiles/r2_sweep_ops.md: 67 vs 279 us at N = 4096, 1746 vs 2235 us at 32k; 6.6 vs 5.4 ms at 65k), the
+    // thread-per-query kernel beyond.  I2P_BALL_WARP=0 / 1 forces one of them.
+    static int warp_form = -1;
+    if (warp_form < 0) { const char *e = getenv("I2P_BALL_WARP"); warp_form = e ? atoi(e) : 2; }
+    if (warp_form == 1 || (warp_form == 2 && n <= 32768)) {
         dim3 grid(ceil_div(m, (Q_THREADS / 32) * BQ_QPW), b);
         ball_query_warp_kernel<<<grid, Q_THREADS, 0, as_stream(stream)>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
         return check_launch("ball_query(warp)");

@@ -167,8 +167,11 @@ __global__ void __launch_bounds__(256) rgb_pool_fwd_kernel(PoolGeom g, const flo
     const int h0 = blockIdx.y * RGB_TH, w0 = blockIdx.x * RGB_TW;
     const float mu = __ldg(stats + c), sc = __ldg(stats + 2 * g.C + c), bt = __ldg(stats + 3 * g.C + c);
     const float *p = y + (size_t)plane * g.H * g.W;
-    for (int idx = threadIdx.x; idx < ZH * ZW; idx += 256) {
-        const int hh = idx / ZW, ww = idx - hh * ZW;
+    // loops cover the part of the tile that lies inside the plane (the pyramid's coarse levels are 10 x 32 planes in a
+    // 32 x 128 tile: iterating the whole tile cost 13x the useful work there)
+    const int zh = min(ZH, g.H - h0 + 2), zw = min(ZW, g.W - w0 + 2);
+    for (int idx = threadIdx.x; idx < zh * zw; idx += 256) {
+        const int hh = idx / zw, ww = idx - hh * zw;
         const int h = h0 - 1 + hh, w = w0 - 1 + ww;
         zt[hh][ww] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? leaky(norm(__ldg(p + (size_t)h * g.W + w), mu, sc, bt), slope)
                                                            : -INFINITY;
@@ -176,9 +179,9 @@ __global__ void __launch_bounds__(256) rgb_pool_fwd_kernel(PoolGeom g, const flo
     __syncthreads();
     const int ho0 = h0 / S, wo0 = w0 / S;
     float *o = out + (size_t)plane * g.Ho * g.Wo;
-    for (int idx = threadIdx.x; idx < OH * OW; idx += 256) {
-        const int oh = idx / OW, ow = idx - oh * OW;
-        if (ho0 + oh >= g.Ho || wo0 + ow >= g.Wo) continue;
+    const int oh_n = min(OH, g.Ho - ho0), ow_n = min(OW, g.Wo - wo0);
+    for (int idx = threadIdx.x; idx < oh_n * ow_n; idx += 256) {
+        const int oh = idx / ow_n, ow = idx - oh * ow_n;
         float best = -INFINITY;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
@@ -207,19 +210,23 @@ __global__ void __launch_bounds__(256) rgb_pool_bwd_kernel(PoolGeom g, const flo
     const float mu = __ldg(stats + c), rs = __ldg(stats + g.C + c), sc = __ldg(stats + 2 * g.C + c),
                 bt = __ldg(stats + 3 * g.C + c);
     const float *p = y + (size_t)plane * g.H * g.W;
-    for (int idx = threadIdx.x; idx < ZH * ZW; idx += 256) {
-        const int hh = idx / ZW, ww = idx - hh * ZW;
+    // (as in the forward kernel: only the part of the tile inside the plane is touched)
+    const int th_n = min(RGB_TH, g.H - h0), tw_n = min(RGB_TW, g.W - w0);
+    const int zh = min(ZH, th_n + 4), zw = min(ZW, tw_n + 4);
+    for (int idx = threadIdx.x; idx < zh * zw; idx += 256) {
+        const int hh = idx / zw, ww = idx - hh * zw;
         const int h = h0 - 2 + hh, w = w0 - 2 + ww;
         zt[hh][ww] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? norm(__ldg(p + (size_t)h * g.W + w), mu, sc, bt) : -INFINITY;
     }
-    for (int idx = threadIdx.x; idx < RGB_TH * RGB_TW; idx += 256) (&dzt[0][0])[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < th_n * tw_n; idx += 256) dzt[idx / tw_n][idx % tw_n] = 0.f;
     __syncthreads();
     // every pooling window that overlaps the tile: window (i, j) is output (ho_first + i, wo_first + j) and its
     // top-left input element sits at tile coordinates (S == 1 ? i : 2 i + 1, ...)
     const int ho_first = S == 1 ? h0 - 1 : h0 / 2, wo_first = S == 1 ? w0 - 1 : w0 / 2;
     const float *dp = dout + (size_t)plane * g.Ho * g.Wo;
-    for (int idx = threadIdx.x; idx < NWH * NWW; idx += 256) {
-        const int i = idx / NWW, j = idx - i * NWW;
+    const int nwh = min(NWH, th_n / S + 2), nww = min(NWW, tw_n / S + 2);
+    for (int idx = threadIdx.x; idx < nwh * nww; idx += 256) {
+        const int i = idx / nww, j = idx - i * nww;
         const int ho = ho_first + i, wo = wo_first + j;
         if (ho < 0 || ho >= g.Ho || wo < 0 || wo >= g.Wo) continue;
         const int th = S == 1 ? i : 2 * i + 1, tw = S == 1 ? j : 2 * j + 1;
@@ -239,10 +246,9 @@ __global__ void __launch_bounds__(256) rgb_pool_bwd_kernel(PoolGeom g, const flo
     }
     __syncthreads();
     float s1 = 0.f, s2 = 0.f;
-    for (int idx = threadIdx.x; idx < RGB_TH * RGB_TW; idx += 256) {
-        const int r = idx / RGB_TW, cc = idx - r * RGB_TW;
+    for (int idx = threadIdx.x; idx < th_n * tw_n; idx += 256) {
+        const int r = idx / tw_n, cc = idx - r * tw_n;
         const int h = h0 + r, w = w0 + cc;
-        if (h >= g.H || w >= g.W) continue;
         const float dz = dzt[r][cc] * (zt[r + 2][cc + 2] > 0.f ? 1.f : slope);
         const float yhat = (__ldg(p + (size_t)h * g.W + w) - mu) * rs;
         s1 += dz;
