@@ -63,15 +63,14 @@ __global__ void __launch_bounds__(256) cv_build_bwd_kernel(CvGeom g, const float
     const int nn = min(CVB_NT, g.N - n0), k1 = min(g.K, k0 + CVB_KT);
     const bool is_max = t >= g.C;
     const int c = is_max ? t - g.C : t;
-    float pv[CVB_NT], accp[CVB_NT], acc1[CVB_NT];
+    float pv[CVB_NT], accp[CVB_NT];
 #pragma unroll
     for (int i = 0; i < CVB_NT; ++i) {
         pv[i] = (!is_max && i < nn) ? __ldg(pi + ((size_t)b * g.N + n0 + i) * g.C + c) : 0.f;
         accp[i] = 0.f;
-        acc1[i] = 0.f;
     }
     for (int k = k0; k < k1; ++k) {
-        float aq = 0.f, a2 = 0.f;   // partial sums over the block's points for (pixel k, this channel), every-pixel form
+        float aq = 0.f;   // partial sum over the block's points for (pixel k, this channel), every-pixel form
         float v[CVB_NT];
 #pragma unroll
         for (int i = 0; i < CVB_NT; ++i)   // the block's eight rows of this pixel: independent loads, all in flight
@@ -89,25 +88,107 @@ __global__ void __launch_bounds__(256) cv_build_bwd_kernel(CvGeom g, const float
                 if (idx != nullptr) atomicAdd(dqi + ((size_t)b * g.N2 + j) * g.C + c, v[i] * pv[i]);
                 else aq = __fmaf_rn(v[i], pv[i], aq);
             }
-            if (t < 6) {   // coordinate channels: both the copy inside X and the separate 6-channel output
-                float w = __ldg(dX + r * g.Cx + t);
-                if (dxyz6 != nullptr) w += __ldg(dxyz6 + r * 6 + t);
-                if (t < 3) acc1[i] += w;
-                else if (idx != nullptr) atomicAdd(dxyz2 + ((size_t)b * g.N2 + j) * 3 + (t - 3), w);
-                else a2 += w;
-            }
         }
         if (idx == nullptr) {
             atomicAdd((is_max ? dmaxc : dqi) + ((size_t)b * g.N2 + k) * g.C + c, aq);
-            if (t >= 3 && t < 6) atomicAdd(dxyz2 + ((size_t)b * g.N2 + k) * 3 + (t - 3), a2);
         }
     }
 #pragma unroll
     for (int i = 0; i < CVB_NT; ++i) {
         if (i >= nn) break;
         if (!is_max) atomicAdd(dpi + ((size_t)b * g.N + n0 + i) * g.C + c, accp[i]);
-        if (t < 3) atomicAdd(dxyz1 + ((size_t)b * g.N + n0 + i) * 3 + t, acc1[i]);
     }
+}
+
+// Every-pixel form (idx == NULL, cost volume 1: 153 MB of dX at batch 8).  ncu of the kernel above on this shape:
+// 120 registers -> 2 blocks per SM, 11 % of the warp slots, 6.2 warps stalled on the long scoreboard per issue, 8 % of
+// the DRAM peak: latency-bound with eight loads in flight per thread.  Here a block owns KT = 4 pixels and a slice of
+// the points; a thread (= channel) walks the slice four points at a time (16 independent loads in flight, ~40
+// registers), keeps the sums over the points for its four pixels in registers (d qi / d maxc / d xyz2: ONE atomic per
+// element and block at the end) and adds each point's sum over the four pixels to d pi / d xyz1 (a coalesced red per
+// point).  Same arithmetic per element as the kernel above.
+constexpr int CVD_KT = 4;
+
+__global__ void __launch_bounds__(256) cv_build_bwd_dense_kernel(CvGeom g, int n_per_block, const float *__restrict__ dX,
+                                                                const float *__restrict__ dxyz6, const float *__restrict__ pi,
+                                                                const float *__restrict__ qi, float *dxyz1, float *dxyz2,
+                                                                float *dpi, float *dqi, float *dmaxc) {
+    const int k0 = blockIdx.x * CVD_KT, b = blockIdx.z, t = threadIdx.x;
+    const int nb = blockIdx.y * n_per_block, ne = min(g.N, nb + n_per_block);
+    const int kn = min(CVD_KT, g.K - k0);
+    const bool is_max = t >= g.C;
+    const int c = is_max ? t - g.C : t;
+    float qv[CVD_KT], aq[CVD_KT];
+#pragma unroll
+    for (int kk = 0; kk < CVD_KT; ++kk) {
+        qv[kk] = (!is_max && kk < kn) ? __ldg(qi + ((size_t)b * g.N2 + k0 + kk) * g.C + c) : 0.f;
+        aq[kk] = 0.f;
+    }
+    const float *base = dX + ((size_t)b * g.N * g.K + k0) * g.Cx + 6 + t;
+    // The K / 4 blocks of a slice all add into the same d pi rows: each starts its walk at a different point, so that
+    // they do not hit the same addresses at the same time (same-address reds serialise in L2).
+    const int nit = (ne - nb + 3) / 4, rot = nit > 0 ? (int)((blockIdx.x * 7u) % (unsigned)nit) : 0;
+    for (int it = 0; it < nit; ++it) {
+        const int n = nb + 4 * ((it + rot) % nit);
+        float v[4][CVD_KT], pv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {       // 16 independent loads
+            const bool in = n + i < ne;
+            pv[i] = (in && !is_max) ? __ldg(pi + ((size_t)b * g.N + n + i) * g.C + c) : 0.f;
+#pragma unroll
+            for (int kk = 0; kk < CVD_KT; ++kk)
+                v[i][kk] = (in && kk < kn) ? __ldg(base + ((size_t)(n + i) * g.K + kk) * g.Cx) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (n + i >= ne) break;
+            if (is_max) {
+#pragma unroll
+                for (int kk = 0; kk < CVD_KT; ++kk) aq[kk] += v[i][kk];
+            } else {
+                float accp = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < CVD_KT; ++kk) {
+                    accp = __fmaf_rn(v[i][kk], qv[kk], accp);
+                    aq[kk] = __fmaf_rn(v[i][kk], pv[i], aq[kk]);
+                }
+                atomicAdd(dpi + ((size_t)b * g.N + n + i) * g.C + c, accp);
+            }
+        }
+    }
+    for (int kk = 0; kk < kn; ++kk) atomicAdd((is_max ? dmaxc : dqi) + ((size_t)b * g.N2 + k0 + kk) * g.C + c, aq[kk]);
+}
+
+// The six coordinate channels (the copy inside X plus the separate 6-channel output), both forms: a block
+// per point, a thread per pixel.  d xyz1[n] = sum over the pixels (block reduction, plain store); d xyz2[k] = sum over the
+// points (one red per element).  In the kernels above these channels were a serial chain of dependent loads on six
+// threads of warp 0 that the whole block waited for (~7 us per iteration: the bulk of their 245 us).
+__global__ void __launch_bounds__(128) cv_coord_bwd_kernel(CvGeom g, const float *__restrict__ dX, const float *__restrict__ dxyz6,
+                                                          const int32_t *__restrict__ idx, float *dxyz1, float *dxyz2) {
+    __shared__ float red[4][3];
+    const int n = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int k = threadIdx.x; k < g.K; k += 128) {
+        const size_t r = ((size_t)b * g.N + n) * g.K + k;
+        float w[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) w[t] = __ldg(dX + r * g.Cx + t) + (dxyz6 != nullptr ? __ldg(dxyz6 + r * 6 + t) : 0.f);
+#pragma unroll
+        const int j = idx != nullptr ? __ldg(idx + r) : k;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            s[t] += w[t];
+            atomicAdd(dxyz2 + ((size_t)b * g.N2 + j) * 3 + t, w[3 + t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s[t] += __shfl_xor_sync(FULL, s[t], off);
+        if (lane == 0) red[warp][t] = s[t];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) dxyz1[((size_t)b * g.N + n) * 3 + threadIdx.x] += red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
 }
 
 __device__ __forceinline__ float masked_logit(float l, float m) { return l * m + -1e10f * (1.f - m); }
@@ -202,9 +283,26 @@ int i2p_cv_build_bwd(int B, int N, int K, int N2, int C, int has_max, const floa
     I2P_REQUIRE(cv_geom(g, B, N, K, N2, C, has_max), "cv_build_bwd: bad sizes");
     I2P_REQUIRE(idx != nullptr || K == N2, "cv_build_bwd: K must equal N2 without an index");
     I2P_REQUIRE(!has_max || dmaxc != nullptr, "cv_build_bwd: dmaxc missing");
+    if (idx == nullptr) {
+        // about two blocks per SM: K / 4 pixel groups x point slices x B
+        const int kb = ceil_div(K, CVD_KT);
+        int splits = ceil_div(2 * 148, kb * B);
+        if (splits < 1) splits = 1;
+        int npb = ceil_div(N, splits);
+        npb = ((npb + 3) / 4) * 4;
+        cv_build_bwd_dense_kernel<<<dim3(kb, ceil_div(N, npb), B), g.Cx - 6, 0, as_stream(stream)>>>(g, npb, dX, dxyz6, pi, qi, dxyz1,
+                                                                                                   dxyz2, dpi, dqi, dmaxc);
+        int rc = check_launch("cv_build_bwd(dense)");
+        if (rc != I2P_OK) return rc;
+        cv_coord_bwd_kernel<<<dim3(N, B), 128, 0, as_stream(stream)>>>(g, dX, dxyz6, nullptr, dxyz1, dxyz2);
+        return check_launch("cv_build_bwd(coordinates)");
+    }
     cv_build_bwd_kernel<<<dim3(ceil_div(N, CVB_NT), ceil_div(K, CVB_KT), B), g.Cx - 6, 0, as_stream(stream)>>>(g, dX, dxyz6, pi, qi, idx, dxyz1, dxyz2,
                                                                                           dpi, dqi, dmaxc);
-    return check_launch("cv_build_bwd");
+    int rc = check_launch("cv_build_bwd");
+    if (rc != I2P_OK) return rc;
+    cv_coord_bwd_kernel<<<dim3(N, B), 128, 0, as_stream(stream)>>>(g, dX, dxyz6, idx, dxyz1, dxyz2);
+    return check_launch("cv_build_bwd(coordinates)");
 }
 
 int i2p_softmax_wsum(long long groups, int K, int C, const float *logit, const float *value, const float *mask, float *out,

@@ -80,14 +80,21 @@ __global__ void __launch_bounds__(HEAD_THREADS) pose_head_fwd_kernel(const HeadA
         a.pooled[(size_t)b * C + tid] = ss;
     }
     __syncthreads();
-    // hidden layer (one output per thread), dropout
-    for (int h = tid; h < Hd; h += HEAD_THREADS) {
-        float v = a.b1[h];
-        const float *w = a.w1 + (size_t)h * C;
-        for (int k = 0; k < C; ++k) v = __fmaf_rn(w[k], pooled[k], v);
-        if (a.drop != nullptr) v *= a.drop[(size_t)b * Hd + h];
-        hidden[h] = v;
-        a.hidden[(size_t)b * Hd + h] = v;
+    // hidden layer: a warp per output (lanes run along the weight row: coalesced), dropout
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int h = warp; h < Hd; h += HEAD_THREADS / 32) {
+            const float *w = a.w1 + (size_t)h * C;
+            float v = 0.f;
+            for (int k = lane; k < C; k += 32) v = __fmaf_rn(__ldg(w + k), pooled[k], v);
+            v = warp_sum(v);
+            if (lane == 0) {
+                v += a.b1[h];
+                if (a.drop != nullptr) v *= a.drop[(size_t)b * Hd + h];
+                hidden[h] = v;
+                a.hidden[(size_t)b * Hd + h] = v;
+            }
+        }
     }
     __syncthreads();
     // the seven head outputs: one warp each
@@ -120,10 +127,15 @@ struct HeadBwdArgs {
     float *dw1, *db1, *dwq, *dbq, *dwt, *dbt;   // accumulated with atomics (sum over the batch)
 };
 
+// grid (B, HEAD_SPLIT): the blocks of a sample all rebuild the (tiny) head gradients, then share the expensive parts --
+// the Hd x C outer product for dW1 and the N x C element-wise tail -- by slices.
+constexpr int HEAD_SPLIT = 4;
+
 __global__ void __launch_bounds__(HEAD_THREADS) pose_head_bwd_kernel(const HeadBwdArgs a) {
-    __shared__ float d7[8], dhid[HEAD_MAXH], dpool[HEAD_MAXC], pooled[HEAD_MAXC];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ float d7[8], dhid[HEAD_MAXH], dpool[HEAD_MAXC], pooled[HEAD_MAXC], part[HEAD_THREADS / 32][HEAD_MAXC];
+    const int b = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x;
     const int C = a.C, N = a.N, Hd = a.Hd;
+    const bool lead = sp == 0;      // the block that adds the small parameter gradients
     if (tid == 0) {
         // q = r / (s + e), s = sqrt(|r|^2 + 1e-10):  dr = dq / (s + e) - r (dq . r) / ((s + e)^2 s)
         float r[4], dq[4];
@@ -132,8 +144,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) pose_head_bwd_kernel(const HeadB
         const float dot = dq[0] * r[0] + dq[1] * r[1] + dq[2] * r[2] + dq[3] * r[3];
         for (int i = 0; i < 4; ++i) d7[i] = dq[i] / den - r[i] * dot / (den * den * s);
         for (int i = 0; i < 3; ++i) d7[4 + i] = a.dt != nullptr ? a.dt[b * 3 + i] : 0.f;
-        for (int i = 0; i < 4; ++i) atomicAdd(a.dbq + i, d7[i]);
-        for (int i = 0; i < 3; ++i) atomicAdd(a.dbt + i, d7[4 + i]);
+        if (lead) {
+            for (int i = 0; i < 4; ++i) atomicAdd(a.dbq + i, d7[i]);
+            for (int i = 0; i < 3; ++i) atomicAdd(a.dbt + i, d7[4 + i]);
+        }
     }
     for (int k = tid; k < C; k += HEAD_THREADS) pooled[k] = a.pooled[(size_t)b * C + k];
     __syncthreads();
@@ -144,33 +158,43 @@ __global__ void __launch_bounds__(HEAD_THREADS) pose_head_bwd_kernel(const HeadB
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             v = __fmaf_rn(a.wq[(size_t)i * Hd + h], d7[i], v);
-            atomicAdd(a.dwq + (size_t)i * Hd + h, d7[i] * hv);
+            if (lead) atomicAdd(a.dwq + (size_t)i * Hd + h, d7[i] * hv);
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             v = __fmaf_rn(a.wt[(size_t)i * Hd + h], d7[4 + i], v);
-            atomicAdd(a.dwt + (size_t)i * Hd + h, d7[4 + i] * hv);
+            if (lead) atomicAdd(a.dwt + (size_t)i * Hd + h, d7[4 + i] * hv);
         }
         if (a.drop != nullptr) v *= a.drop[(size_t)b * Hd + h];
         dhid[h] = v;
-        atomicAdd(a.db1 + h, v);
+        if (lead) atomicAdd(a.db1 + h, v);
     }
     __syncthreads();
-    // dW1 = dhid (x) pooled ; dpooled = W1^T dhid
-    for (int e = tid; e < Hd * C; e += HEAD_THREADS) {
+    // dW1 = dhid (x) pooled: this block's slice of the hidden units
+    const int h_per = (Hd + HEAD_SPLIT - 1) / HEAD_SPLIT, h0 = sp * h_per, h1 = min(Hd, h0 + h_per);
+    for (int e = h0 * C + tid; e < h1 * C; e += HEAD_THREADS) {
         const int h = e / C, k = e - h * C;
         atomicAdd(a.dw1 + e, dhid[h] * pooled[k]);
     }
-    for (int k = tid; k < C; k += HEAD_THREADS) {
+    // dpooled = W1^T dhid: threads = (channel, slice of the hidden units), partial sums meet in shared memory
+    {
+        const int G = HEAD_THREADS / C, k = tid % C, gq = tid / C;
         float v = 0.f;
-        for (int h = 0; h < Hd; ++h) v = __fmaf_rn(a.w1[(size_t)h * C + k], dhid[h], v);
-        dpool[k] = v;
+        if (gq < G) for (int h = gq; h < Hd; h += G) v = __fmaf_rn(__ldg(a.w1 + (size_t)h * C + k), dhid[h], v);
+        if (gq < G) part[gq][k] = v;
+        __syncthreads();
+        if (tid < C) {
+            float t = 0.f;
+            for (int i = 0; i < G; ++i) t += part[i][tid];
+            dpool[tid] = t;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // pooled = sum_n pred p:  dpred = dpooled p ;  dmask = p dpooled (pred - pooled)   (softmax over the points)
     const float *pr = a.pred + (size_t)b * N * C, *mp = a.mask_p + (size_t)b * N * C;
     float *dp = a.dpred + (size_t)b * N * C, *dm = a.dmask + (size_t)b * N * C;
-    for (int e = tid; e < N * C; e += HEAD_THREADS) {
+    const int e_per = (N * C + HEAD_SPLIT - 1) / HEAD_SPLIT, e0 = sp * e_per, e1 = min(N * C, e0 + e_per);
+    for (int e = e0 + tid; e < e1; e += HEAD_THREADS) {
         const int k = e % C;
         const float p = mp[e], g = dpool[k];
         dp[e] = g * p;
@@ -277,10 +301,10 @@ int i2p_pose_head_bwd(int B, int N, int C, int Hd, const float *pred, const floa
                       const float *wt, const float *dq, const float *dt, float *dpred, float *dmask, float *dw1, float *db1,
                       float *dwq, float *dbq, float *dwt, float *dbt, void *stream) {
     using namespace i2p;
-    I2P_REQUIRE(B >= 1 && N >= 1 && C >= 1 && C <= HEAD_MAXC && Hd >= 1 && Hd <= HEAD_MAXH, "pose_head_bwd: bad sizes");
+    I2P_REQUIRE(B >= 1 && N >= 1 && C >= 1 && C <= HEAD_MAXC && HEAD_THREADS % C == 0 && Hd >= 1 && Hd <= HEAD_MAXH, "pose_head_bwd: bad sizes");
     HeadBwdArgs a{B, N, C, Hd, pred, mask_p, pooled, hidden, q_raw, drop, w1, wq, wt, dq, dt, dpred, dmask,
                   dw1, db1, dwq, dbq, dwt, dbt};
-    pose_head_bwd_kernel<<<B, HEAD_THREADS, 0, as_stream(stream)>>>(a);
+    pose_head_bwd_kernel<<<dim3(B, HEAD_SPLIT), HEAD_THREADS, 0, as_stream(stream)>>>(a);
     return check_launch("pose_head_bwd");
 }
 
