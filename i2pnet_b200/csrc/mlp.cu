@@ -413,10 +413,12 @@ __device__ __forceinline__ void chan_merge(float &n, float &mu, float &m2, float
 // Merge of the per-tile (mean, M2) pairs of one channel: two passes over the tile statistics (they sit in L2) --
 // the row-weighted mean first, then M2 = sum_t M2_t + n_t (mean_t - mean)^2 -- with f64 accumulators.  No serial chain
 // of Chan merges (a division each): 45 of these kernels sit between the layers of the step.
-__global__ void __launch_bounds__(128) bn_finalize_kernel(int rows, int cout, int ntiles, const float *tile_stats,
-                                                          const float *gamma, const float *beta, float eps,
-                                                          float *mean, float *rstd, float *scale, float *shift) {
-    __shared__ double part[4];
+constexpr int FIN_THREADS = 512;
+
+__global__ void __launch_bounds__(FIN_THREADS) bn_finalize_kernel(int rows, int cout, int ntiles, const float *tile_stats,
+                                                                  const float *gamma, const float *beta, float eps,
+                                                                  float *mean, float *rstd, float *scale, float *shift) {
+    __shared__ double part[FIN_THREADS / 32];
     __shared__ double bcast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x;
@@ -426,20 +428,43 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(int rows, int cout, in
         for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(FULL, v, off);
         if (lane == 0) part[warp] = v;
         __syncthreads();
-        if (threadIdx.x == 0) bcast = part[0] + part[1] + part[2] + part[3];
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < FIN_THREADS / 32; ++w) t += part[w];
+            bcast = t;
+        }
         __syncthreads();
         return bcast;
     };
+    // (four independent loads per thread in flight: up to 7200 tiles per channel at the first set-abstraction level)
     double s = 0.0;
-    for (int t = threadIdx.x; t < ntiles; t += 128)
-        s += (double)((float)min(MLP_BM, rows - t * MLP_BM) * __ldg(ts + (size_t)t * cout + c).x);
+    for (int t0 = threadIdx.x; t0 < ntiles; t0 += 4 * FIN_THREADS) {
+        float m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * FIN_THREADS;
+            m[u] = t < ntiles ? (float)min(MLP_BM, rows - t * MLP_BM) * __ldg(ts + (size_t)t * cout + c).x : 0.f;
+        }
+        s += ((double)m[0] + (double)m[1]) + ((double)m[2] + (double)m[3]);
+    }
     const double mu_d = block_sum(s) / (double)rows;
     const float mu = (float)mu_d;
     double q = 0.0;
-    for (int t = threadIdx.x; t < ntiles; t += 128) {
-        const float2 v = __ldg(ts + (size_t)t * cout + c);
-        const float d = v.x - mu;
-        q += (double)__fmaf_rn((float)min(MLP_BM, rows - t * MLP_BM) * d, d, v.y);
+    for (int t0 = threadIdx.x; t0 < ntiles; t0 += 4 * FIN_THREADS) {
+        float m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * FIN_THREADS;
+            if (t < ntiles) {
+                const float2 v = __ldg(ts + (size_t)t * cout + c);
+                const float d = v.x - mu;
+                m[u] = __fmaf_rn((float)min(MLP_BM, rows - t * MLP_BM) * d, d, v.y);
+            } else {
+                m[u] = 0.f;
+            }
+        }
+        q += ((double)m[0] + (double)m[1]) + ((double)m[2] + (double)m[3]);
     }
     const double m2 = block_sum(q);
     if (threadIdx.x == 0) {
@@ -513,36 +538,72 @@ struct BnRef {  // a layer's raw output and its batch-norm constants
     float slope;
 };
 
-// s12[0][c] = sum_r dz, s12[1][c] = sum_r dz * yhat   (dz = g * act'(z)); f64 accumulators, pre-zeroed
+// s12[0][c] = sum_r dz, s12[1][c] = sum_r dz * yhat   (dz = g * act'(z)); f64 accumulators, pre-zeroed.
+// Dense source: a thread owns FOUR consecutive channels (128-bit loads of g and y) and every (256 / (cw / 4))-th row of
+// the block's slice, four rows per iteration (eight independent 128-bit loads in flight); the first version read one
+// float per thread and iteration with two loads in flight and was latency-bound at a fifth of the HBM rate.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(long long rows, int c, GradSrc gs, BnRef bn,
                                                             int rows_per_block, double *s12) {
-    __shared__ float r1[256], r2[256];
+    __shared__ float r1[256 * 4], r2[256 * 4];
     const int cw = c < 64 ? c : 64;  // columns per block (c is a multiple of 16)
+    const long long rb = (long long)blockIdx.x * rows_per_block;
+    const long long re = min(rows, rb + rows_per_block);
+    if (gs.dense != nullptr) {
+        const int cq = cw / 4, lanes = 256 / cq;               // threads per row, rows in flight per pass
+        const int q = threadIdx.x % cq, rl = threadIdx.x / cq;
+        const int ch = blockIdx.y * cw + q * 4;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (rl < lanes) {
+            const float4 mu = *reinterpret_cast<const float4 *>(bn.mean + ch), rs = *reinterpret_cast<const float4 *>(bn.rstd + ch);
+            const float4 sc = *reinterpret_cast<const float4 *>(bn.scale + ch), sh = *reinterpret_cast<const float4 *>(bn.shift + ch);
+            const float4 *yp = reinterpret_cast<const float4 *>(bn.y + ch), *gp = reinterpret_cast<const float4 *>(gs.dense + ch);
+            const size_t ld4 = (size_t)c / 4;
+            for (long long r0 = rb + rl; r0 < re; r0 += 4LL * lanes) {
+                float4 yv[4], gv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long r = r0 + (long long)u * lanes;
+                    const bool in = r < re;
+                    yv[u] = in ? __ldg(yp + (size_t)r * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    gv[u] = in ? __ldg(gp + (size_t)r * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float dz;
+                    dz = gv[u].x * act_grad(__fmaf_rn(yv[u].x, sc.x, sh.x), bn.slope); s1[0] += dz; s2[0] += dz * ((yv[u].x - mu.x) * rs.x);
+                    dz = gv[u].y * act_grad(__fmaf_rn(yv[u].y, sc.y, sh.y), bn.slope); s1[1] += dz; s2[1] += dz * ((yv[u].y - mu.y) * rs.y);
+                    dz = gv[u].z * act_grad(__fmaf_rn(yv[u].z, sc.z, sh.z), bn.slope); s1[2] += dz; s2[2] += dz * ((yv[u].z - mu.z) * rs.z);
+                    dz = gv[u].w * act_grad(__fmaf_rn(yv[u].w, sc.w, sh.w), bn.slope); s1[3] += dz; s2[3] += dz * ((yv[u].w - mu.w) * rs.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { r1[threadIdx.x * 4 + j] = s1[j]; r2[threadIdx.x * 4 + j] = s2[j]; }
+        __syncthreads();
+        if (threadIdx.x < cw && blockIdx.y * cw + threadIdx.x < c) {
+            const int qq = threadIdx.x / 4, j = threadIdx.x % 4;
+            float t1 = 0.f, t2 = 0.f;
+            for (int l = 0; l < lanes; ++l) { t1 += r1[(l * cq + qq) * 4 + j]; t2 += r2[(l * cq + qq) * 4 + j]; }
+            atomicAdd(s12 + blockIdx.y * cw + threadIdx.x, (double)t1);
+            atomicAdd(s12 + c + blockIdx.y * cw + threadIdx.x, (double)t2);
+        }
+        return;
+    }
     const int lanes = 256 / cw;
     const int col = threadIdx.x % cw, rl = threadIdx.x / cw;
     const int ch = blockIdx.y * cw + col;
-    const long long rb = (long long)blockIdx.x * rows_per_block;
-    const long long re = min(rows, rb + rows_per_block);
     float s1 = 0.f, s2 = 0.f;
     if (ch < c && rl < lanes) {
         const float mu = bn.mean[ch], rs = bn.rstd[ch], sc = bn.scale[ch], sh = bn.shift[ch];
-        if (gs.dense != nullptr) {
-            for (long long r = rb + rl; r < re; r += lanes) {
-                const float yv = __ldg(bn.y + (size_t)r * c + ch);
-                const float dz = __ldg(gs.dense + (size_t)r * c + ch) * act_grad(__fmaf_rn(yv, sc, sh), bn.slope);
-                s1 += dz;
-                s2 += dz * ((yv - mu) * rs);
-            }
-        } else {  // only the arg-max element of each group carries gradient
-            const long long gb = rb / gs.k, ge = (re + gs.k - 1) / gs.k;
-            for (long long g = gb + rl; g < ge; g += lanes) {
-                const long long r = g * gs.k + __ldg(gs.arg + (size_t)g * c + ch);
-                if (r < rb || r >= re) continue;
-                const float yv = __ldg(bn.y + (size_t)r * c + ch);
-                const float dz = __ldg(gs.dout + (size_t)g * c + ch) * act_grad(__fmaf_rn(yv, sc, sh), bn.slope);
-                s1 += dz;
-                s2 += dz * ((yv - mu) * rs);
-            }
+        // only the arg-max element of each group carries gradient
+        const long long gb = rb / gs.k, ge = (re + gs.k - 1) / gs.k;
+        for (long long g = gb + rl; g < ge; g += lanes) {
+            const long long r = g * gs.k + __ldg(gs.arg + (size_t)g * c + ch);
+            if (r < rb || r >= re) continue;
+            const float yv = __ldg(bn.y + (size_t)r * c + ch);
+            const float dz = __ldg(gs.dout + (size_t)g * c + ch) * act_grad(__fmaf_rn(yv, sc, sh), bn.slope);
+            s1 += dz;
+            s2 += dz * ((yv - mu) * rs);
         }
     }
     r1[threadIdx.x] = s1;
@@ -989,7 +1050,7 @@ int i2p_bn_finalize(int rows, int cout, const float *tile_stats, const float *ga
                     float *mean, float *rstd, float *scale, float *shift, void *stream) {
     using namespace i2p;
     I2P_REQUIRE(rows >= 1 && cout >= 1, "bn_finalize: bad sizes");
-    bn_finalize_kernel<<<cout, 128, 0, as_stream(stream)>>>(rows, cout, ceil_div(rows, MLP_BM), tile_stats,
+    bn_finalize_kernel<<<cout, FIN_THREADS, 0, as_stream(stream)>>>(rows, cout, ceil_div(rows, MLP_BM), tile_stats,
                                                                         gamma, beta, eps, mean, rstd, scale, shift);
     return check_launch("bn_finalize");
 }
