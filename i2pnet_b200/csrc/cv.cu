@@ -220,12 +220,14 @@ __global__ void __launch_bounds__(256) softmax_wsum_kernel(long long total, int 
         const float *lp = logit + (size_t)grp * K * C + c, *vp = value + (size_t)grp * K * C + c;
         const float *mp = mask != nullptr ? mask + (size_t)grp * K : nullptr;
         float mx = -INFINITY;
+#pragma unroll 8
         for (int k = 0; k < K; ++k) {
             float l = __ldg(lp + (size_t)k * C);
             if (mp != nullptr) l = masked_logit(l, __ldg(mp + k));
             mx = fmaxf(mx, l);
         }
         float s = 0.f, acc = 0.f;
+#pragma unroll 8
         for (int k = 0; k < K; ++k) {
             float l = __ldg(lp + (size_t)k * C);
             if (mp != nullptr) l = masked_logit(l, __ldg(mp + k));
@@ -247,18 +249,21 @@ __global__ void __launch_bounds__(256) softmax_wsum_bwd_kernel(long long total, 
         const size_t base = (size_t)grp * K * C + c;
         const float *mp = mask != nullptr ? mask + (size_t)grp * K : nullptr;
         float mx = -INFINITY;
+#pragma unroll 8
         for (int k = 0; k < K; ++k) {
             float l = __ldg(logit + base + (size_t)k * C);
             if (mp != nullptr) l = masked_logit(l, __ldg(mp + k));
             mx = fmaxf(mx, l);
         }
         float s = 0.f;
+#pragma unroll 8
         for (int k = 0; k < K; ++k) {
             float l = __ldg(logit + base + (size_t)k * C);
             if (mp != nullptr) l = masked_logit(l, __ldg(mp + k));
             s += expf(l - mx);
         }
         const float o = __ldg(out + e), gv = __ldg(gout + e), inv = 1.f / s;
+#pragma unroll 4
         for (int k = 0; k < K; ++k) {
             float l = __ldg(logit + base + (size_t)k * C);
             const float m = mp != nullptr ? __ldg(mp + k) : 1.f;

@@ -43,7 +43,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) pose_head_fwd_kernel(const HeadA
     float *mp = a.mask_p + (size_t)b * N * C;
     // softmax over the points, per channel: max, sum of exponentials, weighted sum
     float m = -INFINITY;
-    if (g < G) for (int n = g; n < N; n += G) m = fmaxf(m, mk[(size_t)n * C + c]);
+    if (g < G) {
+#pragma unroll 8
+        for (int n = g; n < N; n += G) m = fmaxf(m, __ldg(mk + (size_t)n * C + c));
+    }
     if (g < G) part[g][c] = m;
     __syncthreads();
     if (tid < C) {
@@ -53,7 +56,11 @@ __global__ void __launch_bounds__(HEAD_THREADS) pose_head_fwd_kernel(const HeadA
     }
     __syncthreads();
     float s = 0.f;
-    if (g < G) for (int n = g; n < N; n += G) s += __expf(mk[(size_t)n * C + c] - cmax[c]);
+    if (g < G) {
+        const float mx = cmax[c];
+#pragma unroll 8
+        for (int n = g; n < N; n += G) s += __expf(__ldg(mk + (size_t)n * C + c) - mx);
+    }
     if (g < G) part[g][c] = s;
     __syncthreads();
     if (tid < C) {
@@ -65,10 +72,11 @@ __global__ void __launch_bounds__(HEAD_THREADS) pose_head_fwd_kernel(const HeadA
     float acc = 0.f;
     if (g < G) {
         const float inv = 1.f / csum[c], mx = cmax[c];
+#pragma unroll 8
         for (int n = g; n < N; n += G) {
-            const float p = __expf(mk[(size_t)n * C + c] - mx) * inv;
+            const float p = __expf(__ldg(mk + (size_t)n * C + c) - mx) * inv;
             mp[(size_t)n * C + c] = p;
-            acc = __fmaf_rn(pr[(size_t)n * C + c], p, acc);
+            acc = __fmaf_rn(__ldg(pr + (size_t)n * C + c), p, acc);
         }
         part[g][c] = acc;
     }
