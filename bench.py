@@ -270,6 +270,21 @@ def time_hot_kernels(device, peak):
         ("tc::fwd_kernel<128,2> @ " + shape, fwd, 4 * rows * (cin + cout)),
         ("select_k_kernel<5,flat> @ SA1 (64x1800, 3600 centres, 9x15, K=32), batch 8", sel, BATCH * (12 * 64 * 1800 + 8 * n * K)),
     ]
+    # the image pyramid's convolution at its most frequent large shape (16 -> 16 channels at 80 x 256, three layers)
+    cb, cc, ch_, cw_ = BATCH, 16, 80, 256
+    cx = torch.randn(cb, cc, ch_, cw_, device=device, generator=g)
+    cwt = torch.randn(cc, cc, 3, 3, device=device, generator=g) * 0.1
+    cy, cdy, cdw = torch.empty_like(cx), torch.randn(cb, cc, ch_, cw_, device=device, generator=g), torch.zeros_like(cwt)
+    cbias = torch.zeros(cc, device=device)
+    cst = torch.empty(cc, L.i2p_conv3x3_stat_slots(cb, cc, ch_, cw_), 3, device=device)
+    cpk = torch.empty(L.i2p_conv3x3_pack_floats(cc, cc, 0), device=device)
+    call("i2p_conv3x3_pack", device, cc, cc, 0, cwt.data_ptr(), cpk.data_ptr())
+    conv_f = lambda: call("i2p_conv3x3_tc", device, cb, cc, cc, ch_, cw_, cx.data_ptr(), cpk.data_ptr(), cbias.data_ptr(), cy.data_ptr(),
+                          cst.data_ptr())
+    conv_w = lambda: call("i2p_conv3x3_wgrad", device, cb, cc, cc, ch_, cw_, cx.data_ptr(), cdy.data_ptr(), cdw.data_ptr())
+    conv_bytes = 4 * cb * ch_ * cw_ * (cc + cc)
+    specs += [("conv::conv3x3_tc_kernel<16,16> @ RGB pyramid 16 -> 16 at 80x256 (tcgen05 3xTF32 implicit GEMM + BN statistics), batch 8", conv_f, conv_bytes),
+              ("conv::wgrad_kernel<16,32> @ RGB pyramid 16 -> 16 at 80x256 (f32 FMA), batch 8", conv_w, conv_bytes)]
     out = []
     for name, fn, alg in specs:
         ms = _event_time(fn, flush)
@@ -303,8 +318,7 @@ def run_ours(args):
     conf = CONFIGS[args.config]
     batch = _per_gpu_batch(conf, world, args.strong)
     eng = TrainStep(batch, conf["points"], conf["image"], cfg=_cfg_of(conf), device=device, seed=0,
-                    use_graph=not args.no_graph, channels_last_rgb=args.channels_last,
-                    cudnn_benchmark=args.cudnn_benchmark, fused_optimizer=not args.stock_optimizer)
+                    use_graph=not args.no_graph, fused_optimizer=not args.stock_optimizer)
     nb = 4  # distinct batches, cycled
     host = [_pairs(conf, batch, 100 * rank + i) for i in range(nb)]
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
@@ -375,9 +389,9 @@ def run_ours(args):
             legacy = legacy_b200(conf, batch)
         config = _config_dict(conf, args.config, batch, world, args.strong)
         engine = dict({"cuda_graph": not args.no_graph, "optimizer": "torch.optim.Adam" if args.stock_optimizer else "fused clip+Adam (2 launches)",
-                       "side_streams": os.environ.get("I2P_STREAMS", "1") != "0", "rgb_channels_last": args.channels_last,
-                       "cudnn_benchmark": args.cudnn_benchmark, "tf32": False,
+                       "side_streams": os.environ.get("I2P_STREAMS", "1") != "0", "tf32": False,
                        "shared_mlp": "tcgen05 3xTF32 split (f32-accurate), mask %d" % _cabi.lib().i2p_get_mlp_tensor_cores(),
+                       "rgb_convolutions": "own tcgen05 3xTF32 implicit GEMM (fwd, dgrad) + f32 FMA wgrad; no cuDNN",
                        "final_loss": loss})
         print(json.dumps({
             "metric": "pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -418,8 +432,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-legacy", action="store_true", help="skip the legacy-kernels-on-B200 leg (oracle/ref_live.py)")
     ap.add_argument("--stock-optimizer", action="store_true", help="torch.optim.Adam + clip instead of the fused flat step")
-    ap.add_argument("--channels-last", action="store_true", help="NHWC memory format for the RGB conv stack")
-    ap.add_argument("--cudnn-benchmark", action="store_true", help="cuDNN algorithm search for the RGB convolutions")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -215,20 +215,13 @@ class FlatAdam:
 
 class TrainStep:
     def __init__(self, batch, n_points=20480, image_hw=(160, 512), cfg=I2PNetConfig, device="cuda:0", seed=0,
-                 use_graph=True, lr=1e-3, weight_decay=1e-4, clip=10.0, group=None, channels_last_rgb=False,
-                 cudnn_benchmark=False, fused_optimizer=True, lr_gamma=0.99):
+                 use_graph=True, lr=1e-3, weight_decay=1e-4, clip=10.0, group=None, fused_optimizer=True, lr_gamma=0.99):
         self.device = torch.device(device)
         self.cfg, self.batch, self.clip, self.group, self.use_graph = cfg, batch, clip, group, use_graph
-        if cudnn_benchmark:   # let cuDNN time its f32 algorithms during the eager warm-up (only if a library conv is on the path)
-            torch.backends.cudnn.benchmark = True
         torch.manual_seed(seed)
         self.model = RegNet_v2(cfg=cfg).to(self.device)
         self.model.train()
-        self.channels_last_rgb = channels_last_rgb
-        if channels_last_rgb:  # NHWC image branch: ATen's channels-last batch-norm / pooling kernels
-            for name in ("RGB_net1", "RGB_net2", "RGB_net3"):
-                getattr(self.model, name).to(memory_format=torch.channels_last)
-        self.fused_optimizer = fused_optimizer and not channels_last_rgb
+        self.fused_optimizer = fused_optimizer
         if self.fused_optimizer:
             self.bucket = FlatGradBucket(self.model.parameters(), align=64)
             self.opt = FlatAdam(self.bucket, lr=lr, weight_decay=weight_decay, max_norm=clip)
@@ -242,8 +235,6 @@ class TrainStep:
         shapes = dict(rgb=(batch, 3, h, w), lidar=(batch, n_points, 3), raw_point_xyz=(batch, n_points, 3),
                       lidar_feats=(batch, n_points, 1), intrinsic=(batch, 3, 3), q_gt=(batch, 4), t_gt=(batch, 3))
         self.inputs = {k: torch.zeros(s, device=self.device) for k, s in shapes.items()}
-        if channels_last_rgb:
-            self.inputs["rgb"] = self.inputs["rgb"].contiguous(memory_format=torch.channels_last)
         self.loss = torch.zeros(1, device=self.device)
         # the refined and the coarse pose of the step: the trainer reads out_3 back every iteration for its running
         # RRE / RTE (cal_rete_once, train20v2learn_wandb_proj.py:485)

@@ -142,7 +142,8 @@ class RegNet_v2(nn.Module):
         RF3 = rgb_branch.join(RF3)
         # pixel centres of RF3 on the normalised camera plane: K3^-1 [u, v, 1]
         K3_inv = inverse3x3(change_intrinsic(intrinsic, RF3, rgb_img))
-        RF3_index = torch.bmm(K3_inv, set_id_grid(RF3.permute(0, 2, 3, 1)).permute(0, 2, 1)).permute(0, 2, 1)
+        # (B,hw,3) = grid K3_inv^T, spelled element-wise: a 3x3 batched product is not worth a library GEMM launch
+        RF3_index = (set_id_grid(RF3.permute(0, 2, 3, 1)).unsqueeze(2) * K3_inv.unsqueeze(1)).sum(-1)
 
         H3, W3 = self.lidar_Hs[2], self.lidar_Ws[2]
         H4, W4 = self.lidar_Hs[-1], self.lidar_Ws[-1]
