@@ -91,6 +91,7 @@ def main():
     ap.add_argument("--with-reference", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.md"))
     ap.add_argument("--sizes", default="4096,8192,16384,32768,65536,131072")
+    ap.add_argument("--ops", default="", help="comma-separated subset of the operators (default: all)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     _cabi.lib()
@@ -118,6 +119,8 @@ def main():
             gen = torch.Generator(device=dev).manual_seed(n)
             refops = {name: fn for name, fn, _, _ in ops_for(ref, dev, n, m, gen)}
         for name, fn, nbytes, flops in ours:
+            if args.ops and name not in args.ops.split(","):
+                continue
             reps = 3 if name == "fps" and n >= 32768 else 10
             ms = event_ms(fn, flush, reps)
             rms = event_ms(refops[name], flush, 2 if name == "fps" and n >= 32768 else 5) if name in refops else None

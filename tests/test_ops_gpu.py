@@ -60,6 +60,103 @@ def test_sweep_size_kernel_matches_reference_kernel(name, dev, reference_ext):
     ref_cases.compare(case, ref_cases.run_product(case, dev), want, "sm_100a kernel vs reference CUDA kernel (sweep size)")
 
 
+_FORCED_FORM = """
+import sys, torch
+from tests import ref_cases
+cases = ref_cases.all_cases()
+dev = torch.device("cuda:0")
+n = 0
+for name in sorted(cases):
+    if cases[name]["op"] in ("ball_query", "three_nn"):
+        ref_cases.compare(cases[name], ref_cases.run_product(cases[name], dev), ref_cases.run_oracle(cases[name]), name)
+        n += 1
+assert n >= 8, n
+print("ok", n)
+"""
+
+
+@pytest.mark.parametrize("env", [{"I2P_CELL_LIST": "1"}, {"I2P_CELL_LIST": "0", "I2P_BALL_WARP": "1"},
+                                 {"I2P_CELL_LIST": "0", "I2P_BALL_WARP": "0"}], ids=["grid", "warp", "thread"])
+def test_every_neighbour_query_form_matches_oracle(env, dev):
+    """The three forms of the ball query (cell list, warp per query, thread per query) are picked by cloud size; each one,
+    forced on every case -- empty neighbourhoods, queries far outside the cloud, quantised coordinates with exact ties --
+    returns the oracle's indices bit for bit.  The form is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", _FORCED_FORM], cwd=root, env={**os.environ, **env}, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+_KNN_FORMS = """
+import sys
+import numpy as np
+import torch
+from i2pnet_b200 import _cabi
+dev = torch.device("cuda:0")
+rng = np.random.Generator(np.random.PCG64(77))
+out = {}
+def cloud(b, n, kind):
+    x = rng.standard_normal((b, n, 3)).astype(np.float32) * np.float32(10)
+    if kind == "quant":
+        x = np.round(x / 2) * 2              # exact distance ties, duplicated points
+    if kind == "planar":
+        x[..., 2] = 1.5
+    if kind == "line":
+        x[..., 1:] = 0
+    if kind == "point":
+        x[...] = x[:, :1]
+    if kind == "slab":
+        x = (rng.random((b, n, 3)).astype(np.float32) * np.float32([80, 80, 4]) - np.float32([40, 40, 3])).astype(np.float32)
+    return np.ascontiguousarray(x.astype(np.float32))
+for name, (b, n, m, k, kind) in {"gauss": (2, 3000, 700, 16, "gauss"), "quant": (2, 2500, 600, 16, "quant"), "planar": (1, 2000, 500, 8, "planar"),
+                                 "line": (1, 1500, 300, 5, "line"), "point": (1, 400, 64, 32, "point"), "k1": (2, 900, 333, 1, "gauss"),
+                                 "k_eq_m": (1, 100, 20, 20, "gauss"), "slab_20k": (2, 20000, 20000, 16, "slab"),
+                                 "far_queries": (1, 500, 3000, 9, "gauss")}.items():
+    unknown, known = cloud(b, n, kind), cloud(b, m, kind)
+    if name == "far_queries":
+        unknown = unknown + np.float32(500)
+    if kind == "quant":
+        unknown[:, : n // 2] = known[:, rng.integers(0, m, n // 2)]
+    u, kn = torch.from_numpy(unknown).to(dev), torch.from_numpy(known).to(dev)
+    d = torch.full((b, n, k), -1.0, device=dev)
+    i = torch.full((b, n, k), -1, dtype=torch.int32, device=dev)
+    _cabi.knn(b, n, m, k, u, kn, d, i)
+    out[name + "_d"], out[name + "_i"] = d.cpu().numpy(), i.cpu().numpy()
+    if m >= 3:
+        d3 = torch.full((b, n, 3), -1.0, device=dev)
+        i3 = torch.full((b, n, 3), -1, dtype=torch.int32, device=dev)
+        _cabi.three_nn(b, n, m, u, kn, d3, i3)
+        out[name + "_d3"], out[name + "_i3"] = d3.cpu().numpy(), i3.cpu().numpy()
+np.savez(sys.argv[1], **out)
+print("ok")
+"""
+
+
+def test_cell_list_knn_equals_brute_force_bit_for_bit(dev, tmp_path):
+    """k-NN / 3-NN over the cell list against the brute-force kernels (themselves checked against the oracle and the
+    reference kernels above) on the same inputs: indices and distances identical, including exact distance ties
+    (quantised clouds, duplicated points), degenerate clouds (planar, collinear, a single location), k = 1, k = m and
+    queries far outside the cloud's bounding box.  The form is read once per process, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for form in ("0", "1"):
+        path = str(tmp_path / ("knn_form%s.npz" % form))
+        out = subprocess.run([sys.executable, "-c", _KNN_FORMS, path], cwd=root, env={**os.environ, "I2P_CELL_LIST": form},
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+        res[form] = np.load(path)
+    assert len(res["0"].files) >= 30
+    for key in res["0"].files:
+        assert np.array_equal(res["0"][key], res["1"][key]), key
+        assert (res["0"][key] != -1).all(), key
+
+
 def _sorted_sets(idx):
     return np.sort(idx, axis=-1)
 
