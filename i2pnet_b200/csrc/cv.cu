@@ -283,6 +283,238 @@ static bool cv_geom(CvGeom &g, int B, int N, int K, int N2, int C, int has_max) 
     return B >= 1 && N >= 1 && K >= 1 && N2 >= 1 && C >= 8 && threads <= 256 && B <= 65535;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// cost-volume operand preparation (PPBackbone_center.py:379-397) as ONE kernel per direction
+// ---------------------------------------------------------------------------------------------
+// Everything between the pyramids' outputs and cv_build is arithmetic on (B, N, C) / (B, N2, C) tensors of ~1 MB:
+// depth restoration xyz = uv * z, the row-wise standardisation (x - mean) / max(std, 1e-12) (unbiased std) of the point
+// and pixel features, and for the backward-validation channel the largest / smallest standardised point feature over the
+// valid points and maxc[k,c] = qi[k,c] * (qi > 0 ? hi[c] : lo[c]).  Through ATen that is ~40 launches forward and more
+// backward, every one of them on the step's critical path (CUPTI timeline: 215 us before cost volume 1, one kernel in
+// flight).  One block per cloud does it all; the extrema carry the index of the first point that attains them, which
+// is where the backward sends their gradient (torch.max's convention).
+constexpr int PREP_THREADS = 512, PREP_WARPS = PREP_THREADS / 32, PREP_MAXJ = 8;    // C <= 256
+
+struct PrepArgs {
+    int N, N2, C, has_max;
+    const float *uv, *z, *pf, *qf;                   // (B,N,3) (B,N,1) (B,N,C) (B,N2,C)
+    float *xyz, *pi, *qi, *den_p, *den_q, *maxc;     // (B,N,3) (B,N,C) (B,N2,C) (B,N) (B,N2) (B,N2,C)
+    float *hi, *lo;                                  // (B,C) each; 0 when the cloud has no valid point
+    int *arg_hi, *arg_lo;                            // (B,C); -1 when the cloud has no valid point
+};
+
+// standardise one row held as v[j] = x[lane + 32 j]; -> the clipped denominator
+__device__ __forceinline__ float standardise_row(float (&v)[PREP_MAXJ], int C, int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < PREP_MAXJ; ++j) s += (lane + 32 * j < C) ? v[j] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < PREP_MAXJ; ++j) {
+        v[j] -= mean;
+        q += (lane + 32 * j < C) ? v[j] * v[j] : 0.f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(FULL, q, o);
+    const float den = fmaxf(sqrtf(q / (float)(C - 1)), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < PREP_MAXJ; ++j) v[j] /= den;
+    return den;
+}
+
+__global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_fwd_kernel(const PrepArgs a) {
+    __shared__ float hi_s[32 * PREP_MAXJ], lo_s[32 * PREP_MAXJ];
+    __shared__ int ahi_s[32 * PREP_MAXJ], alo_s[32 * PREP_MAXJ];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = a.N, N2 = a.N2, C = a.C;
+    float hi[PREP_MAXJ], lo[PREP_MAXJ];
+    int ahi[PREP_MAXJ], alo[PREP_MAXJ];
+#pragma unroll
+    for (int j = 0; j < PREP_MAXJ; ++j) { hi[j] = -INFINITY; lo[j] = INFINITY; ahi[j] = alo[j] = -1; }
+    for (int r = warp; r < N + N2; r += PREP_WARPS) {
+        const bool point = r < N;
+        const size_t row = point ? (size_t)b * N + r : (size_t)b * N2 + (r - N);
+        const float *src = (point ? a.pf : a.qf) + row * C;
+        float v[PREP_MAXJ];
+#pragma unroll
+        for (int j = 0; j < PREP_MAXJ; ++j) v[j] = (lane + 32 * j < C) ? __ldg(src + lane + 32 * j) : 0.f;
+        const float den = standardise_row(v, C, lane);
+        float *dst = (point ? a.pi : a.qi) + row * C;
+#pragma unroll
+        for (int j = 0; j < PREP_MAXJ; ++j)
+            if (lane + 32 * j < C) dst[lane + 32 * j] = v[j];
+        if (lane == 0) (point ? a.den_p : a.den_q)[row] = den;
+        if (point) {
+            const float zz = __ldg(a.z + row);
+            const float x = lane < 3 ? __ldg(a.uv + row * 3 + lane) * zz : 0.f;     // restore depth (:379)
+            if (lane < 3) a.xyz[row * 3 + lane] = x;
+            const bool valid = __any_sync(FULL, x != 0.f);
+            if (valid && a.has_max) {
+#pragma unroll
+                for (int j = 0; j < PREP_MAXJ; ++j) {       // rows come in increasing order: strict comparisons keep the first
+                    if (v[j] > hi[j]) { hi[j] = v[j]; ahi[j] = r; }
+                    if (v[j] < lo[j]) { lo[j] = v[j]; alo[j] = r; }
+                }
+            }
+        }
+    }
+    if (!a.has_max) return;
+    // merge the warps' extrema, one warp at a time (value first, then the smaller point index)
+    for (int w = 0; w < PREP_WARPS; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int j = 0; j < PREP_MAXJ; ++j) {
+                const int c = lane + 32 * j;
+                if (w == 0) { hi_s[c] = hi[j]; ahi_s[c] = ahi[j]; lo_s[c] = lo[j]; alo_s[c] = alo[j]; }
+                else {
+                    if (ahi[j] >= 0 && (ahi_s[c] < 0 || hi[j] > hi_s[c] || (hi[j] == hi_s[c] && ahi[j] < ahi_s[c]))) { hi_s[c] = hi[j]; ahi_s[c] = ahi[j]; }
+                    if (alo[j] >= 0 && (alo_s[c] < 0 || lo[j] < lo_s[c] || (lo[j] == lo_s[c] && alo[j] < alo_s[c]))) { lo_s[c] = lo[j]; alo_s[c] = alo[j]; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const bool any_valid = ahi_s[0] >= 0;      // a valid point sets every channel
+    for (int c = threadIdx.x; c < C; c += PREP_THREADS) {
+        a.hi[(size_t)b * C + c] = any_valid ? hi_s[c] : 0.f;
+        a.lo[(size_t)b * C + c] = any_valid ? lo_s[c] : 0.f;
+        a.arg_hi[(size_t)b * C + c] = any_valid ? ahi_s[c] : -1;
+        a.arg_lo[(size_t)b * C + c] = any_valid ? alo_s[c] : -1;
+    }
+    // maxc = max over the valid points of pi[n,c] * qi[k,c] (-1e10 for a cloud without valid points): the rows of qi this
+    // block wrote above are visible to it after the barrier
+    for (int e = threadIdx.x; e < N2 * C; e += PREP_THREADS) {
+        const int c = e % C;
+        const float q = a.qi[(size_t)b * N2 * C + e];
+        a.maxc[(size_t)b * N2 * C + e] = any_valid ? (q > 0.f ? q * hi_s[c] : q * lo_s[c]) : -1e10f;
+    }
+}
+
+struct PrepBwdArgs {
+    int N, N2, C, has_max;
+    const float *uv, *z, *pi, *qi, *den_p, *den_q, *hi, *lo;
+    const int *arg_hi, *arg_lo;
+    const float *d_xyz, *d_pi, *d_qi, *d_maxc;      // any of them may be null (no gradient arrived)
+    float *d_uv, *d_z, *d_pf, *d_qf;
+};
+
+// backward of one standardised row: y (saved output), g = dL/dy  ->  dL/dx, in place in g
+__device__ __forceinline__ void standardise_row_bwd(float (&g)[PREP_MAXJ], const float (&y)[PREP_MAXJ], float den, int C, int lane) {
+    float sg = 0.f, sgy = 0.f;
+#pragma unroll
+    for (int j = 0; j < PREP_MAXJ; ++j) {
+        const bool in = lane + 32 * j < C;
+        sg += in ? g[j] : 0.f;
+        sgy += in ? g[j] * y[j] : 0.f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sg += __shfl_xor_sync(FULL, sg, o); sgy += __shfl_xor_sync(FULL, sgy, o); }
+    const float mg = sg / (float)C;
+    // the clipped denominator is a constant: only the mean's term remains
+    const float k = den > 1e-12f ? sgy / (float)(C - 1) : 0.f;
+#pragma unroll
+    for (int j = 0; j < PREP_MAXJ; ++j) g[j] = (g[j] - mg - y[j] * k) / den;
+}
+
+__global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_bwd_kernel(const PrepBwdArgs a) {
+    __shared__ float dhi_s[32 * PREP_MAXJ], dlo_s[32 * PREP_MAXJ];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = a.N, N2 = a.N2, C = a.C;
+    const bool use_max = a.has_max && a.d_maxc != nullptr && a.arg_hi[(size_t)b * C] >= 0;
+    for (int c = threadIdx.x; c < 32 * PREP_MAXJ; c += PREP_THREADS) dhi_s[c] = dlo_s[c] = 0.f;
+    __syncthreads();
+    if (use_max) {
+        // d hi[c] = sum over the pixels with qi > 0 of d maxc * qi, d lo[c] over the others
+        float dh[PREP_MAXJ], dl[PREP_MAXJ];
+#pragma unroll
+        for (int j = 0; j < PREP_MAXJ; ++j) dh[j] = dl[j] = 0.f;
+        for (int k = warp; k < N2; k += PREP_WARPS) {
+            const size_t row = ((size_t)b * N2 + k) * C;
+#pragma unroll
+            for (int j = 0; j < PREP_MAXJ; ++j) {
+                const int c = lane + 32 * j;
+                if (c < C) {
+                    const float q = __ldg(a.qi + row + c), t = __ldg(a.d_maxc + row + c) * q;
+                    if (q > 0.f) dh[j] += t; else dl[j] += t;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PREP_MAXJ; ++j) { atomicAdd(&dhi_s[lane + 32 * j], dh[j]); atomicAdd(&dlo_s[lane + 32 * j], dl[j]); }
+    }
+    __syncthreads();
+    for (int r = warp; r < N + N2; r += PREP_WARPS) {
+        const bool point = r < N;
+        const size_t row = point ? (size_t)b * N + r : (size_t)b * N2 + (r - N);
+        const float *ysrc = (point ? a.pi : a.qi) + row * C;
+        const float *gsrc = point ? a.d_pi : a.d_qi;
+        float y[PREP_MAXJ], g[PREP_MAXJ];
+#pragma unroll
+        for (int j = 0; j < PREP_MAXJ; ++j) {
+            const int c = lane + 32 * j;
+            const bool in = c < C;
+            y[j] = in ? __ldg(ysrc + c) : 0.f;
+            g[j] = (in && gsrc != nullptr) ? __ldg(gsrc + row * C + c) : 0.f;
+            if (in && use_max) {
+                if (point) {
+                    if (r == __ldg(a.arg_hi + (size_t)b * C + c)) g[j] += dhi_s[c];
+                    if (r == __ldg(a.arg_lo + (size_t)b * C + c)) g[j] += dlo_s[c];
+                } else {
+                    const float sel = y[j] > 0.f ? __ldg(a.hi + (size_t)b * C + c) : __ldg(a.lo + (size_t)b * C + c);
+                    g[j] += __ldg(a.d_maxc + row * C + c) * sel;
+                }
+            }
+        }
+        standardise_row_bwd(g, y, __ldg((point ? a.den_p : a.den_q) + row), C, lane);
+        float *dst = (point ? a.d_pf : a.d_qf) + row * C;
+#pragma unroll
+        for (int j = 0; j < PREP_MAXJ; ++j)
+            if (lane + 32 * j < C) dst[lane + 32 * j] = g[j];
+        if (point) {
+            const float zz = __ldg(a.z + row);
+            float gz = 0.f;
+            if (lane < 3) {
+                const float gx = a.d_xyz != nullptr ? __ldg(a.d_xyz + row * 3 + lane) : 0.f;
+                a.d_uv[row * 3 + lane] = gx * zz;
+                gz = gx * __ldg(a.uv + row * 3 + lane);
+            }
+            gz += __shfl_down_sync(FULL, gz, 2);
+            gz += __shfl_down_sync(FULL, gz, 1);     // lane 0: g0 u0 + g2 u2 + g1 u1
+            if (lane == 0) a.d_z[row] = gz;
+        }
+    }
+}
+
+// Pixel centres of an (h, w) feature map on the normalised camera plane: K'^-1 [u, v, 1] with K' = the intrinsic rescaled
+// to the map (rows 0 / 1 times sx / sy), inverted by the adjugate (modellearn_proj_center.py:275-287; 57 ATen launches).
+__global__ void __launch_bounds__(256) pixel_rays_kernel(int h, int w, float sx, float sy, const float *__restrict__ intrinsic,
+                                                        float *__restrict__ rays) {
+    const int b = blockIdx.y, p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= h * w) return;
+    const float *K = intrinsic + (size_t)b * 9;
+    // every product and sum rounded separately, in the order of the element-wise formulation it replaces (inverse3x3's
+    // adjugate, then (grid * K^-1).sum(-1)): the rays feed a nearest-pixel selection, where one ulp can flip a near-tie
+    auto mul = [](float x, float y) { return __fmul_rn(x, y); };
+    auto sub = [](float x, float y) { return __fsub_rn(x, y); };
+    auto add = [](float x, float y) { return __fadd_rn(x, y); };
+    const float a_ = mul(K[0], sx), b_ = mul(K[1], sx), c_ = mul(K[2], sx), d_ = mul(K[3], sy), e_ = mul(K[4], sy), f_ = mul(K[5], sy);
+    const float g_ = K[6], h_ = K[7], i_ = K[8];
+    const float A = sub(mul(e_, i_), mul(f_, h_)), Bc = -sub(mul(d_, i_), mul(f_, g_)), Cc = sub(mul(d_, h_), mul(e_, g_));
+    const float det = add(add(mul(a_, A), mul(b_, Bc)), mul(c_, Cc));
+    const float adj[9] = {A, -sub(mul(b_, i_), mul(c_, h_)), sub(mul(b_, f_), mul(c_, e_)),
+                          Bc, sub(mul(a_, i_), mul(c_, g_)), -sub(mul(a_, f_), mul(c_, d_)),
+                          Cc, -sub(mul(a_, h_), mul(b_, g_)), sub(mul(a_, e_), mul(b_, d_))};
+    const float u = (float)(p % w), v = (float)(p / w);
+    float *o = rays + ((size_t)b * h * w + p) * 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        o[i] = add(add(mul(u, __fdiv_rn(adj[3 * i], det)), mul(v, __fdiv_rn(adj[3 * i + 1], det))), __fdiv_rn(adj[3 * i + 2], det));
+}
+
 }  // namespace i2p
 
 extern "C" {
@@ -349,5 +581,37 @@ int i2p_softmax_wsum_bwd(long long groups, int K, int C, const float *logit, con
     softmax_wsum_bwd_kernel<<<(int)(gr < 148 * 16 ? gr : 148 * 16), 256, 0, as_stream(stream)>>>(total, K, C, logit, value, mask, out,
                                                                                                  gout, dlogit, dvalue);
     return check_launch("softmax_wsum_bwd");
+}
+int i2p_cv_prep_fwd(int B, int N, int N2, int C, int has_max, const float *uv, const float *z, const float *pf, const float *qf,
+                    float *xyz, float *pi, float *qi, float *den_p, float *den_q, float *maxc, float *hi, float *lo, int32_t *arg_hi,
+                    int32_t *arg_lo, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(B >= 0 && N >= 1 && N2 >= 1 && C >= 2 && C <= 32 * PREP_MAXJ && B <= 65535, "cv_prep: bad sizes (2 <= C <= 256)");
+    I2P_REQUIRE(!has_max || (maxc != nullptr && hi != nullptr && lo != nullptr && arg_hi != nullptr && arg_lo != nullptr),
+                "cv_prep: outputs of the backward-validation channel missing");
+    if (B == 0) return I2P_OK;
+    PrepArgs a{N, N2, C, has_max ? 1 : 0, uv, z, pf, qf, xyz, pi, qi, den_p, den_q, maxc, hi, lo, arg_hi, arg_lo};
+    cv_prep_fwd_kernel<<<B, PREP_THREADS, 0, as_stream(stream)>>>(a);
+    return check_launch("cv_prep_fwd");
+}
+
+int i2p_cv_prep_bwd(int B, int N, int N2, int C, int has_max, const float *uv, const float *z, const float *pi, const float *qi,
+                    const float *den_p, const float *den_q, const float *hi, const float *lo, const int32_t *arg_hi,
+                    const int32_t *arg_lo, const float *d_xyz, const float *d_pi, const float *d_qi, const float *d_maxc, float *d_uv,
+                    float *d_z, float *d_pf, float *d_qf, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(B >= 0 && N >= 1 && N2 >= 1 && C >= 2 && C <= 32 * PREP_MAXJ && B <= 65535, "cv_prep_bwd: bad sizes (2 <= C <= 256)");
+    if (B == 0) return I2P_OK;
+    PrepBwdArgs a{N, N2, C, has_max ? 1 : 0, uv, z, pi, qi, den_p, den_q, hi, lo, arg_hi, arg_lo, d_xyz, d_pi, d_qi, d_maxc, d_uv, d_z, d_pf, d_qf};
+    cv_prep_bwd_kernel<<<B, PREP_THREADS, 0, as_stream(stream)>>>(a);
+    return check_launch("cv_prep_bwd");
+}
+
+int i2p_pixel_rays(int B, int h, int w, float sx, float sy, const float *intrinsic, float *rays, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(B >= 0 && h >= 1 && w >= 1 && B <= 65535, "pixel_rays: bad sizes");
+    if (B == 0) return I2P_OK;
+    pixel_rays_kernel<<<dim3(ceil_div(h * w, 256), B), 256, 0, as_stream(stream)>>>(h, w, sx, sy, intrinsic, rays);
+    return check_launch("pixel_rays");
 }
 }

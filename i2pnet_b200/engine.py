@@ -330,7 +330,7 @@ class TrainStep:
             raise RuntimeError("TrainStep.warmup_and_capture: load() a real batch first (all-zero inputs put NaNs "
                                "into the range-image maths)")
         snap = self._snapshot()
-        s = torch.cuda.Stream(self.device)
+        s = streams.main_stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(eager_steps):
@@ -342,7 +342,7 @@ class TrainStep:
         self._restore(snap)
         if self.use_graph:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=s):
                 self._step_body()
             torch.cuda.synchronize(self.device)
 

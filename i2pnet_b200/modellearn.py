@@ -19,7 +19,7 @@ from .modules.basicConv import createCNNs
 from .modules.MainModules import CostVolume, DelayWeight, FlowPredictor, PoseHead, ProjectMask
 from .modules.pointnet2_module import SetUpconvModule
 from .pointnet_util import PointNetSetAbstraction, farthest_point_sample, index_points
-from .projectPN.utils import inverse3x3
+from .projectPN.utils import inverse3x3, pixel_rays  # noqa: F401
 from .streams import Fork
 
 
@@ -124,9 +124,7 @@ class RegNet_v2(nn.Module):
 
         # pixels on the normalised camera plane
         RF3 = rgb_branch.join(RF3)
-        RF3_index = set_id_grid(RF3.permute(0, 2, 3, 1))                  # B,h3*w3,3 pixel coordinates
-        intrinsic_3_inv = inverse3x3(change_intrinsic(intrinsic, RF3, rgb_img))
-        RF3_index = torch.bmm(intrinsic_3_inv, RF3_index.permute(0, 2, 1)).permute(0, 2, 1)
+        RF3_index = pixel_rays(intrinsic, RF3.shape[2], RF3.shape[3], rgb_img.shape[2], rgb_img.shape[3])   # B,h3*w3,3
         lidar_uv, lidar_z, LF3 = warp_utils.projection_initial(P3, None, None, None, LF3)
         _, C, H, W = RF3.shape
         RF3 = RF3.reshape(B, C, H * W).permute(0, 2, 1)                   # B,h3*w3,C

@@ -16,7 +16,8 @@ from .config_proj_lidarcenter import I2PNetConfig as cfg_default
 from .modules import warp_utils
 from .modules.basicConv import createCNNs
 from .projectPN.PPBackbone_center import CostVolume, FlowPredictor, PoseHead, ProjectPointNet, ProjSetUpconvModule
-from .projectPN.utils import StrideGrid, check_valid, inverse3x3, project_seq
+from .modules.basicConv import pyramid_out_hw
+from .projectPN.utils import StrideGrid, check_valid, inverse3x3, pixel_rays, project_seq  # noqa: F401
 from .streams import Fork
 
 
@@ -126,6 +127,10 @@ class RegNet_v2(nn.Module):
         # The image pyramid and the LiDAR pyramid are independent up to the first cost volume: the image branch goes
         # to a side stream (streams.py), joined right before its output is first read.
         with Fork(rgb_img) as rgb_branch:
+            # pixel centres of RF3 on the normalised camera plane, K3^-1 [u, v, 1]: they depend on RF3's SHAPE only, so
+            # they are issued ahead of the pyramid instead of on the critical path between the pyramids and cost volume 1
+            h3, w3 = pyramid_out_hw((self.RGB_net1, self.RGB_net2, self.RGB_net3), rgb_img.shape[2], rgb_img.shape[3])
+            RF3_index = pixel_rays(intrinsic, h3, w3, rgb_img.shape[2], rgb_img.shape[3])
             RF3 = self.RGB_net3(self.RGB_net2(self.RGB_net1(rgb_img)))
 
         lidar_norm = torch.zeros(B, N, 3, device=dev) if lidar_feature is None else lidar_feature
@@ -139,11 +144,8 @@ class RegNet_v2(nn.Module):
         P3_raw, P3, LF3, _, _ = self.LiDAR_lv3(P2_raw, P2, LF2, **rfkw)
         P4_raw, P4, LF4, _, sample_idx_4 = self.LiDAR_lv4(P3_raw, P3, LF3, **rfkw)
 
-        RF3 = rgb_branch.join(RF3)
-        # pixel centres of RF3 on the normalised camera plane: K3^-1 [u, v, 1]
-        K3_inv = inverse3x3(change_intrinsic(intrinsic, RF3, rgb_img))
-        # (B,hw,3) = grid K3_inv^T, spelled element-wise: a 3x3 batched product is not worth a library GEMM launch
-        RF3_index = (set_id_grid(RF3.permute(0, 2, 3, 1)).unsqueeze(2) * K3_inv.unsqueeze(1)).sum(-1)
+        RF3, RF3_index = rgb_branch.join(RF3, RF3_index)
+        assert RF3.shape[2:] == (h3, w3), (RF3.shape, h3, w3)
 
         H3, W3 = self.lidar_Hs[2], self.lidar_Ws[2]
         H4, W4 = self.lidar_Hs[-1], self.lidar_Ws[-1]

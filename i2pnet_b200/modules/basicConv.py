@@ -199,6 +199,18 @@ class _Pyramid(nn.Sequential):
         return x
 
 
+def pyramid_out_hw(nets, H, W):
+    """Spatial size of the output of a chain of createCNNs pyramids for an (H, W) input: the 3x3 / stride-1 / pad-1
+    convolutions keep it, MaxPool2d(3, s, 1) gives floor((n - 1) / s) + 1.  (Lets the caller prepare what depends on the
+    feature map's SHAPE only -- the pixel rays of the cost volumes -- before the pyramid has run.)"""
+    for net in nets:
+        for m in net:
+            if isinstance(m, nn.MaxPool2d):
+                s = m.stride if isinstance(m.stride, int) else m.stride[0]
+                H, W = (H - 1) // s + 1, (W - 1) // s + 1
+    return H, W
+
+
 def createCNNs(in_channel, channels, strides):
     layers = _Pyramid()
     last = in_channel

@@ -318,6 +318,59 @@ class _CvBuild(torch.autograd.Function):
         return dxyz1, dxyz2, dpi, dqi, dmaxc, None
 
 
+class _CvPrep(torch.autograd.Function):
+    """Operand preparation of the cost volume as one kernel per direction (csrc/cv.cu cv_prep): depth restoration
+    xyz = uv * z, the row-wise standardisation of the point and pixel features and, for the backward-validation channel,
+    maxc[k,c] = max over the valid points n of pi[n,c] * qi[k,c] = qi[k,c] times the largest (qi > 0) or smallest valid
+    pi[:,c] -- multiplication by a constant is monotonic also after rounding (:379-397).
+    uv (B,N,3), z (B,N,1), pf (B,N,C), qf (B,N2,C) -> xyz (B,N,3), pi (B,N,C), qi (B,N2,C), maxc (B,N2,C) | None"""
+
+    @staticmethod
+    def forward(ctx, uv, z, pf, qf, has_max):
+        from .. import _cabi
+        f32, dev = torch.float32, pf.device
+        uv, z, pf, qf = uv.contiguous(), z.contiguous(), pf.contiguous(), qf.contiguous()
+        B, N, C = pf.shape
+        N2 = qf.shape[1]
+        xyz, pi, qi = torch.empty_like(uv), torch.empty_like(pf), torch.empty_like(qf)
+        den = torch.empty(B * (N + N2), dtype=f32, device=dev)
+        den_p, den_q = den[:B * N], den[B * N:]
+        if has_max:
+            maxc = torch.empty_like(qf)
+            ext = torch.empty(2, B, C, dtype=f32, device=dev)
+            arg = torch.empty(2, B, C, dtype=torch.int32, device=dev)
+        else:
+            maxc = ext = arg = None
+        P = lambda x, n: _cabi._ptr(x, f32, n, dev)
+        _cabi.call("i2p_cv_prep_fwd", dev, B, N, N2, C, int(has_max), P(uv, "warped_xyz"), P(z, "lidar_z"), P(pf, "warped_points"),
+                   P(qf, "f2_points"), xyz.data_ptr(), pi.data_ptr(), qi.data_ptr(), den_p.data_ptr(), den_q.data_ptr(),
+                   maxc.data_ptr() if has_max else None, ext[0].data_ptr() if has_max else None,
+                   ext[1].data_ptr() if has_max else None, arg[0].data_ptr() if has_max else None,
+                   arg[1].data_ptr() if has_max else None)
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(uv, z, pi, qi, den, ext if has_max else empty, arg if has_max else empty)
+        ctx.meta = (B, N, N2, C, bool(has_max))
+        ctx.set_materialize_grads(False)
+        return xyz, pi, qi, maxc
+
+    @staticmethod
+    def backward(ctx, d_xyz, d_pi, d_qi, d_maxc):
+        from .. import _cabi
+        uv, z, pi, qi, den, ext, arg = ctx.saved_tensors
+        B, N, N2, C, has_max = ctx.meta
+        f32, dev = torch.float32, pi.device
+        d_uv, d_z, d_pf, d_qf = torch.empty_like(uv), torch.empty_like(z), torch.empty_like(pi), torch.empty_like(qi)
+        G = lambda g, n: _cabi._ptr(g.contiguous(), f32, n, dev) if g is not None else None
+        # the contiguous copies must outlive the launch: keep them referenced until the call returns
+        keep = [g.contiguous() if g is not None else None for g in (d_xyz, d_pi, d_qi, d_maxc)]
+        _cabi.call("i2p_cv_prep_bwd", dev, B, N, N2, C, int(has_max), uv.data_ptr(), z.data_ptr(), pi.data_ptr(), qi.data_ptr(),
+                   den[:B * N].data_ptr(), den[B * N:].data_ptr(), ext[0].data_ptr() if has_max else None,
+                   ext[1].data_ptr() if has_max else None, arg[0].data_ptr() if has_max else None,
+                   arg[1].data_ptr() if has_max else None, *[G(g, "gradient") for g in keep], d_uv.data_ptr(), d_z.data_ptr(),
+                   d_pf.data_ptr(), d_qf.data_ptr())
+        return d_uv, d_z, d_pf, d_qf, None
+
+
 class _SoftmaxWSum(torch.autograd.Function):
     """sum_k softmax_k(logit [masked]) * value over axis 2 of (B,N,K,C) tensors -> (B,N,C)  (csrc/cv.cu)."""
 
@@ -462,18 +515,7 @@ class CostVolume(nn.Module):
         idx = None
         if self.nsample_q > 0:
             idx = knn_point(self.nsample_q, f2_xyz.contiguous(), warped_xyz.contiguous()).to(torch.int32)
-        warped_xyz = warped_xyz.mul(lidar_z)                        # restore depth (:379)
-        pi_n = _standardise(warped_points)                          # B,N,C
-        qi_n = _standardise(f2_points)                              # B,N2,C
-        maxc = None
-        if self.backward_validation:
-            valid = check_valid(warped_xyz) > 0                     # B,N,1
-            any_valid = valid.any(dim=1, keepdim=True)              # B,1,1
-            hi = torch.where(valid, pi_n, float("-inf")).max(dim=1, keepdim=True)[0]   # B,1,C
-            lo = torch.where(valid, pi_n, float("inf")).min(dim=1, keepdim=True)[0]
-            hi, lo = torch.where(any_valid, hi, 0.0), torch.where(any_valid, lo, 0.0)
-            maxc = torch.where(qi_n > 0, qi_n * hi, qi_n * lo)      # B,N2,C
-            maxc = torch.where(any_valid, maxc, -1e10)
+        warped_xyz, pi_n, qi_n, maxc = _CvPrep.apply(warped_xyz, lidar_z, warped_points, f2_points, self.backward_validation)
         X, xyz6 = _CvBuild.apply(warped_xyz, f2_xyz, pi_n, qi_n, maxc, idx)
         return X, xyz6, warped_xyz
 

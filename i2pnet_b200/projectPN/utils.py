@@ -215,6 +215,25 @@ def inverse3x3(m):
     return adj / det.view(-1, 1, 1)
 
 
+def pixel_rays(intrinsic, h, w, img_h, img_w):
+    """Pixel centres of an (h, w) feature map of an (img_h, img_w) image on the normalised camera plane, (B, h*w, 3):
+    K'^-1 [u, v, 1] with K' the intrinsic (B,3,3) rescaled to the map (src/modellearn_proj_center.py:275-287:
+    change_intrinsic -> torch.inverse on the host -> set_id_grid -> bmm).  One kernel on the device; no gradient (the
+    intrinsic is data)."""
+    sx, sy = w / img_w, h / img_h
+    B = intrinsic.shape[0]
+    if intrinsic.is_cuda:
+        from .. import _cabi
+        K = intrinsic.detach().float().contiguous()
+        rays = torch.empty(B, h * w, 3, dtype=torch.float32, device=K.device)
+        _cabi.call("i2p_pixel_rays", K.device, B, h, w, float(sx), float(sy), _cabi._ptr(K, torch.float32, "intrinsic"), rays.data_ptr())
+        return rays
+    K = torch.cat([intrinsic[:, 0:1] * sx, intrinsic[:, 1:2] * sy, intrinsic[:, 2:3]], dim=1).float()
+    v, u = torch.meshgrid(torch.arange(h, dtype=K.dtype), torch.arange(w, dtype=K.dtype), indexing="ij")
+    grid = torch.stack([u, v, torch.ones_like(u)], dim=-1).reshape(1, h * w, 3)
+    return (grid.unsqueeze(2) * inverse3x3(K).unsqueeze(1)).sum(-1)
+
+
 # ---------------------------------------------------------------------------------------------
 # brute-force kNN grouping
 # ---------------------------------------------------------------------------------------------

@@ -23,6 +23,26 @@ ENABLED = os.environ.get("I2P_STREAMS", "1") != "0"
 _POOL_SIZE = 4
 _pools = {}
 
+# Stream priorities (lower number = dispatched first).  The block scheduler hands out the blocks of the kernel that was
+# launched first; a 200 us kernel with thousands of blocks on one stream therefore starves every small kernel launched
+# after it on another stream until its last block has been dispatched -- in the replayed step the image branch's backward
+# (a chain of fifteen 10-70 us kernels, the tail of the step) sat idle for half of its 1.9 ms behind the LiDAR pyramid's
+# wide weight-gradient kernels (CUPTI timeline, tools/profile_step.py timeline).  With priorities the scheduler prefers
+# the blocks of the chain kernels as soon as slots free up: branches (consumed by the chain) first, the chain itself
+# second, weight gradients (consumed by nobody before the optimiser) last.  Captured kernel nodes keep the priority
+# of the stream they were captured on.  I2P_STREAM_PRIORITIES=0: all streams at the default priority.
+PRIORITIES = os.environ.get("I2P_STREAM_PRIORITIES", "1") != "0"
+_PRIORITY = {"branch": -2, "main": -1, "wgrad": 0}
+
+
+def priority_of(kind):
+    return _PRIORITY[kind] if PRIORITIES else 0
+
+
+def main_stream(device):
+    """A stream of the chain's priority for a step engine to run / capture the step on."""
+    return torch.cuda.Stream(device, priority=priority_of("main"))
+
 
 def _side_stream(device, avoid, kind="branch"):
     """Round-robin over a small pool of side streams.  Two disjoint pools: "branch" for sub-graphs whose results the
@@ -31,7 +51,7 @@ def _side_stream(device, avoid, kind="branch"):
     wait for the forking stream, and if that side stream were also the stream a branch lives on (the image pyramid's
     backward, say), the branch would inherit a dependency on wherever the forking chain happened to be -- measured: the
     image branch's backward started 0.9 ms late, serialised behind the LiDAR pyramid's backward."""
-    pool = _pools.setdefault((device.index, kind), {"streams": [torch.cuda.Stream(device) for _ in range(_POOL_SIZE)], "next": 0})
+    pool = _pools.setdefault((device.index, kind), {"streams": [torch.cuda.Stream(device, priority=priority_of(kind)) for _ in range(_POOL_SIZE)], "next": 0})
     for _ in range(_POOL_SIZE):
         s = pool["streams"][pool["next"]]
         pool["next"] = (pool["next"] + 1) % _POOL_SIZE

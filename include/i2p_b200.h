@@ -252,6 +252,25 @@ int i2p_softmax_wsum(long long groups, int K, int C, const float *logit, const f
 int i2p_softmax_wsum_bwd(long long groups, int K, int C, const float *logit, const float *value, const float *mask,
                          const float *out, const float *gout, float *dlogit, float *dvalue, void *stream);
 
+/* Operand preparation of the cost volume (src/projectPN/PPBackbone_center.py:379-397; replaces ~40 element-wise /
+ * reduction launches per direction): xyz (B,N,3) = uv * z; pi (B,N,C), qi (B,N2,C) = the point / pixel features
+ * standardised over the channel axis, (x - mean) / max(unbiased std, 1e-12), with the clipped denominators in den_p (B,N),
+ * den_q (B,N2); has_max: hi / lo (B,C) = largest / smallest pi[:,c] over the valid points (xyz != 0), arg_hi / arg_lo (B,C)
+ * the first point attaining it (0 / -1 for a cloud without valid points), maxc (B,N2,C) = qi * (qi > 0 ? hi : lo)
+ * (-1e10 without valid points) = max over the valid points of pi[n,c] qi[k,c], the backward-validation channel. */
+int i2p_cv_prep_fwd(int B, int N, int N2, int C, int has_max, const float *uv, const float *z, const float *pf, const float *qf,
+                    float *xyz, float *pi, float *qi, float *den_p, float *den_q, float *maxc, float *hi, float *lo, int32_t *arg_hi,
+                    int32_t *arg_lo, void *stream);
+/* d_xyz (B,N,3), d_pi (B,N,C), d_qi, d_maxc (B,N2,C), each or NULL -> d_uv (B,N,3), d_z (B,N), d_pf (B,N,C), d_qf (B,N2,C) */
+int i2p_cv_prep_bwd(int B, int N, int N2, int C, int has_max, const float *uv, const float *z, const float *pi, const float *qi,
+                    const float *den_p, const float *den_q, const float *hi, const float *lo, const int32_t *arg_hi,
+                    const int32_t *arg_lo, const float *d_xyz, const float *d_pi, const float *d_qi, const float *d_maxc, float *d_uv,
+                    float *d_z, float *d_pf, float *d_qf, void *stream);
+/* rays (B, h*w, 3) = K'^-1 [u, v, 1]: pixel centres of an (h, w) feature map on the normalised camera plane, K' = intrinsic
+ * (B,3,3) with row 0 scaled by sx and row 1 by sy (src/modellearn_proj_center.py:275-287: change_intrinsic, the host
+ * round trip through torch.inverse, set_id_grid and the batched product). */
+int i2p_pixel_rays(int B, int h, int w, float sx, float sy, const float *intrinsic, float *rays, void *stream);
+
 /* ---- quaternion product: replaces mul_q of src/modules/warp_utils.py:25-60 (one launch instead of ~30) ----
  * out (B,N,4) = A (x) B with A = a (B,na,4), B = b (B,nb,4), na / nb in {1, N} (broadcast over points),
  * either operand optionally conjugated (the backward pass is da = dc (x) conj(b), db = conj(a) (x) dc). */

@@ -124,10 +124,25 @@ def golden_iter():
     for head in (model.l4_head, model.l3_head):
         head.DP1.p = 0.0
     t = lambda k: torch.from_numpy(g[k])
-    with torch.no_grad():
-        out3, out4, _, _, _, _ = model(t("rgb_u8").float(), t("lidar"), t("raw_point_xyz"), None, t("intrinsic"), None, None,
-                                       None, t("lidar_feats"), cfg)
-    _save("ref_model_iter_kitti_b2.npz", out3=out3, out4=out4)
+    # the neighbour sets the reference itself selected in its six refinements (knn_point of the second cost volume: the 32
+    # pixels nearest to every point warped by the previous pose): the GPU test pins them, so that it compares arithmetic
+    # and not which side of a near-tie a 1e-6 pose difference falls on
+    from src.projectPN import utils as RP       # grouping() -> knn_point(), src/projectPN/utils.py:329, 369
+    sets, orig = [], RP.knn_point
+
+    def record(nsample, xyz, new_xyz):
+        idx = orig(nsample, xyz, new_xyz)
+        sets.append(idx.clone())
+        return idx
+    RP.knn_point = record
+    try:
+        with torch.no_grad():
+            out3, out4, _, _, _, _ = model(t("rgb_u8").float(), t("lidar"), t("raw_point_xyz"), None, t("intrinsic"), None, None,
+                                           None, t("lidar_feats"), cfg)
+    finally:
+        RP.knn_point = orig
+    assert len(sets) == 6 and all(s.shape == sets[0].shape for s in sets) and int(torch.stack(sets).max()) < 32768
+    _save("ref_model_iter_kitti_b2.npz", out3=out3, out4=out4, knn_sets=torch.stack(sets).to(torch.int16))
 
 
 def golden_nus():

@@ -156,16 +156,35 @@ def _run_iter_model(state, g, device):
     return out3, out4
 
 
-def check_iter_model(device, knn_flip_tol=None):
+def check_iter_model(device, knn_flip_tol=None, pin_knn_sets=False):
     """The six-iteration inference model against the reference's own
     src/modellearn_proj_center_iter.py run on the same inputs and weights (tests/golden/make_golden.py iter).
-    knn_flip_tol: see check_against_golden -- six refinements, six pose-dependent neighbour selections."""
+    Every refinement selects, per point, the 32 pixels nearest to the point warped by the PREVIOUS pose: 2736 selections
+    in all, of which a handful sit on near-ties that a 1e-6 pose difference flips (1 of 456 in the single-pass model, see
+    check_against_golden), each flip worth up to 2e-3 of the refined pose.
+    pin_knn_sets: the selections are replaced by the ones the reference made (recorded in the fixture), so the run
+    compares arithmetic and is held to the north-star tolerance; otherwise out3 is held to knn_flip_tol."""
     g, state = load_golden_model()
     ref = np.load(os.path.join(GOLDEN, "ref_model_iter_kitti_b2.npz"))
-    out3, out4 = _run_iter_model(state, g, device)
+    from i2pnet_b200.projectPN import PPBackbone_center as P
+    orig, calls = P.knn_point, []
+
+    def replay(nsample, xyz, new_xyz):
+        idx = torch.from_numpy(ref["knn_sets"][len(calls)].astype(np.int64)).to(new_xyz.device)
+        calls.append(idx)
+        assert idx.shape == (new_xyz.shape[0], new_xyz.shape[1], nsample)
+        return idx
+    try:
+        if pin_knn_sets:
+            P.knn_point = replay
+        out3, out4 = _run_iter_model(state, g, device)
+    finally:
+        P.knn_point = orig
+    assert not pin_knn_sets or len(calls) == 6
     assert _rel(out4.cpu(), ref["out4"]) < REL
-    assert _rel(out3.cpu(), ref["out3"]) < (knn_flip_tol or REL), _rel(out3.cpu(), ref["out3"])
-    if knn_flip_tol is None:
+    tol3 = REL if pin_knn_sets else (knn_flip_tol or REL)
+    assert _rel(out3.cpu(), ref["out3"]) < tol3, _rel(out3.cpu(), ref["out3"])
+    if pin_knn_sets or knn_flip_tol is None:
         check_pose_distance(out3, ref["out3"])
     assert _rel(out3.cpu(), g["out3"]) > 1e-3          # and it is not the single-pass answer
 

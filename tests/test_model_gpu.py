@@ -117,7 +117,8 @@ def test_iter_model_matches_reference():
     from tests.test_host_logic_cpu import check_iter_model
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    check_iter_model("cuda:0", knn_flip_tol=2e-3)
+    check_iter_model("cuda:0", pin_knn_sets=True)           # the reference's own neighbour sets: arithmetic at 1e-4
+    check_iter_model("cuda:0", knn_flip_tol=1e-2)           # free-running: a few of the 2736 selections flip (<= 2e-3 each)
 
 
 def test_reference_python_runs_unchanged_on_dropin_modules():
