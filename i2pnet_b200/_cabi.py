@@ -60,10 +60,13 @@ _SIGNATURES = {
     "i2p_cv_build_bwd": [_int] * 6 + [_vp] * 11,
     "i2p_softmax_wsum": [_ll, _int, _int] + [_vp] * 5,
     "i2p_softmax_wsum_bwd": [_ll, _int, _int] + [_vp] * 8,
-    "i2p_cv_prep_fwd": [_int] * 5 + [_vp] * 15,
+    "i2p_cv_prep_fwd": [_int] * 5 + [_vp] * 16,
+    "i2p_cv_prep_scratch_floats": [_int] * 4,
     "i2p_cv_prep_bwd": [_int] * 5 + [_vp] * 19,
     "i2p_pixel_rays": [_int, _int, _int, _flt, _flt, _vp, _vp, _vp],
     "i2p_quat_mul": [_int] * 6 + [_vp] * 4,
+    "i2p_quat_warp_fwd": [_int] * 3 + [_vp] * 5,
+    "i2p_quat_warp_bwd": [_int] * 3 + [_vp] * 7,
     "i2p_clip_adam_step": [_ll] + [_vp] * 5 + [_flt] * 6 + [_int, _vp],
     "i2p_rgb_bn_stats": [_int] * 4 + [_vp, _vp, _vp],
     "i2p_rgb_bn_finalize": [_int, _int, _vp, _vp, _vp, _flt, _flt, _vp, _vp, _vp, _vp, _vp, _vp],

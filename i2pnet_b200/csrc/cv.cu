@@ -302,6 +302,9 @@ struct PrepArgs {
     float *xyz, *pi, *qi, *den_p, *den_q, *maxc;     // (B,N,3) (B,N,C) (B,N2,C) (B,N) (B,N2) (B,N2,C)
     float *hi, *lo;                                  // (B,C) each; 0 when the cloud has no valid point
     int *arg_hi, *arg_lo;                            // (B,C); -1 when the cloud has no valid point
+    float *scratch;                                  // (B, S, 2, C) per-block extrema, S = blocks per cloud
+    int *scratch_arg;
+    unsigned *tickets;                               // (B) zero between launches
 };
 
 // standardise one row held as v[j] = x[lane + 32 j]; -> the clipped denominator
@@ -329,13 +332,15 @@ __device__ __forceinline__ float standardise_row(float (&v)[PREP_MAXJ], int C, i
 __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_fwd_kernel(const PrepArgs a) {
     __shared__ float hi_s[32 * PREP_MAXJ], lo_s[32 * PREP_MAXJ];
     __shared__ int ahi_s[32 * PREP_MAXJ], alo_s[32 * PREP_MAXJ];
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ unsigned ticket_s;
+    const int b = blockIdx.y, S = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = a.N, N2 = a.N2, C = a.C;
     float hi[PREP_MAXJ], lo[PREP_MAXJ];
     int ahi[PREP_MAXJ], alo[PREP_MAXJ];
 #pragma unroll
     for (int j = 0; j < PREP_MAXJ; ++j) { hi[j] = -INFINITY; lo[j] = INFINITY; ahi[j] = alo[j] = -1; }
-    for (int r = warp; r < N + N2; r += PREP_WARPS) {
+    // the cloud's rows (points, then pixels) are dealt to the S blocks of the cloud and their warps
+    for (int r = blockIdx.x * PREP_WARPS + warp; r < N + N2; r += S * PREP_WARPS) {
         const bool point = r < N;
         const size_t row = point ? (size_t)b * N + r : (size_t)b * N2 + (r - N);
         const float *src = (point ? a.pf : a.qf) + row * C;
@@ -364,20 +369,39 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_fwd_kernel(const Prep
     }
     if (!a.has_max) return;
     // merge the warps' extrema, one warp at a time (value first, then the smaller point index)
+    auto merge = [&](int c, float h, int ah, float l, int al, bool first) {
+        if (first) { hi_s[c] = h; ahi_s[c] = ah; lo_s[c] = l; alo_s[c] = al; return; }
+        if (ah >= 0 && (ahi_s[c] < 0 || h > hi_s[c] || (h == hi_s[c] && ah < ahi_s[c]))) { hi_s[c] = h; ahi_s[c] = ah; }
+        if (al >= 0 && (alo_s[c] < 0 || l < lo_s[c] || (l == lo_s[c] && al < alo_s[c]))) { lo_s[c] = l; alo_s[c] = al; }
+    };
     for (int w = 0; w < PREP_WARPS; ++w) {
         if (warp == w) {
 #pragma unroll
-            for (int j = 0; j < PREP_MAXJ; ++j) {
-                const int c = lane + 32 * j;
-                if (w == 0) { hi_s[c] = hi[j]; ahi_s[c] = ahi[j]; lo_s[c] = lo[j]; alo_s[c] = alo[j]; }
-                else {
-                    if (ahi[j] >= 0 && (ahi_s[c] < 0 || hi[j] > hi_s[c] || (hi[j] == hi_s[c] && ahi[j] < ahi_s[c]))) { hi_s[c] = hi[j]; ahi_s[c] = ahi[j]; }
-                    if (alo[j] >= 0 && (alo_s[c] < 0 || lo[j] < lo_s[c] || (lo[j] == lo_s[c] && alo[j] < alo_s[c]))) { lo_s[c] = lo[j]; alo_s[c] = alo[j]; }
-                }
-            }
+            for (int j = 0; j < PREP_MAXJ; ++j) merge(lane + 32 * j, hi[j], ahi[j], lo[j], alo[j], w == 0);
         }
         __syncthreads();
     }
+    // the block's extrema go to the cloud's scratch rows; the block that finishes last merges them (its ticket says so)
+    float *sc_v = a.scratch + ((size_t)b * S + blockIdx.x) * 2 * C;
+    int *sc_i = a.scratch_arg + ((size_t)b * S + blockIdx.x) * 2 * C;
+    for (int c = threadIdx.x; c < C; c += PREP_THREADS) {
+        sc_v[c] = hi_s[c]; sc_v[C + c] = lo_s[c]; sc_i[c] = ahi_s[c]; sc_i[C + c] = alo_s[c];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket_s = atomicAdd(a.tickets + b, 1u);
+    __syncthreads();
+    if (ticket_s != (unsigned)(S - 1)) return;
+    __threadfence();
+    if (threadIdx.x == 0) a.tickets[b] = 0u;            // ready for the next launch
+    for (int c = threadIdx.x; c < C; c += PREP_THREADS) {
+        for (int s2 = 0; s2 < S; ++s2) {
+            const float *pv = a.scratch + ((size_t)b * S + s2) * 2 * C;
+            const int *pa = a.scratch_arg + ((size_t)b * S + s2) * 2 * C;
+            merge(c, __ldcg(pv + c), __ldcg(pa + c), __ldcg(pv + C + c), __ldcg(pa + C + c), s2 == 0);
+        }
+    }
+    __syncthreads();
     const bool any_valid = ahi_s[0] >= 0;      // a valid point sets every channel
     for (int c = threadIdx.x; c < C; c += PREP_THREADS) {
         a.hi[(size_t)b * C + c] = any_valid ? hi_s[c] : 0.f;
@@ -385,11 +409,11 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_fwd_kernel(const Prep
         a.arg_hi[(size_t)b * C + c] = any_valid ? ahi_s[c] : -1;
         a.arg_lo[(size_t)b * C + c] = any_valid ? alo_s[c] : -1;
     }
-    // maxc = max over the valid points of pi[n,c] * qi[k,c] (-1e10 for a cloud without valid points): the rows of qi this
-    // block wrote above are visible to it after the barrier
+    // maxc = max over the valid points of pi[n,c] * qi[k,c] (-1e10 for a cloud without valid points); the pixel rows were
+    // written by all blocks of the cloud: read them past L1
     for (int e = threadIdx.x; e < N2 * C; e += PREP_THREADS) {
         const int c = e % C;
-        const float q = a.qi[(size_t)b * N2 * C + e];
+        const float q = __ldcg(a.qi + (size_t)b * N2 * C + e);
         a.maxc[(size_t)b * N2 * C + e] = any_valid ? (q > 0.f ? q * hi_s[c] : q * lo_s[c]) : -1e10f;
     }
 }
@@ -422,13 +446,14 @@ __device__ __forceinline__ void standardise_row_bwd(float (&g)[PREP_MAXJ], const
 
 __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_bwd_kernel(const PrepBwdArgs a) {
     __shared__ float dhi_s[32 * PREP_MAXJ], dlo_s[32 * PREP_MAXJ];
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, S = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = a.N, N2 = a.N2, C = a.C;
     const bool use_max = a.has_max && a.d_maxc != nullptr && a.arg_hi[(size_t)b * C] >= 0;
     for (int c = threadIdx.x; c < 32 * PREP_MAXJ; c += PREP_THREADS) dhi_s[c] = dlo_s[c] = 0.f;
     __syncthreads();
     if (use_max) {
-        // d hi[c] = sum over the pixels with qi > 0 of d maxc * qi, d lo[c] over the others
+        // d hi[c] = sum over the pixels with qi > 0 of d maxc * qi, d lo[c] over the others (every block of the cloud
+        // computes them: N2 rows, cheaper than a second kernel)
         float dh[PREP_MAXJ], dl[PREP_MAXJ];
 #pragma unroll
         for (int j = 0; j < PREP_MAXJ; ++j) dh[j] = dl[j] = 0.f;
@@ -447,7 +472,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_bwd_kernel(const Prep
         for (int j = 0; j < PREP_MAXJ; ++j) { atomicAdd(&dhi_s[lane + 32 * j], dh[j]); atomicAdd(&dlo_s[lane + 32 * j], dl[j]); }
     }
     __syncthreads();
-    for (int r = warp; r < N + N2; r += PREP_WARPS) {
+    for (int r = blockIdx.x * PREP_WARPS + warp; r < N + N2; r += S * PREP_WARPS) {
         const bool point = r < N;
         const size_t row = point ? (size_t)b * N + r : (size_t)b * N2 + (r - N);
         const float *ysrc = (point ? a.pi : a.qi) + row * C;
@@ -582,16 +607,33 @@ int i2p_softmax_wsum_bwd(long long groups, int K, int C, const float *logit, con
                                                                                                  gout, dlogit, dvalue);
     return check_launch("softmax_wsum_bwd");
 }
+// blocks per cloud: enough that a warp sees two or three rows (the kernels are latency-bound chains of row reductions)
+static int prep_blocks(int rows) {
+    const int s = i2p::ceil_div(rows, 2 * i2p::PREP_WARPS);
+    return s < 1 ? 1 : (s > 16 ? 16 : s);
+}
+
+int i2p_cv_prep_scratch_floats(int B, int N, int N2, int C) {
+    /* per-block extrema (value + index) and one ticket per cloud, in 4-byte words */
+    return B * prep_blocks(N + N2) * 4 * C + B;
+}
+
 int i2p_cv_prep_fwd(int B, int N, int N2, int C, int has_max, const float *uv, const float *z, const float *pf, const float *qf,
                     float *xyz, float *pi, float *qi, float *den_p, float *den_q, float *maxc, float *hi, float *lo, int32_t *arg_hi,
-                    int32_t *arg_lo, void *stream) {
+                    int32_t *arg_lo, float *scratch, void *stream) {
     using namespace i2p;
     I2P_REQUIRE(B >= 0 && N >= 1 && N2 >= 1 && C >= 2 && C <= 32 * PREP_MAXJ && B <= 65535, "cv_prep: bad sizes (2 <= C <= 256)");
-    I2P_REQUIRE(!has_max || (maxc != nullptr && hi != nullptr && lo != nullptr && arg_hi != nullptr && arg_lo != nullptr),
+    I2P_REQUIRE(!has_max || (maxc != nullptr && hi != nullptr && lo != nullptr && arg_hi != nullptr && arg_lo != nullptr && scratch != nullptr),
                 "cv_prep: outputs of the backward-validation channel missing");
     if (B == 0) return I2P_OK;
-    PrepArgs a{N, N2, C, has_max ? 1 : 0, uv, z, pf, qf, xyz, pi, qi, den_p, den_q, maxc, hi, lo, arg_hi, arg_lo};
-    cv_prep_fwd_kernel<<<B, PREP_THREADS, 0, as_stream(stream)>>>(a);
+    const int S = prep_blocks(N + N2);
+    PrepArgs a{N, N2, C, has_max ? 1 : 0, uv, z, pf, qf, xyz, pi, qi, den_p, den_q, maxc, hi, lo, arg_hi, arg_lo, nullptr, nullptr, nullptr};
+    if (has_max) {
+        a.scratch = scratch;
+        a.scratch_arg = reinterpret_cast<int *>(scratch) + (size_t)B * S * 2 * C;
+        a.tickets = reinterpret_cast<unsigned *>(scratch) + (size_t)B * S * 4 * C;
+    }
+    cv_prep_fwd_kernel<<<dim3(S, B), PREP_THREADS, 0, as_stream(stream)>>>(a);
     return check_launch("cv_prep_fwd");
 }
 
@@ -603,7 +645,7 @@ int i2p_cv_prep_bwd(int B, int N, int N2, int C, int has_max, const float *uv, c
     I2P_REQUIRE(B >= 0 && N >= 1 && N2 >= 1 && C >= 2 && C <= 32 * PREP_MAXJ && B <= 65535, "cv_prep_bwd: bad sizes (2 <= C <= 256)");
     if (B == 0) return I2P_OK;
     PrepBwdArgs a{N, N2, C, has_max ? 1 : 0, uv, z, pi, qi, den_p, den_q, hi, lo, arg_hi, arg_lo, d_xyz, d_pi, d_qi, d_maxc, d_uv, d_z, d_pf, d_qf};
-    cv_prep_bwd_kernel<<<B, PREP_THREADS, 0, as_stream(stream)>>>(a);
+    cv_prep_bwd_kernel<<<dim3(prep_blocks(N + N2), B), PREP_THREADS, 0, as_stream(stream)>>>(a);
     return check_launch("cv_prep_bwd");
 }
 

@@ -183,8 +183,7 @@ class RegNet_v2(nn.Module):
         -> out_3 (B,7), attention weights, q3, t3"""
         B, n3 = s["B"], s["H3W3"]
         P3_l4, LF3_cv = s["P3_l4"], s["LF3_cv"]
-        zero = torch.zeros((B, 1), device=P3_l4.device)
-        P3_warped = warp_utils.warp_quat_xyz(P3_l4, q_in, torch.cat([zero, t_in], -1)) * check_valid(P3_l4)
+        P3_warped = warp_utils.rigid_warp(P3_l4, q_in, t_in, mask_invalid=True)      # warp_quat_xyz(...) * check_valid(P3_l4)
         lidar_z = P3_warped[:, :, 2:]
         lidar_uv = P3_warped / (lidar_z + 1e-10)
         concat_3 = self.cost_volume2(s["P3_raw"], lidar_uv, LF3_cv, s["l3_grid"], s["RF3_index"], s["RF3"], lidar_z, cfg=cfg)
@@ -198,10 +197,8 @@ class RegNet_v2(nn.Module):
         q3, t3, W_l3 = self.l3_head(l3_predict, l3_w, P3_warped, LF3_cv, None)
 
         q = warp_utils.mul_q(q3.view(B, 1, 4), q_in.view(B, 1, 4)).squeeze(1)
-        tq_in = torch.cat([zero, t_in], 1).view(B, 1, 4)
-        t3q = torch.cat([zero, t3], 1).view(B, 1, 4)
-        t = (warp_utils.mul_q(warp_utils.mul_q(q3, tq_in), warp_utils.inv_q(q3)) + t3q).squeeze(1)
-        return torch.cat([q, t[:, 1:]], 1), W_l3, q3, t3
+        t = warp_utils.rigid_warp(t_in.view(B, 1, 3), q3, t3).view(B, 3)             # t = R(q3) t_in + t3  (:414-421)
+        return torch.cat([q, t], 1), W_l3, q3, t3
 
     def set_bn(self):
         for name in ("flow_predictor0", "flow_predictor0_w", "flow_predictor0_predict", "LiDAR_lv1", "LiDAR_lv2",

@@ -43,6 +43,53 @@ class _QuatMul(Function):
         return da, db
 
 
+class _QuatWarp(Function):
+    """out = (q (x) [0, p] (x) q^-1)[1:4] + t [, zero where p is all-zero]: csrc/quat.cu quat_warp, one launch per direction.
+    p (B,N,3), q (B,4), t (B,3), f32 CUDA."""
+
+    @staticmethod
+    def forward(ctx, p, q, t, mask_invalid):
+        from .. import _cabi
+        f32 = torch.float32
+        p, q, t = p.contiguous(), q.contiguous(), t.contiguous()
+        if q.data_ptr() % 16:
+            q = q.clone()
+        B, N = p.shape[0], p.shape[1]
+        out = torch.empty(B, N, 3, dtype=f32, device=p.device)
+        _cabi.call("i2p_quat_warp_fwd", p.device, B, N, int(mask_invalid), _cabi._ptr(p, f32, "points"), _cabi._ptr(q, f32, "quaternion", p.device),
+                   _cabi._ptr(t, f32, "translation", p.device), out.data_ptr())
+        ctx.save_for_backward(p, q)
+        ctx.mask_invalid = bool(mask_invalid)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .. import _cabi
+        p, q = ctx.saved_tensors
+        f32, dev = torch.float32, p.device
+        B, N = p.shape[0], p.shape[1]
+        g = g.contiguous()
+        need_p, need_q, need_t = ctx.needs_input_grad[:3]
+        dp = torch.empty_like(p) if need_p else None
+        dq = torch.empty(B, 4, dtype=f32, device=dev) if need_q else None
+        dt = torch.empty(B, 3, dtype=f32, device=dev) if need_t else None
+        _cabi.call("i2p_quat_warp_bwd", dev, B, N, int(ctx.mask_invalid), p.data_ptr(), q.data_ptr(), _cabi._ptr(g, f32, "gradient", dev),
+                   dp.data_ptr() if need_p else None, dq.data_ptr() if need_q else None, dt.data_ptr() if need_t else None)
+        return dp, dq, dt, None
+
+
+def rigid_warp(xyz, quat, trans, mask_invalid=False):
+    """xyz (B,N,3), quat (B,4), trans (B,3) -> q [0,p] q^-1 + t, (B,N,3); mask_invalid: all-zero points (empty range-image
+    cells) stay zero, the `* check_valid(xyz)` the reference applies after the warp (src/modellearn_proj_center.py:334).
+    One kernel on the device, the reference's mul_q / inv_q composition elsewhere."""
+    B, N, _ = xyz.shape
+    quat, trans = quat.reshape(B, 4), trans.reshape(B, 3)
+    if USE_FUSED_QUAT and xyz.is_cuda and xyz.dtype == torch.float32 and quat.dtype == torch.float32 and trans.dtype == torch.float32:
+        return _QuatWarp.apply(xyz, quat, trans, mask_invalid)
+    out = warp_quat_xyz(xyz, quat, torch.cat([trans.new_zeros(B, 1), trans], -1))
+    return out * torch.any(torch.ne(xyz, 0), dim=-1, keepdim=True).float() if mask_invalid else out
+
+
 def inv_q(q):
     """q (B,1,4) or (B,4) -> conj(q) / (|q|^2 + 1e-10), (B,4)"""
     q = q.reshape(q.shape[0], 4)

@@ -318,6 +318,21 @@ class _CvBuild(torch.autograd.Function):
         return dxyz1, dxyz2, dpi, dqi, dmaxc, None
 
 
+_PREP_SCRATCH = {}
+
+
+def _prep_scratch(dev, B, N, N2, C):
+    """Work space of cv_prep's cross-block reduction: per-block extrema and one ticket per cloud that the kernel itself
+    leaves at zero -- so one zero-filled buffer per (stream, sizes) serves every launch (launches on one stream are
+    ordered; different streams get different buffers)."""
+    from .. import _cabi
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, B, N, N2, C)
+    buf = _PREP_SCRATCH.get(key)
+    if buf is None:
+        buf = _PREP_SCRATCH[key] = torch.zeros(_cabi.lib().i2p_cv_prep_scratch_floats(B, N, N2, C), dtype=torch.float32, device=dev)
+    return buf
+
+
 class _CvPrep(torch.autograd.Function):
     """Operand preparation of the cost volume as one kernel per direction (csrc/cv.cu cv_prep): depth restoration
     xyz = uv * z, the row-wise standardisation of the point and pixel features and, for the backward-validation channel,
@@ -342,11 +357,12 @@ class _CvPrep(torch.autograd.Function):
         else:
             maxc = ext = arg = None
         P = lambda x, n: _cabi._ptr(x, f32, n, dev)
+        scratch = _prep_scratch(dev, B, N, N2, C) if has_max else None
         _cabi.call("i2p_cv_prep_fwd", dev, B, N, N2, C, int(has_max), P(uv, "warped_xyz"), P(z, "lidar_z"), P(pf, "warped_points"),
                    P(qf, "f2_points"), xyz.data_ptr(), pi.data_ptr(), qi.data_ptr(), den_p.data_ptr(), den_q.data_ptr(),
                    maxc.data_ptr() if has_max else None, ext[0].data_ptr() if has_max else None,
                    ext[1].data_ptr() if has_max else None, arg[0].data_ptr() if has_max else None,
-                   arg[1].data_ptr() if has_max else None)
+                   arg[1].data_ptr() if has_max else None, scratch.data_ptr() if has_max else None)
         empty = torch.empty(0, device=dev)
         ctx.save_for_backward(uv, z, pi, qi, den, ext if has_max else empty, arg if has_max else empty)
         ctx.meta = (B, N, N2, C, bool(has_max))

@@ -260,7 +260,10 @@ int i2p_softmax_wsum_bwd(long long groups, int K, int C, const float *logit, con
  * (-1e10 without valid points) = max over the valid points of pi[n,c] qi[k,c], the backward-validation channel. */
 int i2p_cv_prep_fwd(int B, int N, int N2, int C, int has_max, const float *uv, const float *z, const float *pf, const float *qf,
                     float *xyz, float *pi, float *qi, float *den_p, float *den_q, float *maxc, float *hi, float *lo, int32_t *arg_hi,
-                    int32_t *arg_lo, void *stream);
+                    int32_t *arg_lo, float *scratch, void *stream);
+/* has_max: `scratch` = i2p_cv_prep_scratch_floats() 4-byte words whose LAST B words (the clouds' tickets) are zero before the
+ * first launch; the kernel leaves them zero, so one buffer zeroed once serves every later launch of these sizes on a stream. */
+int i2p_cv_prep_scratch_floats(int B, int N, int N2, int C);
 /* d_xyz (B,N,3), d_pi (B,N,C), d_qi, d_maxc (B,N2,C), each or NULL -> d_uv (B,N,3), d_z (B,N), d_pf (B,N,C), d_qf (B,N2,C) */
 int i2p_cv_prep_bwd(int B, int N, int N2, int C, int has_max, const float *uv, const float *z, const float *pi, const float *qi,
                     const float *den_p, const float *den_q, const float *hi, const float *lo, const int32_t *arg_hi,
@@ -276,6 +279,14 @@ int i2p_pixel_rays(int B, int h, int w, float sx, float sy, const float *intrins
  * either operand optionally conjugated (the backward pass is da = dc (x) conj(b), db = conj(a) (x) dc). */
 int i2p_quat_mul(int B, int N, int na, int nb, int conj_a, int conj_b, const float *a, const float *b, float *out,
                  void *stream);
+/* Rigid warp of a point set by a pose, warp_quat_xyz (src/modules/warp_utils.py:78-94) and the pose composition
+ * t = R(q3) t_in + t3 (src/modellearn_proj_center.py:414-421) as one launch per direction:
+ * out (B,N,3) = (q (x) [0, p] (x) q^-1)[1:4] + t, q^-1 = conj(q) / (|q|^2 + 1e-10); p (B,N,3), q (B,4), t (B,3).
+ * mask_invalid: all-zero points stay zero (the reference multiplies by check_valid afterwards).
+ * Backward: g (B,N,3) -> dp (B,N,3), dq (B,4), dt (B,3), each or NULL. */
+int i2p_quat_warp_fwd(int B, int N, int mask_invalid, const float *p, const float *q, const float *t, float *out, void *stream);
+int i2p_quat_warp_bwd(int B, int N, int mask_invalid, const float *p, const float *q, const float *g, float *dp, float *dq,
+                      float *dt, void *stream);
 
 /* ---- 3x3 convolutions of the RGB feature pyramid (src/modules/basicConv.py:6-20; replaces the library convolution
  * behind nn.Conv2d(k = 3, stride 1, padding 1) forward, its data gradient and its weight gradient) -------------------
