@@ -17,7 +17,7 @@ clip 10, train...proj.py:198-205,481).
 import torch
 import torch.distributed as dist
 
-from . import _cabi, streams
+from . import _cabi, scratch, streams
 from .compute_loss import Get_loss
 from .config_proj_lidarcenter import I2PNetConfig
 from .modellearn_proj_center import RegNet_v2
@@ -248,6 +248,13 @@ class TrainStep:
     def _step_body(self):
         x = self.inputs
         self.bucket.begin_step()
+        scratch.begin_step(self.device)          # the step's zero-initialised work space: one memset (scratch.py)
+        try:
+            self._forward_backward(x)
+        finally:
+            scratch.end_step()
+
+    def _forward_backward(self, x):
         out3, out4, _, _, sx, sq = self.model(x["rgb"], x["lidar"], x["raw_point_xyz"], None, x["intrinsic"], None,
                                               None, None, x["lidar_feats"], self.cfg)
         loss, _, _ = Get_loss(out3, out4, x["q_gt"], x["t_gt"], sx, sq, self.cfg)

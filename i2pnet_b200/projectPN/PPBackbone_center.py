@@ -302,7 +302,8 @@ class _CvBuild(torch.autograd.Function):
         dxyz6 = dxyz6.contiguous() if dxyz6 is not None else None
         # five accumulators carved out of one zero-filled buffer (a single fill launch)
         sizes = [B * N * 3, B * N * C, B * N2 * 3, B * N2 * C, B * N2 * C if has_max else 0]
-        flat = torch.zeros(sum(sizes), dtype=f32, device=dev)
+        from .. import scratch
+        flat = scratch.zeros(sum(sizes), f32, dev)
         offs = [0]
         for n_ in sizes:
             offs.append(offs[-1] + n_)

@@ -94,6 +94,7 @@ class FusedMLPFunction(Function):
         ctx.save_for_backward(x, *params, *ys, *stats, *([arg] if arg is not None else []))
         ctx.meta = (L, reduce_k, tuple(slopes))
         ctx.weights = [params[4 * l] for l in range(L)]      # the Parameter objects (their gradient sinks, engine.grad_sink)
+        ctx.biases = [params[4 * l + 1] for l in range(L)]
         ctx.packs = packs     # the weights do not change between forward and backward
         return out
 
@@ -110,19 +111,26 @@ class FusedMLPFunction(Function):
         # one zero-filled f64 buffer for every layer's batch-norm sums and one f32 buffer for every dW and
         # (identically zero) bias gradient: two fill launches per chain instead of three per layer
         couts = [ys[l].shape[1] for l in range(L)]
-        s12_all = torch.zeros(2 * sum(couts), dtype=f64, device=dev)
-        wsizes = [params[4 * l].numel() for l in range(L)]
-        wz = torch.zeros(sum(wsizes) + sum(couts), dtype=f32, device=dev)
+        from .. import scratch
+        from ..engine import grad_sink
+        s12_all = scratch.zeros(2 * sum(couts), f64, dev)
+        # weights / biases with a gradient sink (step engine) need no buffer of their own: dW accumulates into the sink, the
+        # bias gradient under a batch-norm is identically zero and the sink already holds zero
+        w_sinks = [grad_sink(ctx.weights[l]) for l in range(L)]
+        b_sunk = [grad_sink(ctx.biases[l]) is not None for l in range(L)]
+        wsizes = [0 if w_sinks[l] is not None else params[4 * l].numel() for l in range(L)]
+        bsizes = [0 if b_sunk[l] else couts[l] for l in range(L)]
+        wz = scratch.zeros(sum(wsizes) + sum(bsizes), f32, dev) if sum(wsizes) + sum(bsizes) else None
         s12, dws, dbs = [], [], []
         o12 = ow = 0
         for l in range(L):
             s12.append(s12_all[o12:o12 + 2 * couts[l]].view(2, couts[l]))
             o12 += 2 * couts[l]
-            dws.append(wz[ow:ow + wsizes[l]].view(params[4 * l].shape))
+            dws.append(wz[ow:ow + wsizes[l]].view(params[4 * l].shape) if wsizes[l] else None)
             ow += wsizes[l]
         for l in range(L):
-            dbs.append(wz[ow:ow + couts[l]])
-            ow += couts[l]
+            dbs.append(wz[ow:ow + bsizes[l]] if bsizes[l] else None)
+            ow += bsizes[l]
 
         def src(l, g):  # (g_dense, dout, arg, k) of layer l
             if l == L - 1 and reduce_k:
@@ -145,7 +153,6 @@ class FusedMLPFunction(Function):
         grads = [None] * (4 * L)
         dx = None
         from .. import streams as _streams
-        from ..engine import grad_sink
         for l in range(L - 1, -1, -1):
             w = params[4 * l]
             cout, cin = w.shape[0], w.shape[1]
@@ -158,7 +165,7 @@ class FusedMLPFunction(Function):
             # The weight gradient is needed by the optimiser alone, the data gradient by the rest of the backward pass:
             # dW goes to a side stream (it reads what dX reads), and under a step engine it accumulates straight into
             # the flat gradient buffer and stays un-joined until the whole backward has been issued (streams.defer_or_join).
-            sink = grad_sink(ctx.weights[l])
+            sink = w_sinks[l]
             dw_target = sink if sink is not None else dws[l]
             with _streams.Fork(grad_out, g if g is not None else grad_out, ys[l], stats[l], s12_all, inp,
                                *([pst] if pst is not None else []), *([arg] if arg is not None else []), kind="wgrad") as branch:

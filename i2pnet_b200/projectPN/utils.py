@@ -140,7 +140,8 @@ class GatherRows(Function):
     def backward(ctx, grad_out):
         (flat_idx,) = ctx.saved_tensors
         B, M, C = grad_out.shape
-        grad = torch.zeros(B, ctx.hw, C, device=grad_out.device, dtype=torch.float32)
+        from .. import scratch
+        grad = scratch.zeros((B, ctx.hw, C), torch.float32, grad_out.device)
         _cabi.gather_rows_grad(B, ctx.hw, C, M, grad_out.contiguous(), flat_idx, grad)
         return grad, None
 
