@@ -53,6 +53,7 @@ _SIGNATURES = {
     "i2p_bn_bwd_reduce": [_ll, _int, _vp, _vp, _vp, _int] + [_vp] * 5 + [_flt, _vp, _vp],
     "i2p_pw_linear_bwd_dx": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 3 + [_vp] * 5 + [_flt, _vp, _vp],
     "i2p_pw_pack_weights": [_int, _int, _vp, _vp, _vp],
+    "i2p_pw_pack_weights_multi": [_int, _vp, _vp],
     "i2p_pw_linear_fwd_tc": [_int] * 3 + [_vp] * 3 + [_flt] + [_vp] * 5,
     "i2p_pw_linear_bwd_dx_tc": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 3 + [_vp] * 5 + [_flt, _vp, _vp],
     "i2p_pw_linear_bwd_dw_tc": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 4 + [_flt, _vp, _vp],

@@ -100,11 +100,11 @@ __host__ __device__ inline PackGeom pack_geom(int cin, int cout) {
 
 // layout 0: no-swizzle canonical order ((k / 4) * bn + n) * 4 + k % 4; layout 1: SWIZZLE_128B atoms of 8 rows x 128 B
 // (row n of the tile holds its 32 k contiguously, the 16-byte chunk index XORed with n % 8)
-__global__ void __launch_bounds__(256) pack_weights_kernel(int cin, int cout, int layout, const float *__restrict__ w,
-                                                           float *__restrict__ pack) {
+__device__ __forceinline__ void pack_weights_body(int cin, int cout, int layout, const float *__restrict__ w, float *__restrict__ pack,
+                                                  int block, int nblocks) {
     const PackGeom g = pack_geom(cin, cout);
     const long long half_f = g.floats_f / 2, half_x = g.floats_x / 2;
-    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < half_f + half_x; e += (long long)gridDim.x * 256) {
+    for (long long e = (long long)block * 256 + threadIdx.x; e < half_f + half_x; e += (long long)nblocks * 256) {
         const bool fwd = e < half_f;
         const long long q = fwd ? e : e - half_f;
         const int bn = fwd ? g.bn_f : g.bn_x, nc = fwd ? g.nc_f : g.nc_x;
@@ -131,6 +131,20 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(int cin, int cout, in
         base[r] = __uint_as_float(hi);
         base[per + r] = __uint_as_float(lo);
     }
+}
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(int cin, int cout, int layout, const float *__restrict__ w,
+                                                           float *__restrict__ pack) {
+    pack_weights_body(cin, cout, layout, w, pack, blockIdx.x, gridDim.x);
+}
+
+// Every layer of a model in one launch: table[l] = { cin | cout << 32, weight pointer, pack pointer }, blockIdx.y = layer.
+// (The weights change once per optimiser step; packing them layer by layer inside the forward pass put ~40 launches on
+// the serial chain of the step.)
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(int layout, const long long *__restrict__ table) {
+    const long long *t = table + (size_t)blockIdx.y * 3;
+    const int cin = (int)(t[0] & 0xffffffffll), cout = (int)(t[0] >> 32);
+    pack_weights_body(cin, cout, layout, reinterpret_cast<const float *>(t[1]), reinterpret_cast<float *>(t[2]), blockIdx.x, gridDim.x);
 }
 
 // instruction descriptor, kind::tf32, f32 accumulate, M = 128; a_mn / b_mn: the operand is MN-major
@@ -861,6 +875,14 @@ int i2p_pw_pack_weights(int cin, int cout, const float *w, float *pack, void *st
     const long long blocks = (total + 255) / 256;
     tc::pack_weights_kernel<<<(int)(blocks < 592 ? blocks : 592), 256, 0, as_stream(stream)>>>(cin, cout, tc::swizzled() ? 1 : 0, w, pack);
     return check_launch("pw_pack_weights");
+}
+
+int i2p_pw_pack_weights_multi(int n, const long long *table, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(n >= 0 && n <= 65535 && (n == 0 || table != nullptr), "pw_pack_weights_multi: bad table");
+    if (n == 0) return I2P_OK;
+    tc::pack_weights_multi_kernel<<<dim3(16, n), 256, 0, as_stream(stream)>>>(tc::swizzled() ? 1 : 0, table);
+    return check_launch("pw_pack_weights_multi");
 }
 
 int i2p_pw_linear_fwd_tc(int rows, int cin, int cout, const float *x, const float *in_scale, const float *in_shift,

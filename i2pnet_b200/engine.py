@@ -21,6 +21,7 @@ from . import _cabi, scratch, streams
 from .compute_loss import Get_loss
 from .config_proj_lidarcenter import I2PNetConfig
 from .modellearn_proj_center import RegNet_v2
+from .projectPN import fused_mlp
 
 INPUT_KEYS = ("rgb", "lidar", "raw_point_xyz", "lidar_feats", "intrinsic", "q_gt", "t_gt")
 
@@ -249,10 +250,12 @@ class TrainStep:
         x = self.inputs
         self.bucket.begin_step()
         scratch.begin_step(self.device)          # the step's zero-initialised work space: one memset (scratch.py)
+        fused_mlp.packs_begin_step(self.device)  # tensor-core copies of every shared-MLP weight: one launch (fused_mlp.py)
         try:
             self._forward_backward(x)
         finally:
             scratch.end_step()
+            fused_mlp.packs_end_step()
 
     def _forward_backward(self, x):
         out3, out4, _, _, sx, sq = self.model(x["rgb"], x["lidar"], x["raw_point_xyz"], None, x["intrinsic"], None,

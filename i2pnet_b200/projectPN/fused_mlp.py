@@ -10,6 +10,8 @@ backward (see mlp.cu for the algebra).  Numerically it is the same f32 computati
 (merged Welford) batch statistics; the bias feeding a BatchNorm gets an exactly zero gradient
 instead of autograd's rounding noise.
 """
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -21,6 +23,83 @@ f64 = torch.float64
 
 def _p(t):
     return None if t is None else t.data_ptr()
+
+
+class _PackRegistry:
+    """Packed (tf32 hi / lo, UMMA layout) copies of the shared-MLP weights under a step engine.  The weights change once
+    per optimiser step, so the engine packs every registered layer in ONE launch at the start of the step
+    (`packs_begin_step`) instead of one launch per layer inside the forward chain; layers are registered the first time a
+    forward pass meets them (the eager warm-up steps).  Without an engine every forward packs its own copy, as before."""
+
+    def __init__(self, device):
+        self.device, self.entries, self.table, self.dirty, self.active, self.packed = device, {}, None, False, False, False
+
+    def begin_step(self):
+        self.active, self.packed = True, False
+        dead = [k for k, e in self.entries.items() if e["ref"]() is None]      # layers of models that are gone
+        for k in dead:
+            del self.entries[k]
+            self.dirty = True
+        if not self.entries:
+            self.table = None
+            return
+        if (self.table is None or self.dirty) and not torch.cuda.is_current_stream_capturing():
+            rows = []
+            for e in self.entries.values():
+                e["ptr"] = e["ref"]().data_ptr()
+                rows.append([e["cin"] | (e["cout"] << 32), e["ptr"], e["pack"].data_ptr()])
+            self.table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+            self.n_table = len(rows)
+            for e in self.entries.values():
+                e["in_table"] = True
+            self.dirty = False
+        if self.table is not None and not self.dirty:
+            call("i2p_pw_pack_weights_multi", self.device, self.n_table, self.table.data_ptr())
+            self.packed = True
+
+    def get(self, w, cin, cout):
+        """-> (pack tensor, already packed this step)"""
+        e = self.entries.get(id(w))
+        if e is not None and e["ref"]() is not w:       # the id of a dead parameter, reused
+            e = None
+        if e is None:
+            pack = torch.empty(_cabi.lib().i2p_pw_pack_floats(cin, cout), dtype=f32, device=self.device)
+            e = self.entries[id(w)] = dict(ref=weakref.ref(w), cin=cin, cout=cout, pack=pack, ptr=None, in_table=False)
+            self.dirty = True
+        ready = self.packed and e["in_table"] and e["ptr"] == w.data_ptr()
+        if not ready and e["in_table"] and e["ptr"] != w.data_ptr():
+            self.dirty = True              # the parameter was re-seated: rebuild the table at the next step
+        return e["pack"], ready
+
+
+_REGISTRIES = {}
+
+
+def packs_begin_step(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        return
+    reg = _REGISTRIES.get(device.index)
+    if reg is None:
+        reg = _REGISTRIES[device.index] = _PackRegistry(device)
+    reg.begin_step()
+
+
+def packs_end_step():
+    for reg in _REGISTRIES.values():
+        reg.active = False
+
+
+def _weight_pack(w, cin, cout, dev):
+    reg = _REGISTRIES.get(dev.index)
+    if reg is not None and reg.active:
+        pack, ready = reg.get(w, cin, cout)
+        if not ready:
+            call("i2p_pw_pack_weights", dev, cin, cout, _ptr(w, f32, "weight", dev), pack.data_ptr())
+        return pack
+    pack = torch.empty(_cabi.lib().i2p_pw_pack_floats(cin, cout), dtype=f32, device=dev)
+    call("i2p_pw_pack_weights", dev, cin, cout, _ptr(w, f32, "weight", dev), pack.data_ptr())
+    return pack
 
 
 class FusedMLPFunction(Function):
@@ -47,8 +126,7 @@ class FusedMLPFunction(Function):
             dx_tc = bool(tc_mask & 2) and lib.i2p_pw_tc_supported(1, rows, cin, cout)
             pack = None
             if fwd_tc or dx_tc:   # tf32 (hi, lo) halves of W in the UMMA layout, both orientations, once per step
-                pack = torch.empty(lib.i2p_pw_pack_floats(cin, cout), dtype=f32, device=dev)
-                call("i2p_pw_pack_weights", dev, cin, cout, _ptr(w, f32, "weight", dev), pack.data_ptr())
+                pack = _weight_pack(w, cin, cout, dev)
             scale_p = _p(in_stats[2]) if in_stats is not None else None
             shift_p = _p(in_stats[3]) if in_stats is not None else None
             if fwd_tc:

@@ -191,6 +191,9 @@ int i2p_pw_linear_bwd_dw(int rows, int cin, int cout, const float *g_dense, cons
 int i2p_pw_tc_supported(int kind, int rows, int cin, int cout);
 long long i2p_pw_pack_floats(int cin, int cout);
 int i2p_pw_pack_weights(int cin, int cout, const float *w, float *pack, void *stream);
+/* The same for n layers in one launch: table (n, 3) int64 on the device, row l = { cin | cout << 32, weight pointer,
+ * pack pointer } (the pointers as integers).  A step engine packs every layer once per optimiser step this way. */
+int i2p_pw_pack_weights_multi(int n, const long long *table, void *stream);
 int i2p_pw_linear_fwd_tc(int rows, int cin, int cout, const float *x, const float *in_scale, const float *in_shift,
                          float in_slope, const float *wpack, const float *bias, float *y, float *tile_stats, void *stream);
 int i2p_pw_linear_bwd_dx_tc(int rows, int cin, int cout, const float *g_dense, const float *dout, const int32_t *arg, int k,
