@@ -79,6 +79,7 @@ _SIGNATURES = {
     "i2p_pose_loss_fwd": [_int, _int] + [_vp] * 8,
     "i2p_pose_loss_bwd": [_int, _int] + [_vp] * 12,
     "i2p_conv3x3_pack": [_int, _int, _int, _vp, _vp, _vp],
+    "i2p_conv3x3_pack_multi": [_int, _vp, _vp],
     "i2p_conv3x3_tc": [_int] * 5 + [_vp] * 6,
     "i2p_conv3x3_wgrad": [_int] * 5 + [_vp] * 4,
     "i2p_pw_linear_bwd_dw": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 4 + [_flt, _vp, _vp],

@@ -44,13 +44,13 @@ __host__ __device__ inline long long block_floats(int ki, int no) { return 2LL *
 
 // W (no_src..): forward  pack[n = co][k = ci][tap] = w[co][ci][tap]            (w is (cout, cin, 3, 3))
 //               dgrad    pack[n = ci][k = co][tap] = w[co][ci][8 - tap]
-__global__ void __launch_bounds__(256) pack_kernel(int cin, int cout, int dgrad, const float *__restrict__ w,
-                                                   float *__restrict__ pack) {
+__device__ __forceinline__ void pack_body(int cin, int cout, int dgrad, const float *__restrict__ w, float *__restrict__ pack, int block,
+                                          int nblocks) {
     const int ki = dgrad ? cout : cin, no = dgrad ? cin : cout;
     const int ck = ck_of(ki), bn = bn_of(no), kgs = ck / 4;
     const int nch = chunks_of(ki), nt = ntiles_of(no);
     const long long half = 9LL * kgs * bn * 4, total = (long long)nt * nch * half;
-    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    for (long long e = (long long)block * 256 + threadIdx.x; e < total; e += (long long)nblocks * 256) {
         const long long blk = e / half;
         int r = (int)(e - blk * half);
         const int t = (int)(blk / nch), c = (int)(blk - (long long)t * nch);
@@ -68,6 +68,18 @@ __global__ void __launch_bounds__(256) pack_kernel(int cin, int cout, int dgrad,
         base[nl * 4 + el] = __uint_as_float(hi);
         base[(bn + nl) * 4 + el] = __uint_as_float(lo);
     }
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(int cin, int cout, int dgrad, const float *__restrict__ w,
+                                                   float *__restrict__ pack) {
+    pack_body(cin, cout, dgrad, w, pack, blockIdx.x, gridDim.x);
+}
+
+// every layer and orientation of a pyramid in one launch: table[l] = { cin | cout << 32, dgrad, weight pointer, pack pointer }
+__global__ void __launch_bounds__(256) pack_multi_kernel(const long long *__restrict__ table) {
+    const long long *t = table + (size_t)blockIdx.y * 4;
+    pack_body((int)(t[0] & 0xffffffffll), (int)(t[0] >> 32), (int)t[1], reinterpret_cast<const float *>(t[2]),
+              reinterpret_cast<float *>(t[3]), blockIdx.x, gridDim.x);
 }
 
 struct Args {
@@ -654,6 +666,14 @@ int i2p_conv3x3_pack(int cin, int cout, int dgrad, const float *w, float *pack, 
     const long long blocks = (total + 255) / 256;
     conv::pack_kernel<<<(int)(blocks < 592 ? blocks : 592), 256, 0, as_stream(stream)>>>(cin, cout, dgrad, w, pack);
     return check_launch("conv3x3_pack");
+}
+
+int i2p_conv3x3_pack_multi(int n, const long long *table, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(n >= 0 && n <= 65535 && (n == 0 || table != nullptr), "conv3x3_pack_multi: bad table");
+    if (n == 0) return I2P_OK;
+    conv::pack_multi_kernel<<<dim3(16, n), 256, 0, as_stream(stream)>>>(table);
+    return check_launch("conv3x3_pack_multi");
 }
 
 /* y (B, no, H, W) = conv3x3(x (B, ki, H, W), pad 1) [+ bias]; wpack from i2p_conv3x3_pack (forward: cin = ki, cout = no;

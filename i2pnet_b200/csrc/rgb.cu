@@ -163,97 +163,113 @@ __global__ void __launch_bounds__(256) rgb_pool_fwd_kernel(PoolGeom g, const flo
                                                           float *__restrict__ out) {
     constexpr int ZH = RGB_TH + 2, ZW = RGB_TW + 2, OH = RGB_TH / S, OW = RGB_TW / S;
     __shared__ float zt[ZH][ZW + 1];
-    const int plane = blockIdx.z, c = plane % g.C;
+    const int plane = blockIdx.z, c = plane % g.C, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h0 = blockIdx.y * RGB_TH, w0 = blockIdx.x * RGB_TW;
     const float mu = __ldg(stats + c), sc = __ldg(stats + 2 * g.C + c), bt = __ldg(stats + 3 * g.C + c);
     const float *p = y + (size_t)plane * g.H * g.W;
-    // loops cover the part of the tile that lies inside the plane (the pyramid's coarse levels are 10 x 32 planes in a
-    // 32 x 128 tile: iterating the whole tile cost 13x the useful work there)
+    // Loops cover the part of the tile that lies inside the plane (the pyramid's coarse levels are 10 x 32 planes in a
+    // 32 x 128 tile), a warp per row and a lane per column: no index division anywhere (the first version spent a
+    // third of its instructions on idx / width, idx % width -- these kernels are instruction-bound, not HBM-bound).
     const int zh = min(ZH, g.H - h0 + 2), zw = min(ZW, g.W - w0 + 2);
-    for (int idx = threadIdx.x; idx < zh * zw; idx += 256) {
-        const int hh = idx / zw, ww = idx - hh * zw;
-        const int h = h0 - 1 + hh, w = w0 - 1 + ww;
-        zt[hh][ww] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? leaky(norm(__ldg(p + (size_t)h * g.W + w), mu, sc, bt), slope)
-                                                           : -INFINITY;
+    for (int hh = warp; hh < zh; hh += 8) {
+        const int h = h0 - 1 + hh;
+        const bool row_in = h >= 0 && h < g.H;
+        const float *pr = p + (size_t)h * g.W + (w0 - 1);
+        for (int ww = lane; ww < zw; ww += 32) {
+            const int w = w0 - 1 + ww;
+            zt[hh][ww] = (row_in && w >= 0 && w < g.W) ? leaky(norm(__ldg(pr + ww), mu, sc, bt), slope) : -INFINITY;
+        }
     }
     __syncthreads();
     const int ho0 = h0 / S, wo0 = w0 / S;
     float *o = out + (size_t)plane * g.Ho * g.Wo;
     const int oh_n = min(OH, g.Ho - ho0), ow_n = min(OW, g.Wo - wo0);
-    for (int idx = threadIdx.x; idx < oh_n * ow_n; idx += 256) {
-        const int oh = idx / ow_n, ow = idx - oh * ow_n;
-        float best = -INFINITY;
+    for (int oh = warp; oh < oh_n; oh += 8) {
+        float *orow = o + (size_t)(ho0 + oh) * g.Wo + wo0;
+        for (int ow = lane; ow < ow_n; ow += 32) {
+            float best = -INFINITY;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+            for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const float v = zt[oh * S + kh][ow * S + kw];
-                if (v > best || isnan(v)) best = v;
-            }
-        o[(size_t)(ho0 + oh) * g.Wo + wo0 + ow] = best;
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float v = zt[oh * S + kh][ow * S + kw];
+                    best = (v > best || v != v) ? v : best;
+                }
+            orow[ow] = best;
+        }
     }
 }
 
 // Pass 0: dz = pooled gradient * act' for every element of the tile, written to dy; s12[slot][0][c] += sum dz,
 // s12[slot][1][c] += sum dz * yhat.  Pass 1 (rgb_bn_bwd_apply_kernel) then streams dy <- scale * (dz - S1/n - yhat S2/n).
 template <int S>
-__global__ void __launch_bounds__(256) rgb_pool_bwd_kernel(PoolGeom g, const float *__restrict__ y, const float *__restrict__ stats,
+__global__ void __launch_bounds__(256, 4) rgb_pool_bwd_kernel(PoolGeom g, const float *__restrict__ y, const float *__restrict__ stats,
                                                           float slope, const float *__restrict__ dout, double *s12,
                                                           float *__restrict__ dy) {
     constexpr int ZH = RGB_TH + 4, ZW = RGB_TW + 4;
     constexpr int NWH = RGB_TH / S + (S == 1 ? 2 : 1), NWW = RGB_TW / S + (S == 1 ? 2 : 1);   // windows touching the tile
-    __shared__ float zt[ZH][ZW + 1];          // pre-activation z, origin (h0 - 2, w0 - 2), -inf outside the plane
+    __shared__ float zt[ZH][ZW + 1];          // ACTIVATED value, origin (h0 - 2, w0 - 2), -inf outside the plane
     __shared__ float dzt[RGB_TH][RGB_TW];     // gradient w.r.t. the activated value
     __shared__ float red[RGB_THREADS / 32];
-    const int plane = blockIdx.z, c = plane % g.C;
+    const int plane = blockIdx.z, c = plane % g.C, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h0 = blockIdx.y * RGB_TH, w0 = blockIdx.x * RGB_TW;
     const float mu = __ldg(stats + c), rs = __ldg(stats + g.C + c), sc = __ldg(stats + 2 * g.C + c),
                 bt = __ldg(stats + 3 * g.C + c);
     const float *p = y + (size_t)plane * g.H * g.W;
-    // (as in the forward kernel: only the part of the tile inside the plane is touched)
+    // (as in the forward kernel: only the part of the tile inside the plane is touched; a warp per row, a lane per column)
     const int th_n = min(RGB_TH, g.H - h0), tw_n = min(RGB_TW, g.W - w0);
     const int zh = min(ZH, th_n + 4), zw = min(ZW, tw_n + 4);
-    for (int idx = threadIdx.x; idx < zh * zw; idx += 256) {
-        const int hh = idx / zw, ww = idx - hh * zw;
-        const int h = h0 - 2 + hh, w = w0 - 2 + ww;
-        zt[hh][ww] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? norm(__ldg(p + (size_t)h * g.W + w), mu, sc, bt) : -INFINITY;
+    for (int hh = warp; hh < zh; hh += 8) {
+        const int h = h0 - 2 + hh;
+        const bool row_in = h >= 0 && h < g.H;
+        const float *pr = p + (size_t)h * g.W + (w0 - 2);
+        for (int ww = lane; ww < zw; ww += 32) {
+            const int w = w0 - 2 + ww;
+            // the activation is monotonic: the arg-max of the activated window is taken on the same values as the forward
+            zt[hh][ww] = (row_in && w >= 0 && w < g.W) ? leaky(norm(__ldg(pr + ww), mu, sc, bt), slope) : -INFINITY;
+        }
     }
-    for (int idx = threadIdx.x; idx < th_n * tw_n; idx += 256) dzt[idx / tw_n][idx % tw_n] = 0.f;
+    for (int r = warp; r < th_n; r += 8)
+        for (int cc = lane; cc < tw_n; cc += 32) dzt[r][cc] = 0.f;
     __syncthreads();
     // every pooling window that overlaps the tile: window (i, j) is output (ho_first + i, wo_first + j) and its
     // top-left input element sits at tile coordinates (S == 1 ? i : 2 i + 1, ...)
     const int ho_first = S == 1 ? h0 - 1 : h0 / 2, wo_first = S == 1 ? w0 - 1 : w0 / 2;
     const float *dp = dout + (size_t)plane * g.Ho * g.Wo;
     const int nwh = min(NWH, th_n / S + 2), nww = min(NWW, tw_n / S + 2);
-    for (int idx = threadIdx.x; idx < nwh * nww; idx += 256) {
-        const int i = idx / nww, j = idx - i * nww;
-        const int ho = ho_first + i, wo = wo_first + j;
-        if (ho < 0 || ho >= g.Ho || wo < 0 || wo >= g.Wo) continue;
-        const int th = S == 1 ? i : 2 * i + 1, tw = S == 1 ? j : 2 * j + 1;
-        float best = -INFINITY;
-        int bh = 0, bw = 0;
+    for (int i = warp; i < nwh; i += 8) {
+        const int ho = ho_first + i;
+        if (ho < 0 || ho >= g.Ho) continue;
+        const int th = S == 1 ? i : 2 * i + 1;
+        const float *drow = dp + (size_t)ho * g.Wo + wo_first;
+        for (int j = lane; j < nww; j += 32) {
+            const int wo = wo_first + j;
+            if (wo < 0 || wo >= g.Wo) continue;
+            const int tw = S == 1 ? j : 2 * j + 1;
+            float best = -INFINITY;
+            int bh = 0, bw = 0;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+            for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const float zr = zt[th + kh][tw + kw];
-                if (zr == -INFINITY) continue;          // outside the plane (padding never wins, also for slope 0)
-                const float v = leaky(zr, slope);
-                if (v > best || isnan(v)) { best = v; bh = kh; bw = kw; }
-            }
-        const int r = th + bh - 2, cc = tw + bw - 2;   // arg-max position in core-tile coordinates
-        if (r >= 0 && r < RGB_TH && cc >= 0 && cc < RGB_TW) atomicAdd(&dzt[r][cc], __ldg(dp + (size_t)ho * g.Wo + wo));
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float v = zt[th + kh][tw + kw];        // padding is -inf: it never wins (v > -inf is false for it)
+                    if (v > best || v != v) { best = v; bh = kh; bw = kw; }
+                }
+            const int r = th + bh - 2, cc = tw + bw - 2;   // arg-max position in core-tile coordinates
+            if (r >= 0 && r < RGB_TH && cc >= 0 && cc < RGB_TW) atomicAdd(&dzt[r][cc], __ldg(drow + j));
+        }
     }
     __syncthreads();
     float s1 = 0.f, s2 = 0.f;
-    for (int idx = threadIdx.x; idx < th_n * tw_n; idx += 256) {
-        const int r = idx / tw_n, cc = idx - r * tw_n;
-        const int h = h0 + r, w = w0 + cc;
-        const float dz = dzt[r][cc] * (zt[r + 2][cc + 2] > 0.f ? 1.f : slope);
-        const float yhat = (__ldg(p + (size_t)h * g.W + w) - mu) * rs;
-        s1 += dz;
-        s2 += dz * yhat;
-        dy[(size_t)plane * g.H * g.W + (size_t)h * g.W + w] = dz;
+    for (int r = warp; r < th_n; r += 8) {
+        const size_t row = (size_t)plane * g.H * g.W + (size_t)(h0 + r) * g.W + w0;
+        for (int cc = lane; cc < tw_n; cc += 32) {
+            const float dz = dzt[r][cc] * (zt[r + 2][cc + 2] > 0.f ? 1.f : slope);     // sign of the activated value = sign of z
+            const float yhat = (__ldg(y + row + cc) - mu) * rs;
+            s1 += dz;
+            s2 += dz * yhat;
+            dy[row + cc] = dz;
+        }
     }
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);

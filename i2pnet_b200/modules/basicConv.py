@@ -84,8 +84,8 @@ class _ConvBlock(Function):
         Cout = w.shape[0]
         L = _cabi.lib()
         xp = _ptr(x, f32, "conv input", dev)
-        pack = torch.empty(L.i2p_conv3x3_pack_floats(Cin, Cout, 0), dtype=f32, device=dev)
-        call("i2p_conv3x3_pack", dev, Cin, Cout, 0, _ptr(w, f32, "conv weight", dev), pack.data_ptr())
+        from ..projectPN.fused_mlp import conv_weight_pack
+        pack = conv_weight_pack(w, Cin, Cout, 0, dev)       # once per step for all layers under a step engine
         batch_stats = bn.training or not bn.track_running_stats
         ntiles = L.i2p_conv3x3_stat_slots(B, Cout, H, W)     # one statistics slot per persistent CTA
         y = torch.empty(B, Cout, H, W, dtype=f32, device=dev)
@@ -149,8 +149,8 @@ class _ConvBlock(Function):
             grad_sink(ctx.params[1]).add_(dy.sum(dim=(0, 2, 3)))
         gx = None
         if ctx.needs_input_grad[0]:
-            pack = torch.empty(L.i2p_conv3x3_pack_floats(Cin, Cout, 1), dtype=f32, device=dev)
-            call("i2p_conv3x3_pack", dev, Cin, Cout, 1, w.data_ptr(), pack.data_ptr())
+            from ..projectPN.fused_mlp import conv_weight_pack
+            pack = conv_weight_pack(ctx.params[0], Cin, Cout, 1, dev)
             gx = torch.empty_like(x)
             call("i2p_conv3x3_tc", dev, B, Cout, Cin, H, W, dy.data_ptr(), pack.data_ptr(), None, gx.data_ptr(), None)
         return gx, gw, gb, dgb[0], dgb[1], None, None, None

@@ -10,6 +10,7 @@ backward (see mlp.cu for the algebra).  Numerically it is the same f32 computati
 (merged Welford) batch statistics; the bias feeding a BatchNorm gets an exactly zero gradient
 instead of autograd's rounding noise.
 """
+import os
 import weakref
 
 import torch
@@ -26,13 +27,18 @@ def _p(t):
 
 
 class _PackRegistry:
-    """Packed (tf32 hi / lo, UMMA layout) copies of the shared-MLP weights under a step engine.  The weights change once
-    per optimiser step, so the engine packs every registered layer in ONE launch at the start of the step
-    (`packs_begin_step`) instead of one launch per layer inside the forward chain; layers are registered the first time a
-    forward pass meets them (the eager warm-up steps).  Without an engine every forward packs its own copy, as before."""
+    """Packed (tf32 hi / lo, UMMA layout) copies of the weights of the tensor-core kernels under a step engine.  The weights
+    change once per optimiser step, so the engine packs every registered layer in ONE launch per kernel family at the
+    start of the step (`packs_begin_step`) instead of one launch per layer inside the forward / backward chains; layers are
+    registered the first time a pass meets them (the eager warm-up steps).  Without an engine every pass packs its own
+    copy, as before.  kind "mlp": i2p_pw_pack_weights (both orientations in one buffer); kind "conv": i2p_conv3x3_pack,
+    variant = dgrad."""
+
+    MULTI = {"mlp": ("i2p_pw_pack_weights_multi", lambda e, key: [e["cin"] | (e["cout"] << 32), e["ptr"], e["pack"].data_ptr()]),
+             "conv": ("i2p_conv3x3_pack_multi", lambda e, key: [e["cin"] | (e["cout"] << 32), key[2], e["ptr"], e["pack"].data_ptr()])}
 
     def __init__(self, device):
-        self.device, self.entries, self.table, self.dirty, self.active, self.packed = device, {}, None, False, False, False
+        self.device, self.entries, self.tables, self.dirty, self.active, self.packed = device, {}, {}, False, False, False
 
     def begin_step(self):
         self.active, self.packed = True, False
@@ -41,30 +47,30 @@ class _PackRegistry:
             del self.entries[k]
             self.dirty = True
         if not self.entries:
-            self.table = None
+            self.tables = {}
             return
-        if (self.table is None or self.dirty) and not torch.cuda.is_current_stream_capturing():
-            rows = []
-            for e in self.entries.values():
+        if (not self.tables or self.dirty) and not torch.cuda.is_current_stream_capturing():
+            rows = {}
+            for key, e in self.entries.items():
                 e["ptr"] = e["ref"]().data_ptr()
-                rows.append([e["cin"] | (e["cout"] << 32), e["ptr"], e["pack"].data_ptr()])
-            self.table = torch.tensor(rows, dtype=torch.int64).to(self.device)
-            self.n_table = len(rows)
-            for e in self.entries.values():
+                rows.setdefault(key[0], []).append(self.MULTI[key[0]][1](e, key))
                 e["in_table"] = True
+            self.tables = {kind: (len(r), torch.tensor(r, dtype=torch.int64).to(self.device)) for kind, r in rows.items()}
             self.dirty = False
-        if self.table is not None and not self.dirty:
-            call("i2p_pw_pack_weights_multi", self.device, self.n_table, self.table.data_ptr())
+        if self.tables and not self.dirty:
+            for kind, (n, table) in self.tables.items():
+                call(self.MULTI[kind][0], self.device, n, table.data_ptr())
             self.packed = True
 
-    def get(self, w, cin, cout):
+    def get(self, kind, w, variant, cin, cout, floats):
         """-> (pack tensor, already packed this step)"""
-        e = self.entries.get(id(w))
+        key = (kind, id(w), variant)
+        e = self.entries.get(key)
         if e is not None and e["ref"]() is not w:       # the id of a dead parameter, reused
             e = None
         if e is None:
-            pack = torch.empty(_cabi.lib().i2p_pw_pack_floats(cin, cout), dtype=f32, device=self.device)
-            e = self.entries[id(w)] = dict(ref=weakref.ref(w), cin=cin, cout=cout, pack=pack, ptr=None, in_table=False)
+            pack = torch.empty(floats, dtype=f32, device=self.device)
+            e = self.entries[key] = dict(ref=weakref.ref(w), cin=cin, cout=cout, pack=pack, ptr=None, in_table=False)
             self.dirty = True
         ready = self.packed and e["in_table"] and e["ptr"] == w.data_ptr()
         if not ready and e["in_table"] and e["ptr"] != w.data_ptr():
@@ -73,6 +79,7 @@ class _PackRegistry:
 
 
 _REGISTRIES = {}
+_PACK_ONCE = os.environ.get("I2P_PACK_ONCE", "mlp,conv").split(",")      # A/B switch: which kernel families pack once per step
 
 
 def packs_begin_step(device):
@@ -91,14 +98,27 @@ def packs_end_step():
 
 
 def _weight_pack(w, cin, cout, dev):
+    floats = _cabi.lib().i2p_pw_pack_floats(cin, cout)
     reg = _REGISTRIES.get(dev.index)
-    if reg is not None and reg.active:
-        pack, ready = reg.get(w, cin, cout)
-        if not ready:
-            call("i2p_pw_pack_weights", dev, cin, cout, _ptr(w, f32, "weight", dev), pack.data_ptr())
-        return pack
-    pack = torch.empty(_cabi.lib().i2p_pw_pack_floats(cin, cout), dtype=f32, device=dev)
-    call("i2p_pw_pack_weights", dev, cin, cout, _ptr(w, f32, "weight", dev), pack.data_ptr())
+    if reg is not None and reg.active and "mlp" in _PACK_ONCE:
+        pack, ready = reg.get("mlp", w, 0, cin, cout, floats)
+    else:
+        pack, ready = torch.empty(floats, dtype=f32, device=dev), False
+    if not ready:
+        call("i2p_pw_pack_weights", dev, cin, cout, _ptr(w, f32, "weight", dev), pack.data_ptr())
+    return pack
+
+
+def conv_weight_pack(w, cin, cout, dgrad, dev):
+    """Packed operand of the 3x3 convolution kernels (csrc/conv.cu) for weight w (cout, cin, 3, 3)."""
+    floats = _cabi.lib().i2p_conv3x3_pack_floats(cin, cout, int(dgrad))
+    reg = _REGISTRIES.get(dev.index)
+    if reg is not None and reg.active and "conv" in _PACK_ONCE:
+        pack, ready = reg.get("conv", w, int(dgrad), cin, cout, floats)
+    else:
+        pack, ready = torch.empty(floats, dtype=f32, device=dev), False
+    if not ready:
+        call("i2p_conv3x3_pack", dev, cin, cout, int(dgrad), _ptr(w, f32, "weight", dev), pack.data_ptr())
     return pack
 
 

@@ -303,6 +303,8 @@ long long i2p_conv3x3_pack_floats(int cin, int cout, int dgrad);
 int i2p_conv3x3_tiles(int H, int W);
 int i2p_conv3x3_stat_slots(int B, int no, int H, int W);
 int i2p_conv3x3_pack(int cin, int cout, int dgrad, const float *w, float *pack, void *stream);
+/* n packs in one launch: table (n, 4) int64 on the device, row = { cin | cout << 32, dgrad, weight pointer, pack pointer } */
+int i2p_conv3x3_pack_multi(int n, const long long *table, void *stream);
 int i2p_conv3x3_tc(int B, int ki, int no, int H, int W, const float *x, const float *wpack, const float *bias, float *y,
                    float *tile_stats, void *stream);
 int i2p_conv3x3_wgrad(int B, int cin, int cout, int H, int W, const float *x, const float *dy, float *dw, void *stream);

@@ -31,8 +31,40 @@ print("stream: busy / first / last / gaps inside")
 for k, v in sorted(st.items(), key=lambda kv: -sum(r["d"] for r in kv[1])):
     gaps = sum(max(0.0, b["s"] - a["e"]) for a, b in zip(v, v[1:]))
     print("  %4s busy %6.0f n %3d  %6.0f .. %6.0f  gaps %6.0f" % (k, sum(r["d"] for r in v), len(v), v[0]["s"] - t0, v[-1]["e"] - t0, gaps))
-if len(sys.argv) > 2:
+if len(sys.argv) > 2 and sys.argv[2] != "path":
     frm = float(sys.argv[2]) + t0
     for r in rows:
         if r["s"] >= frm and r["d"] > 8:
             print("%7.0f %6.1f %4s %s" % (r["s"] - t0, r["d"], r["stream"], r["name"][:90]))
+
+
+def critical_path(rows, t0):
+    """Walk back from the last kernel: the predecessor of a kernel is the one (any stream) that ended last before it
+    started -- what it waited for.  -> time on the path by kernel name, and the idle time between the links."""
+    import collections
+    by_end = sorted(rows, key=lambda r: r["e"])
+    ends = [r["e"] for r in by_end]
+    import bisect
+    cur = max(rows, key=lambda r: r["e"])
+    on_path, gaps, n = collections.Counter(), 0.0, 0
+    while True:
+        on_path[cur["name"].replace("void ", "").replace("at::native::", "")[:70]] += cur["d"]
+        n += 1
+        i = bisect.bisect_right(ends, cur["s"] + 0.05) - 1
+        while i >= 0 and by_end[i] is cur:
+            i -= 1
+        if i < 0:
+            break
+        prev = by_end[i]
+        if prev["e"] < t0 or cur["s"] - prev["e"] > 200:
+            break
+        gaps += max(0.0, cur["s"] - prev["e"])
+        cur = prev
+    return on_path, gaps, n
+
+
+if len(sys.argv) > 2 and sys.argv[2] == "path":
+    on_path, gaps, n = critical_path(rows, t0)
+    print("critical path: %d kernels, %.0f us of kernel time, %.0f us between them" % (n, sum(on_path.values()), gaps))
+    for k, v in on_path.most_common(40):
+        print("%7.1f %s" % (v, k))
