@@ -23,6 +23,18 @@ extern std::atomic<uint64_t> g_launches;
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);
 
+// Dynamic shared memory a weight-gradient launch asks for at least (I2P_WGRAD_SMEM bytes, 0 = only what it needs): the
+// weight-gradient kernels run on low-priority side streams beside the step's serial chain; asking for more than half an
+// SM's shared memory keeps them at one CTA per SM, so that a chain kernel always finds room (runtime.cu).
+int wgrad_smem_floor();
+template <typename K>
+inline int wgrad_smem(K kernel, int needed) {
+    const int floor_ = wgrad_smem_floor();
+    if (floor_ <= needed) return needed;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, floor_);
+    return floor_;
+}
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

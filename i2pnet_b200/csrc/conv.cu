@@ -738,7 +738,7 @@ int i2p_conv3x3_wgrad(int B, int cin, int cout, int H, int W, const float *x, co
         if (gx < 1) gx = 1;                                                                                    \
         if (gx > a.ntiles) gx = a.ntiles;                                                                      \
         dim3 grid(gx, groups);                                                                                 \
-        conv::wgrad_kernel<CI_, TW_><<<grid, conv::THREADS, G::BYTES, s>>>(a);                                 \
+        conv::wgrad_kernel<CI_, TW_><<<grid, conv::THREADS, wgrad_smem(conv::wgrad_kernel<CI_, TW_>, G::BYTES), s>>>(a); \
     } while (0)
     if (cin <= 4) I2P_WGRAD(4, 8);
     else I2P_WGRAD(16, 32);

@@ -294,7 +294,9 @@ static bool cv_geom(CvGeom &g, int B, int N, int K, int N2, int C, int has_max) 
 // backward, every one of them on the step's critical path (CUPTI timeline: 215 us before cost volume 1, one kernel in
 // flight).  One block per cloud does it all; the extrema carry the index of the first point that attains them, which
 // is where the backward sends their gradient (torch.max's convention).
-constexpr int PREP_THREADS = 512, PREP_WARPS = PREP_THREADS / 32, PREP_MAXJ = 8;    // C <= 256
+// (128-thread blocks: these kernels run beside persistent weight-gradient kernels that fill the SMs; a 512-thread block
+// with ~90 registers per thread needs 3/4 of an SM's register file at once and waited up to 90 us for it)
+constexpr int PREP_THREADS = 128, PREP_WARPS = PREP_THREADS / 32, PREP_MAXJ = 8;    // C <= 256
 
 struct PrepArgs {
     int N, N2, C, has_max;
@@ -457,6 +459,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_bwd_kernel(const Prep
         float dh[PREP_MAXJ], dl[PREP_MAXJ];
 #pragma unroll
         for (int j = 0; j < PREP_MAXJ; ++j) dh[j] = dl[j] = 0.f;
+#pragma unroll 4
         for (int k = warp; k < N2; k += PREP_WARPS) {
             const size_t row = ((size_t)b * N2 + k) * C;
 #pragma unroll
@@ -610,7 +613,7 @@ int i2p_softmax_wsum_bwd(long long groups, int K, int C, const float *logit, con
 // blocks per cloud: enough that a warp sees two or three rows (the kernels are latency-bound chains of row reductions)
 static int prep_blocks(int rows) {
     const int s = i2p::ceil_div(rows, 2 * i2p::PREP_WARPS);
-    return s < 1 ? 1 : (s > 16 ? 16 : s);
+    return s < 1 ? 1 : (s > 32 ? 32 : s);
 }
 
 int i2p_cv_prep_scratch_floats(int B, int N, int N2, int C) {

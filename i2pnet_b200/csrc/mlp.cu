@@ -887,7 +887,7 @@ static int launch_dw(DwArgs a, cudaStream_t s) {
     if (rpb < 8 * BK) rpb = 8 * BK;
     a.rows_per_block = rpb;
     dim3 grid(ceil_div(a.cout, BMo), ceil_div(a.cin, BNi), ceil_div(a.rows, rpb));
-    pw_linear_bwd_dw_kernel<BMo, BNi, BK><<<grid, MLP_THREADS, sizeof(DyTables), s>>>(a);
+    pw_linear_bwd_dw_kernel<BMo, BNi, BK><<<grid, MLP_THREADS, wgrad_smem(pw_linear_bwd_dw_kernel<BMo, BNi, BK>, (int)sizeof(DyTables)), s>>>(a);
     return check_launch("pw_linear_bwd_dw");
 }
 
@@ -993,7 +993,7 @@ static int launch_dw_skinny(DwArgs a, cudaStream_t s) {
     if (rpb < 4 * BK) rpb = 4 * BK;
     a.rows_per_block = rpb;
     dim3 grid(tiles, ceil_div(a.rows, rpb));
-    pw_linear_bwd_dw_skinny_kernel<CO><<<grid, MLP_THREADS, sizeof(DyTables), s>>>(a);
+    pw_linear_bwd_dw_skinny_kernel<CO><<<grid, MLP_THREADS, wgrad_smem(pw_linear_bwd_dw_skinny_kernel<CO>, (int)sizeof(DyTables)), s>>>(a);
     return check_launch("pw_linear_bwd_dw(skinny)");
 }
 

@@ -971,7 +971,9 @@ int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, c
     const int bn = cout <= 64 ? 64 : 128;
     const int mt = ceil_div(cin, tc::BM), ntl = ceil_div(cout, bn);
     // about two waves of CTAs (2 resident per SM), at least 8 chunks of rows per CTA
-    int chunks = (2 * 2 * 148 + mt * ntl - 1) / (mt * ntl);
+    static int waves = -1;     // I2P_DW_WAVES: tuning override (shorter CTAs let the block scheduler interleave the step's chain kernels)
+    if (waves < 0) { const char *e = getenv("I2P_DW_WAVES"); waves = e ? atoi(e) : 2; if (waves < 1) waves = 1; }
+    int chunks = (waves * 2 * 148 + mt * ntl - 1) / (mt * ntl);
     int rpb = (rows + chunks - 1) / chunks;
     rpb = ((rpb + tc::BK - 1) / tc::BK) * tc::BK;
     if (rpb < 8 * tc::BK) rpb = 8 * tc::BK;
@@ -984,7 +986,7 @@ int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, c
     do {                                                                                                      \
         static bool once = false;                                                                             \
         if (!once) { tc::allow_smem(tc::dw_kernel<BN_, V_, M_>, tc::dw_smem_bytes<BN_>()); once = true; }     \
-        tc::dw_kernel<BN_, V_, M_><<<grid, tc::THREADS, tc::dw_smem_bytes<BN_>(), s>>>(a);                    \
+        tc::dw_kernel<BN_, V_, M_><<<grid, tc::THREADS, wgrad_smem(tc::dw_kernel<BN_, V_, M_>, tc::dw_smem_bytes<BN_>()), s>>>(a); \
     } while (0)
 #define I2P_DW_V(BN_, M_) do { if (vec == 4) I2P_DW(BN_, 4, M_); else if (vec == 2) I2P_DW(BN_, 2, M_); else I2P_DW(BN_, 1, M_); } while (0)
     if (bn == 64) { if (maxk) I2P_DW_V(64, true); else I2P_DW_V(64, false); }

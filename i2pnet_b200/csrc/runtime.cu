@@ -1,5 +1,6 @@
 // Error state, launch accounting and ABI version of libi2p_b200.so.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,6 +26,12 @@ int check_launch(const char *what) {
         return I2P_ERR_CUDA;
     }
     return I2P_OK;
+}
+
+int wgrad_smem_floor() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("I2P_WGRAD_SMEM"); v = e ? atoi(e) : 0; if (v < 0) v = 0; if (v > 227 * 1024) v = 227 * 1024; }
+    return v;
 }
 
 }  // namespace i2p
