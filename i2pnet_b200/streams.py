@@ -33,6 +33,8 @@ _pools = {}
 # of the stream they were captured on.  I2P_STREAM_PRIORITIES=0: all streams at the default priority.
 PRIORITIES = os.environ.get("I2P_STREAM_PRIORITIES", "1") != "0"
 _PRIORITY = {"branch": -2, "main": -1, "wgrad": 0}
+if os.environ.get("I2P_STREAM_PRIORITY_LEVELS"):        # tuning override: "branch,main,wgrad", e.g. "-2,-1,-1"
+    _PRIORITY = dict(zip(("branch", "main", "wgrad"), (int(v) for v in os.environ["I2P_STREAM_PRIORITY_LEVELS"].split(","))))
 
 
 def priority_of(kind):
