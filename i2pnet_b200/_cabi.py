@@ -59,8 +59,8 @@ _SIGNATURES = {
     "i2p_pw_linear_bwd_dw_tc": [_int] * 3 + [_vp] * 3 + [_int] + [_vp] * 5 + [_flt] + [_vp] * 4 + [_flt, _vp, _vp],
     "i2p_cv_build": [_int] * 5 + [_vp] * 9,
     "i2p_cv_build_bwd": [_int] * 6 + [_vp] * 11,
-    "i2p_softmax_wsum": [_ll, _int, _int] + [_vp] * 5,
-    "i2p_softmax_wsum_bwd": [_ll, _int, _int] + [_vp] * 8,
+    "i2p_softmax_wsum": [_ll, _int, _int] + [_vp] * 6,
+    "i2p_softmax_wsum_bwd": [_ll, _int, _int] + [_vp] * 9,
     "i2p_cv_prep_fwd": [_int] * 5 + [_vp] * 16,
     "i2p_cv_prep_scratch_floats": [_int] * 4,
     "i2p_cv_prep_bwd": [_int] * 5 + [_vp] * 19,

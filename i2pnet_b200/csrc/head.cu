@@ -12,7 +12,7 @@
 
 namespace i2p {
 
-constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_THREADS = 1024;    // the forward is three dependent passes over the points of ONE sample per block: latency-bound, so as many row groups as a block holds (256 threads: 50 us per head, twice on the serial chain)
 constexpr int HEAD_MAXC = 128, HEAD_MAXH = 256;
 
 struct HeadArgs {
@@ -138,9 +138,10 @@ struct HeadBwdArgs {
 // grid (B, HEAD_SPLIT): the blocks of a sample all rebuild the (tiny) head gradients, then share the expensive parts --
 // the Hd x C outer product for dW1 and the N x C element-wise tail -- by slices.
 constexpr int HEAD_SPLIT = 4;
+constexpr int HEAD_BWD_THREADS = 256;
 
-__global__ void __launch_bounds__(HEAD_THREADS) pose_head_bwd_kernel(const HeadBwdArgs a) {
-    __shared__ float d7[8], dhid[HEAD_MAXH], dpool[HEAD_MAXC], pooled[HEAD_MAXC], part[HEAD_THREADS / 32][HEAD_MAXC];
+__global__ void __launch_bounds__(HEAD_BWD_THREADS) pose_head_bwd_kernel(const HeadBwdArgs a) {
+    __shared__ float d7[8], dhid[HEAD_MAXH], dpool[HEAD_MAXC], pooled[HEAD_MAXC], part[HEAD_BWD_THREADS / 32][HEAD_MAXC];
     const int b = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x;
     const int C = a.C, N = a.N, Hd = a.Hd;
     const bool lead = sp == 0;      // the block that adds the small parameter gradients
@@ -157,10 +158,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) pose_head_bwd_kernel(const HeadB
             for (int i = 0; i < 3; ++i) atomicAdd(a.dbt + i, d7[4 + i]);
         }
     }
-    for (int k = tid; k < C; k += HEAD_THREADS) pooled[k] = a.pooled[(size_t)b * C + k];
+    for (int k = tid; k < C; k += HEAD_BWD_THREADS) pooled[k] = a.pooled[(size_t)b * C + k];
     __syncthreads();
     // d hidden (after dropout) = Wq^T dq_raw + Wt^T dt ; head weight gradients ; through the dropout
-    for (int h = tid; h < Hd; h += HEAD_THREADS) {
+    for (int h = tid; h < Hd; h += HEAD_BWD_THREADS) {
         const float hv = a.hidden[(size_t)b * Hd + h];
         float v = 0.f;
 #pragma unroll
@@ -180,13 +181,13 @@ __global__ void __launch_bounds__(HEAD_THREADS) pose_head_bwd_kernel(const HeadB
     __syncthreads();
     // dW1 = dhid (x) pooled: this block's slice of the hidden units
     const int h_per = (Hd + HEAD_SPLIT - 1) / HEAD_SPLIT, h0 = sp * h_per, h1 = min(Hd, h0 + h_per);
-    for (int e = h0 * C + tid; e < h1 * C; e += HEAD_THREADS) {
+    for (int e = h0 * C + tid; e < h1 * C; e += HEAD_BWD_THREADS) {
         const int h = e / C, k = e - h * C;
         atomicAdd(a.dw1 + e, dhid[h] * pooled[k]);
     }
     // dpooled = W1^T dhid: threads = (channel, slice of the hidden units), partial sums meet in shared memory
     {
-        const int G = HEAD_THREADS / C, k = tid % C, gq = tid / C;
+        const int G = HEAD_BWD_THREADS / C, k = tid % C, gq = tid / C;
         float v = 0.f;
         if (gq < G) for (int h = gq; h < Hd; h += G) v = __fmaf_rn(__ldg(a.w1 + (size_t)h * C + k), dhid[h], v);
         if (gq < G) part[gq][k] = v;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) pose_head_bwd_kernel(const HeadB
     const float *pr = a.pred + (size_t)b * N * C, *mp = a.mask_p + (size_t)b * N * C;
     float *dp = a.dpred + (size_t)b * N * C, *dm = a.dmask + (size_t)b * N * C;
     const int e_per = (N * C + HEAD_SPLIT - 1) / HEAD_SPLIT, e0 = sp * e_per, e1 = min(N * C, e0 + e_per);
-    for (int e = e0 + tid; e < e1; e += HEAD_THREADS) {
+    for (int e = e0 + tid; e < e1; e += HEAD_BWD_THREADS) {
         const int k = e % C;
         const float p = mp[e], g = dpool[k];
         dp[e] = g * p;
@@ -309,10 +310,10 @@ int i2p_pose_head_bwd(int B, int N, int C, int Hd, const float *pred, const floa
                       const float *wt, const float *dq, const float *dt, float *dpred, float *dmask, float *dw1, float *db1,
                       float *dwq, float *dbq, float *dwt, float *dbt, void *stream) {
     using namespace i2p;
-    I2P_REQUIRE(B >= 1 && N >= 1 && C >= 1 && C <= HEAD_MAXC && HEAD_THREADS % C == 0 && Hd >= 1 && Hd <= HEAD_MAXH, "pose_head_bwd: bad sizes");
+    I2P_REQUIRE(B >= 1 && N >= 1 && C >= 1 && C <= HEAD_MAXC && HEAD_BWD_THREADS % C == 0 && Hd >= 1 && Hd <= HEAD_MAXH, "pose_head_bwd: bad sizes");
     HeadBwdArgs a{B, N, C, Hd, pred, mask_p, pooled, hidden, q_raw, drop, w1, wq, wt, dq, dt, dpred, dmask,
                   dw1, db1, dwq, dbq, dwt, dbt};
-    pose_head_bwd_kernel<<<dim3(B, HEAD_SPLIT), HEAD_THREADS, 0, as_stream(stream)>>>(a);
+    pose_head_bwd_kernel<<<dim3(B, HEAD_SPLIT), HEAD_BWD_THREADS, 0, as_stream(stream)>>>(a);
     return check_launch("pose_head_bwd");
 }
 

@@ -399,23 +399,26 @@ class _SoftmaxWSum(torch.autograd.Function):
         mask = mask.contiguous() if mask is not None else None
         B, N, K, C = logit.shape
         out = torch.empty(B, N, C, dtype=f32, device=dev)
+        stat = torch.empty(B, N, C, 2, dtype=f32, device=dev) if C % 8 == 0 else None      # (max, 1 / sum) per (group, channel)
         _cabi.call("i2p_softmax_wsum", dev, B * N, K, C, _cabi._ptr(logit, f32, "logit", dev), _cabi._ptr(value, f32, "value", dev),
-                   _cabi._ptr(mask, f32, "mask", dev) if mask is not None else None, out.data_ptr())
-        ctx.save_for_backward(logit, value, out, mask if mask is not None else torch.empty(0, device=dev))
-        ctx.has_mask = mask is not None
+                   _cabi._ptr(mask, f32, "mask", dev) if mask is not None else None, out.data_ptr(),
+                   stat.data_ptr() if stat is not None else None)
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(logit, value, out, mask if mask is not None else empty, stat if stat is not None else empty)
+        ctx.has_mask, ctx.has_stat = mask is not None, stat is not None
         return out
 
     @staticmethod
     def backward(ctx, gout):
         from .. import _cabi
-        logit, value, out, mask = ctx.saved_tensors
+        logit, value, out, mask, stat = ctx.saved_tensors
         f32, dev = torch.float32, logit.device
         B, N, K, C = logit.shape
         gout = gout.contiguous()
         dlogit, dvalue = torch.empty_like(logit), torch.empty_like(value)
         _cabi.call("i2p_softmax_wsum_bwd", dev, B * N, K, C, logit.data_ptr(), value.data_ptr(),
                    mask.data_ptr() if ctx.has_mask else None, out.data_ptr(), _cabi._ptr(gout, f32, "grad", dev),
-                   dlogit.data_ptr(), dvalue.data_ptr())
+                   stat.data_ptr() if ctx.has_stat else None, dlogit.data_ptr(), dvalue.data_ptr())
         return dlogit, dvalue, None
 
 

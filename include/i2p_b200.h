@@ -248,12 +248,14 @@ int i2p_cv_build(int B, int N, int K, int N2, int C, const float *xyz1, const fl
 int i2p_cv_build_bwd(int B, int N, int K, int N2, int C, int has_max, const float *dX, const float *dxyz6, const float *pi,
                      const float *qi, const int32_t *idx, float *dxyz1, float *dxyz2, float *dpi, float *dqi, float *dmaxc,
                      void *stream);
-/* out (G,C) = sum_k softmax_k(l) v, l = logit (G,K,C) [* mask + -1e10 (1 - mask), mask (G,K) or NULL], v = value (G,K,C) */
+/* out (G,C) = sum_k softmax_k(l) v, l = logit (G,K,C) [* mask + -1e10 (1 - mask), mask (G,K) or NULL], v = value (G,K,C);
+ * stat (G,C,2) or NULL receives (max_k l, 1 / sum_k exp(l - max)) for the backward pass (needs C % 8 == 0) */
 int i2p_softmax_wsum(long long groups, int K, int C, const float *logit, const float *value, const float *mask, float *out,
-                     void *stream);
-/* gout (G,C) -> dlogit, dvalue (G,K,C); the softmax is recomputed from logit */
+                     float *stat, void *stream);
+/* gout (G,C) -> dlogit, dvalue (G,K,C); with stat from the forward an element-wise pass, without it the softmax is
+ * recomputed from logit */
 int i2p_softmax_wsum_bwd(long long groups, int K, int C, const float *logit, const float *value, const float *mask,
-                         const float *out, const float *gout, float *dlogit, float *dvalue, void *stream);
+                         const float *out, const float *gout, const float *stat, float *dlogit, float *dvalue, void *stream);
 
 /* Operand preparation of the cost volume (src/projectPN/PPBackbone_center.py:379-397; replaces ~40 element-wise /
  * reduction launches per direction): xyz (B,N,3) = uv * z; pi (B,N,C), qi (B,N2,C) = the point / pixel features
