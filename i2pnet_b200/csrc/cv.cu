@@ -381,16 +381,17 @@ struct PrepArgs {
 };
 
 // standardise one row held as v[j] = x[lane + 32 j]; -> the clipped denominator
-__device__ __forceinline__ float standardise_row(float (&v)[PREP_MAXJ], int C, int lane) {
+template <int MJ>
+__device__ __forceinline__ float standardise_row(float (&v)[MJ], int C, int lane) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < PREP_MAXJ; ++j) s += (lane + 32 * j < C) ? v[j] : 0.f;
+    for (int j = 0; j < MJ; ++j) s += (lane + 32 * j < C) ? v[j] : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
     const float mean = s / (float)C;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < PREP_MAXJ; ++j) {
+    for (int j = 0; j < MJ; ++j) {
         v[j] -= mean;
         q += (lane + 32 * j < C) ? v[j] * v[j] : 0.f;
     }
@@ -398,32 +399,33 @@ __device__ __forceinline__ float standardise_row(float (&v)[PREP_MAXJ], int C, i
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(FULL, q, o);
     const float den = fmaxf(sqrtf(q / (float)(C - 1)), 1e-12f);
 #pragma unroll
-    for (int j = 0; j < PREP_MAXJ; ++j) v[j] /= den;
+    for (int j = 0; j < MJ; ++j) v[j] /= den;
     return den;
 }
 
-__global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_fwd_kernel(const PrepArgs a) {
+template <int MJ>     // MJ = channels per lane: C <= 32 MJ
+__global__ void __launch_bounds__(PREP_THREADS) cv_prep_fwd_kernel(const PrepArgs a) {
     __shared__ float hi_s[32 * PREP_MAXJ], lo_s[32 * PREP_MAXJ];
     __shared__ int ahi_s[32 * PREP_MAXJ], alo_s[32 * PREP_MAXJ];
     __shared__ unsigned ticket_s;
     const int b = blockIdx.y, S = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = a.N, N2 = a.N2, C = a.C;
-    float hi[PREP_MAXJ], lo[PREP_MAXJ];
-    int ahi[PREP_MAXJ], alo[PREP_MAXJ];
+    float hi[MJ], lo[MJ];
+    int ahi[MJ], alo[MJ];
 #pragma unroll
-    for (int j = 0; j < PREP_MAXJ; ++j) { hi[j] = -INFINITY; lo[j] = INFINITY; ahi[j] = alo[j] = -1; }
+    for (int j = 0; j < MJ; ++j) { hi[j] = -INFINITY; lo[j] = INFINITY; ahi[j] = alo[j] = -1; }
     // the cloud's rows (points, then pixels) are dealt to the S blocks of the cloud and their warps
     for (int r = blockIdx.x * PREP_WARPS + warp; r < N + N2; r += S * PREP_WARPS) {
         const bool point = r < N;
         const size_t row = point ? (size_t)b * N + r : (size_t)b * N2 + (r - N);
         const float *src = (point ? a.pf : a.qf) + row * C;
-        float v[PREP_MAXJ];
+        float v[MJ];
 #pragma unroll
-        for (int j = 0; j < PREP_MAXJ; ++j) v[j] = (lane + 32 * j < C) ? __ldg(src + lane + 32 * j) : 0.f;
+        for (int j = 0; j < MJ; ++j) v[j] = (lane + 32 * j < C) ? __ldg(src + lane + 32 * j) : 0.f;
         const float den = standardise_row(v, C, lane);
         float *dst = (point ? a.pi : a.qi) + row * C;
 #pragma unroll
-        for (int j = 0; j < PREP_MAXJ; ++j)
+        for (int j = 0; j < MJ; ++j)
             if (lane + 32 * j < C) dst[lane + 32 * j] = v[j];
         if (lane == 0) (point ? a.den_p : a.den_q)[row] = den;
         if (point) {
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_fwd_kernel(const Prep
             const bool valid = __any_sync(FULL, x != 0.f);
             if (valid && a.has_max) {
 #pragma unroll
-                for (int j = 0; j < PREP_MAXJ; ++j) {       // rows come in increasing order: strict comparisons keep the first
+                for (int j = 0; j < MJ; ++j) {       // rows come in increasing order: strict comparisons keep the first
                     if (v[j] > hi[j]) { hi[j] = v[j]; ahi[j] = r; }
                     if (v[j] < lo[j]) { lo[j] = v[j]; alo[j] = r; }
                 }
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_fwd_kernel(const Prep
     for (int w = 0; w < PREP_WARPS; ++w) {
         if (warp == w) {
 #pragma unroll
-            for (int j = 0; j < PREP_MAXJ; ++j) merge(lane + 32 * j, hi[j], ahi[j], lo[j], alo[j], w == 0);
+            for (int j = 0; j < MJ; ++j) merge(lane + 32 * j, hi[j], ahi[j], lo[j], alo[j], w == 0);
         }
         __syncthreads();
     }
@@ -482,12 +484,17 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_fwd_kernel(const Prep
         a.arg_hi[(size_t)b * C + c] = any_valid ? ahi_s[c] : -1;
         a.arg_lo[(size_t)b * C + c] = any_valid ? alo_s[c] : -1;
     }
-    // maxc = max over the valid points of pi[n,c] * qi[k,c] (-1e10 for a cloud without valid points); the pixel rows were
-    // written by all blocks of the cloud: read them past L1
-    for (int e = threadIdx.x; e < N2 * C; e += PREP_THREADS) {
-        const int c = e % C;
-        const float q = __ldcg(a.qi + (size_t)b * N2 * C + e);
-        a.maxc[(size_t)b * N2 * C + e] = any_valid ? (q > 0.f ? q * hi_s[c] : q * lo_s[c]) : -1e10f;
+}
+
+// maxc = max over the valid points of pi[n,c] * qi[k,c] = qi times the largest (qi > 0) or smallest valid pi[:,c]; -1e10 for a
+// cloud without valid points.  (Element-wise over (B, N2, C); inside the last block of cv_prep_fwd it was a serial 25 us.)
+__global__ void __launch_bounds__(256) cv_maxc_kernel(long long total, int N2C, int C, const float *__restrict__ qi, const float *__restrict__ hi,
+                                                     const float *__restrict__ lo, const int *__restrict__ arg_hi, float *__restrict__ maxc) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long b = e / N2C;
+        const int c = (int)(e % C);
+        const float q = qi[e];
+        maxc[e] = __ldg(arg_hi + b * C) >= 0 ? (q > 0.f ? q * __ldg(hi + b * C + c) : q * __ldg(lo + b * C + c)) : -1e10f;
     }
 }
 
@@ -500,10 +507,11 @@ struct PrepBwdArgs {
 };
 
 // backward of one standardised row: y (saved output), g = dL/dy  ->  dL/dx, in place in g
-__device__ __forceinline__ void standardise_row_bwd(float (&g)[PREP_MAXJ], const float (&y)[PREP_MAXJ], float den, int C, int lane) {
+template <int MJ>
+__device__ __forceinline__ void standardise_row_bwd(float (&g)[MJ], const float (&y)[MJ], float den, int C, int lane) {
     float sg = 0.f, sgy = 0.f;
 #pragma unroll
-    for (int j = 0; j < PREP_MAXJ; ++j) {
+    for (int j = 0; j < MJ; ++j) {
         const bool in = lane + 32 * j < C;
         sg += in ? g[j] : 0.f;
         sgy += in ? g[j] * y[j] : 0.f;
@@ -514,10 +522,11 @@ __device__ __forceinline__ void standardise_row_bwd(float (&g)[PREP_MAXJ], const
     // the clipped denominator is a constant: only the mean's term remains
     const float k = den > 1e-12f ? sgy / (float)(C - 1) : 0.f;
 #pragma unroll
-    for (int j = 0; j < PREP_MAXJ; ++j) g[j] = (g[j] - mg - y[j] * k) / den;
+    for (int j = 0; j < MJ; ++j) g[j] = (g[j] - mg - y[j] * k) / den;
 }
 
-__global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_bwd_kernel(const PrepBwdArgs a) {
+template <int MJ>
+__global__ void __launch_bounds__(PREP_THREADS) cv_prep_bwd_kernel(const PrepBwdArgs a) {
     __shared__ float dhi_s[32 * PREP_MAXJ], dlo_s[32 * PREP_MAXJ];
     const int b = blockIdx.y, S = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = a.N, N2 = a.N2, C = a.C;
@@ -527,14 +536,14 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_bwd_kernel(const Prep
     if (use_max) {
         // d hi[c] = sum over the pixels with qi > 0 of d maxc * qi, d lo[c] over the others (every block of the cloud
         // computes them: N2 rows, cheaper than a second kernel)
-        float dh[PREP_MAXJ], dl[PREP_MAXJ];
+        float dh[MJ], dl[MJ];
 #pragma unroll
-        for (int j = 0; j < PREP_MAXJ; ++j) dh[j] = dl[j] = 0.f;
+        for (int j = 0; j < MJ; ++j) dh[j] = dl[j] = 0.f;
 #pragma unroll 4
         for (int k = warp; k < N2; k += PREP_WARPS) {
             const size_t row = ((size_t)b * N2 + k) * C;
 #pragma unroll
-            for (int j = 0; j < PREP_MAXJ; ++j) {
+            for (int j = 0; j < MJ; ++j) {
                 const int c = lane + 32 * j;
                 if (c < C) {
                     const float q = __ldg(a.qi + row + c), t = __ldg(a.d_maxc + row + c) * q;
@@ -543,7 +552,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_bwd_kernel(const Prep
             }
         }
 #pragma unroll
-        for (int j = 0; j < PREP_MAXJ; ++j) { atomicAdd(&dhi_s[lane + 32 * j], dh[j]); atomicAdd(&dlo_s[lane + 32 * j], dl[j]); }
+        for (int j = 0; j < MJ; ++j) { atomicAdd(&dhi_s[lane + 32 * j], dh[j]); atomicAdd(&dlo_s[lane + 32 * j], dl[j]); }
     }
     __syncthreads();
     for (int r = blockIdx.x * PREP_WARPS + warp; r < N + N2; r += S * PREP_WARPS) {
@@ -551,9 +560,9 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_bwd_kernel(const Prep
         const size_t row = point ? (size_t)b * N + r : (size_t)b * N2 + (r - N);
         const float *ysrc = (point ? a.pi : a.qi) + row * C;
         const float *gsrc = point ? a.d_pi : a.d_qi;
-        float y[PREP_MAXJ], g[PREP_MAXJ];
+        float y[MJ], g[MJ];
 #pragma unroll
-        for (int j = 0; j < PREP_MAXJ; ++j) {
+        for (int j = 0; j < MJ; ++j) {
             const int c = lane + 32 * j;
             const bool in = c < C;
             y[j] = in ? __ldg(ysrc + c) : 0.f;
@@ -571,7 +580,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 1) cv_prep_bwd_kernel(const Prep
         standardise_row_bwd(g, y, __ldg((point ? a.den_p : a.den_q) + row), C, lane);
         float *dst = (point ? a.d_pf : a.d_qf) + row * C;
 #pragma unroll
-        for (int j = 0; j < PREP_MAXJ; ++j)
+        for (int j = 0; j < MJ; ++j)
             if (lane + 32 * j < C) dst[lane + 32 * j] = g[j];
         if (point) {
             const float zz = __ldg(a.z + row);
@@ -723,8 +732,14 @@ int i2p_cv_prep_fwd(int B, int N, int N2, int C, int has_max, const float *uv, c
         a.scratch_arg = reinterpret_cast<int *>(scratch) + (size_t)B * S * 2 * C;
         a.tickets = reinterpret_cast<unsigned *>(scratch) + (size_t)B * S * 4 * C;
     }
-    cv_prep_fwd_kernel<<<dim3(S, B), PREP_THREADS, 0, as_stream(stream)>>>(a);
-    return check_launch("cv_prep_fwd");
+    if (C <= 64) cv_prep_fwd_kernel<2><<<dim3(S, B), PREP_THREADS, 0, as_stream(stream)>>>(a);
+    else if (C <= 128) cv_prep_fwd_kernel<4><<<dim3(S, B), PREP_THREADS, 0, as_stream(stream)>>>(a);
+    else cv_prep_fwd_kernel<PREP_MAXJ><<<dim3(S, B), PREP_THREADS, 0, as_stream(stream)>>>(a);
+    int rc = check_launch("cv_prep_fwd");
+    if (rc != I2P_OK || !has_max) return rc;
+    const long long total = (long long)B * N2 * C, gr = (total + 255) / 256;
+    cv_maxc_kernel<<<(int)(gr < 148 * 8 ? gr : 148 * 8), 256, 0, as_stream(stream)>>>(total, N2 * C, C, qi, hi, lo, arg_hi, maxc);
+    return check_launch("cv_prep_fwd(maxc)");
 }
 
 int i2p_cv_prep_bwd(int B, int N, int N2, int C, int has_max, const float *uv, const float *z, const float *pi, const float *qi,
@@ -735,7 +750,10 @@ int i2p_cv_prep_bwd(int B, int N, int N2, int C, int has_max, const float *uv, c
     I2P_REQUIRE(B >= 0 && N >= 1 && N2 >= 1 && C >= 2 && C <= 32 * PREP_MAXJ && B <= 65535, "cv_prep_bwd: bad sizes (2 <= C <= 256)");
     if (B == 0) return I2P_OK;
     PrepBwdArgs a{N, N2, C, has_max ? 1 : 0, uv, z, pi, qi, den_p, den_q, hi, lo, arg_hi, arg_lo, d_xyz, d_pi, d_qi, d_maxc, d_uv, d_z, d_pf, d_qf};
-    cv_prep_bwd_kernel<<<dim3(prep_blocks(N + N2), B), PREP_THREADS, 0, as_stream(stream)>>>(a);
+    const dim3 grid(prep_blocks(N + N2), B);
+    if (C <= 64) cv_prep_bwd_kernel<2><<<grid, PREP_THREADS, 0, as_stream(stream)>>>(a);
+    else if (C <= 128) cv_prep_bwd_kernel<4><<<grid, PREP_THREADS, 0, as_stream(stream)>>>(a);
+    else cv_prep_bwd_kernel<PREP_MAXJ><<<grid, PREP_THREADS, 0, as_stream(stream)>>>(a);
     return check_launch("cv_prep_bwd");
 }
 
