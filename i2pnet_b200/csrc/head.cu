@@ -138,7 +138,7 @@ struct HeadBwdArgs {
 // grid (B, HEAD_SPLIT): the blocks of a sample all rebuild the (tiny) head gradients, then share the expensive parts --
 // the Hd x C outer product for dW1 and the N x C element-wise tail -- by slices.
 constexpr int HEAD_SPLIT = 4;
-constexpr int HEAD_BWD_THREADS = 256;
+constexpr int HEAD_BWD_THREADS = 1024;   // (same reasoning as the forward: dependent passes of a few KB per block)
 
 __global__ void __launch_bounds__(HEAD_BWD_THREADS) pose_head_bwd_kernel(const HeadBwdArgs a) {
     __shared__ float d7[8], dhid[HEAD_MAXH], dpool[HEAD_MAXC], pooled[HEAD_MAXC], part[HEAD_BWD_THREADS / 32][HEAD_MAXC];
@@ -189,7 +189,10 @@ __global__ void __launch_bounds__(HEAD_BWD_THREADS) pose_head_bwd_kernel(const H
     {
         const int G = HEAD_BWD_THREADS / C, k = tid % C, gq = tid / C;
         float v = 0.f;
-        if (gq < G) for (int h = gq; h < Hd; h += G) v = __fmaf_rn(__ldg(a.w1 + (size_t)h * C + k), dhid[h], v);
+        if (gq < G) {
+#pragma unroll 8
+            for (int h = gq; h < Hd; h += G) v = __fmaf_rn(__ldg(a.w1 + (size_t)h * C + k), dhid[h], v);
+        }
         if (gq < G) part[gq][k] = v;
         __syncthreads();
         if (tid < C) {
