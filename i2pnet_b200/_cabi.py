@@ -43,6 +43,7 @@ _SIGNATURES = {
     "i2p_fused_conv_select_k": [_int] * 8 + [_flt, _int, _int] + [_vp] * 8 + [_int, _int, _vp],
     "i2p_select_k_flat": [_int] * 8 + [_flt, _int, _int] + [_vp] * 3 + [_int] * 3 + [_vp] * 2 + [_int, _int, _vp],
     "i2p_gather_rows": [_int] * 4 + [_vp] * 4,
+    "i2p_sa_geometry": [_int] * 4 + [_vp] * 6,
     "i2p_gather_rows_grad": [_int] * 4 + [_vp] * 4,
     "i2p_knn_point": [_int] * 4 + [_vp] * 5,
     "i2p_project_seq": [_int] * 4 + [_flt, _flt, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -121,6 +121,28 @@ __global__ void __launch_bounds__(G_THREADS) gather_rows_kernel(long long total,
     }
 }
 
+// First-level set-abstraction operand (ProjectPointNet.forward_center, src/projectPN/PPBackbone_center.py:150-178):
+// out[b,j,k,:] = [ g - c (3) | centre (3) | g (3) | |g - c| (1) ],  g = src[b, idx[b,j,k]], c = ctr[b,j], centre = cen[b,j]:
+// gather, subtraction, broadcast, vector norm and concatenation (five launches, four passes over the 37 MB result at
+// batch 8) as one pass.  Thread per (b, j, k) row: ten consecutive floats.
+__global__ void __launch_bounds__(G_THREADS) sa_geometry_kernel(long long rows, int hw, int n, int K, const float *__restrict__ src,
+                                                                const float *__restrict__ ctr, const float *__restrict__ cen,
+                                                                const int32_t *__restrict__ idx, float *__restrict__ out) {
+    for (long long r = (long long)blockIdx.x * G_THREADS + threadIdx.x; r < rows; r += (long long)gridDim.x * G_THREADS) {
+        const long long bj = r / K, b = bj / n;
+        const float *g = src + (b * hw + __ldg(idx + r)) * 3, *c = ctr + bj * 3, *e = cen + bj * 3;
+        const float gx = __ldg(g), gy = __ldg(g + 1), gz = __ldg(g + 2);
+        const float dx = __fsub_rn(gx, __ldg(c)), dy = __fsub_rn(gy, __ldg(c + 1)), dz = __fsub_rn(gz, __ldg(c + 2));
+        const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        float2 *o = reinterpret_cast<float2 *>(out + r * 10);      // 40-byte rows: 8-byte aligned
+        o[0] = make_float2(dx, dy);
+        o[1] = make_float2(dz, __ldg(e));
+        o[2] = make_float2(__ldg(e + 1), __ldg(e + 2));
+        o[3] = make_float2(gx, gy);
+        o[4] = make_float2(gz, d);
+    }
+}
+
 __device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
 __device__ __forceinline__ void red_add(float4 *p, float4 v) { atomicAdd(p, v); }  // red.global.add.v4.f32
 
@@ -229,6 +251,17 @@ int i2p_gather_rows(int b, int hw, int c, int m, const float *feature, const int
                                                                                         flat_idx, out);
     }
     return check_launch("gather_rows");
+}
+
+int i2p_sa_geometry(int b, int hw, int n, int k, const float *src, const float *ctr, const float *cen, const int32_t *flat_idx,
+                    float *out, void *stream) {
+    using namespace i2p;
+    I2P_REQUIRE(b >= 0 && hw >= 1 && n >= 0 && k >= 1, "sa_geometry: bad sizes");
+    I2P_REQUIRE((reinterpret_cast<uintptr_t>(out) & 7) == 0, "sa_geometry: out must be 8-byte aligned");
+    const long long rows = (long long)b * n * k;
+    if (rows == 0) return I2P_OK;
+    sa_geometry_kernel<<<rows_grid(rows), G_THREADS, 0, as_stream(stream)>>>(rows, hw, n, k, src, ctr, cen, flat_idx, out);
+    return check_launch("sa_geometry");
 }
 
 int i2p_gather_rows_grad(int b, int hw, int c, int m, const float *grad_out, const int32_t *flat_idx,

@@ -197,6 +197,9 @@ class ProjectPointNet(nn.Module):
         channels (+ feature_proj when using_intens).  The reference also gathers feature_proj when
         it is not used (:157); this does not."""
         B = xyz_proj.shape[0]
+        needs_grad = torch.is_grad_enabled() and (xyz_proj.requires_grad or xyz_proj_raw.requires_grad)
+        if USE_FUSED_SA_GEOMETRY and xyz_proj.is_cuda and xyz_proj.dtype == torch.float32 and not using_intens and not needs_grad:
+            return self._forward_center_fused(xyz_proj_raw, xyz_proj, sample_idx, raw_feat_point)
         sample_idx, new_raw, new_xyz, flat, grouped_xyz, norm = self._group(xyz_proj_raw, xyz_proj, sample_idx,
                                                                             raw_feat_point)
         centre = new_xyz.reshape(B, self.out_h * self.out_w, 1, 3).expand(-1, -1, norm.shape[2], -1)
@@ -206,6 +209,27 @@ class ProjectPointNet(nn.Module):
             parts.append(gather_rows(feature_proj, flat))
         new_points = self._mlp_max(torch.cat(parts, -1), B)
         return new_raw, new_xyz, new_points, grouped_xyz, sample_idx
+
+    def _forward_center_fused(self, xyz_proj_raw, xyz_proj, sample_idx, raw_feat_point):
+        """forward_center with the ten geometric channels written by one kernel (csrc/gather.cu sa_geometry) instead of
+        gather + subtract + broadcast + norm + concatenate; the coordinates carry no gradient at the first level."""
+        from .. import _cabi
+        B, n, K = xyz_proj.shape[0], self.out_h * self.out_w, self.nsample
+        dev, f32 = xyz_proj.device, torch.float32
+        sample_idx = _centres(sample_idx, B, self.out_h, self.out_w, self.stride_H, self.stride_W, dev)
+        new_xyz = _take_centres(xyz_proj, sample_idx, B, self.H, self.W)
+        new_raw = _take_centres(xyz_proj_raw, sample_idx, B, self.H, self.W)
+        xyz_pr = xyz_proj if self.usetrans else xyz_proj_raw
+        flat, _ = select_flat(xyz_pr, xyz_pr, _centre_index(sample_idx, B, self.out_h, self.out_w),
+                              self.kernel_size, self.nsample, FLAG_SHIFT | FLAG_COPY, self.distance)
+        src, ctr = (xyz_proj_raw, new_raw) if raw_feat_point else (xyz_proj, new_xyz)
+        src, ctr, cen = src.detach().contiguous(), ctr.detach().contiguous(), new_xyz.detach().contiguous()
+        flat = flat.contiguous()
+        operand = torch.empty(B, n, K, 10, dtype=f32, device=dev)
+        _cabi.call("i2p_sa_geometry", dev, B, self.H * self.W, n, K, _cabi._ptr(src, f32, "xyz", dev), _cabi._ptr(ctr, f32, "centres", dev),
+                   _cabi._ptr(cen, f32, "centres", dev), _cabi._ptr(flat, torch.int32, "neighbour index", dev), operand.data_ptr())
+        new_points = self._mlp_max(operand, B)
+        return new_raw, new_xyz, new_points, operand[..., 6:9], sample_idx
 
     def set_bn(self):
         for conv in self.mlp_convs:
@@ -264,6 +288,7 @@ class ProjSetUpconvModule(nn.Module):
             conv.set_bn()
 
 
+USE_FUSED_SA_GEOMETRY = True   # False: the first level's geometric operand through gather / subtract / norm / concatenate
 USE_FUSED_CV = True   # False: the reference's broadcast / mask / concatenate / softmax formulation through ATen
 
 

@@ -111,6 +111,11 @@ int i2p_select_k_flat(int batch, int H, int W, int npoints, int kH, int kW, int 
  * (B,M) int32 -> out (B,M,C).  Backward: grad_feature (B,HW,C) += scatter of grad_out. */
 int i2p_gather_rows(int b, int hw, int c, int m, const float *feature, const int32_t *flat_idx, float *out,
                     void *stream);
+/* First-level set-abstraction operand (ProjectPointNet.forward_center, src/projectPN/PPBackbone_center.py:150-178) in one
+ * pass: out (b, n, k, 10) = [ g - c | centre | g | |g - c| ], g = src (b,hw,3)[idx (b,n,k)], c = ctr (b,n,3), centre = cen (b,n,3).
+ * Forward only (the level-1 coordinates are data). */
+int i2p_sa_geometry(int b, int hw, int n, int k, const float *src, const float *ctr, const float *cen, const int32_t *flat_idx,
+                    float *out, void *stream);
 int i2p_gather_rows_grad(int b, int hw, int c, int m, const float *grad_out, const int32_t *flat_idx,
                          float *grad_feature, void *stream);
 

@@ -191,3 +191,50 @@ def check_iter_model(device, knn_flip_tol=None, pin_knn_sets=False):
 
 def test_iter_model_host_logic_matches_reference(oracle_backend):
     check_iter_model("cpu")
+
+
+def test_pixel_rays_and_pyramid_shape_host_spelling():
+    """pixel_rays (host spelling) = change_intrinsic -> inverse -> set_id_grid -> batched product of the reference
+    (src/modellearn_proj_center.py:275-287); pyramid_out_hw predicts the feature-map size the pyramids produce."""
+    from i2pnet_b200.modellearn_proj_center import change_intrinsic, set_id_grid
+    from i2pnet_b200.modules.basicConv import createCNNs, pyramid_out_hw
+    from i2pnet_b200.projectPN.utils import pixel_rays
+    torch.manual_seed(0)
+    nets = (createCNNs(3, [4, 4, 8], [2, 1, 2]), createCNNs(8, [8, 8], [2, 2]), createCNNs(8, [8], [1]))
+    x = torch.randn(2, 3, 37, 50)
+    y = x
+    with torch.no_grad():
+        for n in nets:
+            y = n(y)
+    assert tuple(y.shape[2:]) == pyramid_out_hw(nets, 37, 50)
+    K = torch.tensor([[700.0, 0.0, 25.0], [0.0, 650.0, 18.0], [0.0, 0.0, 1.0]]).repeat(2, 1, 1)
+    K[1, 0, 2] += 2.5
+    h, w = y.shape[2:]
+    rays = pixel_rays(K, h, w, 37, 50)
+    K3 = change_intrinsic(K.double(), y.double(), x)
+    ref = torch.bmm(torch.linalg.inv(K3), set_id_grid(y.double().permute(0, 2, 3, 1)).permute(0, 2, 1)).permute(0, 2, 1)
+    assert rays.shape == (2, h * w, 3) and torch.allclose(rays.double(), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_rigid_warp_host_spelling_is_the_reference_composition():
+    """rigid_warp on CPU tensors is warp_quat_xyz (src/modules/warp_utils.py:78-94) times check_valid; N = 1 is the pose
+    composition t = R(q3) t_in + t3 of src/modellearn_proj_center.py:414-421."""
+    from i2pnet_b200.modules import warp_utils as W
+    from i2pnet_b200.projectPN.utils import check_valid
+    torch.manual_seed(1)
+    p, q, t = torch.randn(2, 9, 3), torch.randn(2, 4), torch.randn(2, 3)
+    p[:, 2] = 0
+    ref = W.warp_quat_xyz(p, q, torch.cat([torch.zeros(2, 1), t], -1))
+    assert torch.equal(W.rigid_warp(p, q, t), ref)
+    assert torch.equal(W.rigid_warp(p, q, t, mask_invalid=True), ref * check_valid(p))
+    tq = torch.cat([torch.zeros(2, 1), p[:, 0]], 1).view(2, 1, 4)
+    comp = (W.mul_q(W.mul_q(q, tq), W.inv_q(q)) + torch.cat([torch.zeros(2, 1), t], 1).view(2, 1, 4)).squeeze(1)[:, 1:]
+    assert torch.allclose(W.rigid_warp(p[:, :1], q, t).view(2, 3), comp, atol=1e-6)
+
+
+def test_step_scratch_is_plain_zeros_without_an_engine():
+    from i2pnet_b200 import scratch
+    scratch.begin_step("cpu")             # no arena on the host: a no-op
+    z = scratch.zeros((2, 3), torch.float32, "cpu")
+    scratch.end_step()
+    assert z.shape == (2, 3) and z.dtype == torch.float32 and float(z.abs().sum()) == 0.0

@@ -136,3 +136,31 @@ def test_reference_python_runs_unchanged_on_dropin_modules():
              "three_interpolate_wrapper", "three_interpolate_grad_wrapper", "knn_wrapper"]
     assert all(callable(getattr(pointnet2_cuda, n)) for n in names)
     assert callable(fused_conv_select_k_cuda.fused_conv_select_k)
+
+
+def test_first_level_geometry_operand_one_kernel():
+    """ProjectPointNet.forward_center with the ten geometric channels from csrc/gather.cu sa_geometry against the
+    gather / subtract / broadcast / norm / concatenate formulation (src/projectPN/PPBackbone_center.py:150-178): identical
+    neighbour coordinates, features within f32 rounding of the vector norm, for both coordinate sources."""
+    from i2pnet_b200.projectPN import PPBackbone_center as P
+    from i2pnet_b200.projectPN.utils import project_seq
+    from i2pnet_b200.synthetic import make_pairs
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    d = make_pairs(2, seed=11, occupy_centres=(4, 8))
+    raw, (cam,) = project_seq(d["raw_point_xyz"].to(dev), [d["lidar"].to(dev)], 64, 1800, False)
+    net = P.ProjectPointNet(64, 1800, 16, 225, 4, 8, [9, 15], 32, 0.75, 10, [16, 16, 32]).to(dev)
+    for raw_feat_point in (False, True):
+        res = {}
+        for fused in (True, False):
+            P.USE_FUSED_SA_GEOMETRY = fused
+            try:
+                with torch.no_grad():
+                    res[fused] = net.forward_center(raw, cam, None, raw_feat_point=raw_feat_point)
+            finally:
+                P.USE_FUSED_SA_GEOMETRY = True
+        new_raw_f, new_xyz_f, feat_f, grouped_f, _ = res[True]
+        new_raw_a, new_xyz_a, feat_a, grouped_a, _ = res[False]
+        assert torch.equal(new_raw_f, new_raw_a) and torch.equal(new_xyz_f, new_xyz_a)
+        assert torch.equal(grouped_f, grouped_a)
+        assert float((feat_f - feat_a).abs().max()) <= 2e-5 * float(feat_a.abs().max())
