@@ -134,7 +134,7 @@ class _ConvBlock(Function):
         # weight gradient: nobody but the optimiser reads it -> side stream, joined at the end of the backward pass
         sink_w = grad_sink(ctx.params[0])
         gw = gb = None
-        with _streams.Fork(dy, x, kind="wgrad") as branch:
+        with _streams.Fork(dy, x, kind="cwgrad") as branch:
             if sink_w is None:
                 gw = torch.zeros_like(w)
             call("i2p_conv3x3_wgrad", dev, B, Cin, Cout, H, W, x.data_ptr(), dy.data_ptr(),

@@ -32,9 +32,10 @@ _pools = {}
 # second, weight gradients (consumed by nobody before the optimiser) last.  Captured kernel nodes keep the priority
 # of the stream they were captured on.  I2P_STREAM_PRIORITIES=0: all streams at the default priority.
 PRIORITIES = os.environ.get("I2P_STREAM_PRIORITIES", "1") != "0"
-_PRIORITY = {"branch": -2, "main": -1, "wgrad": 0}
-if os.environ.get("I2P_STREAM_PRIORITY_LEVELS"):        # tuning override: "branch,main,wgrad", e.g. "-2,-1,-1"
-    _PRIORITY = dict(zip(("branch", "main", "wgrad"), (int(v) for v in os.environ["I2P_STREAM_PRIORITY_LEVELS"].split(","))))
+_PRIORITY = {"branch": -2, "main": -1, "wgrad": 0, "cwgrad": 0}     # cwgrad: the image pyramid's weight gradients
+if os.environ.get("I2P_STREAM_PRIORITY_LEVELS"):        # tuning override: "branch,main,wgrad[,cwgrad]", e.g. "-2,-1,-1"
+    _lv = [int(v) for v in os.environ["I2P_STREAM_PRIORITY_LEVELS"].split(",")]
+    _PRIORITY = dict(zip(("branch", "main", "wgrad", "cwgrad"), _lv + _lv[2:3] * (4 - len(_lv))))
 
 
 def priority_of(kind):
