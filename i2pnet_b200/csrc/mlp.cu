@@ -1007,7 +1007,7 @@ static int g_mlp_tc = -1;
 static int mlp_tc_mask() {
     if (g_mlp_tc < 0) {
         const char *e = getenv("I2P_MLP_TC");
-        g_mlp_tc = (e == nullptr) ? 55 : atoi(e);
+        g_mlp_tc = (e == nullptr) ? 119 : atoi(e);
     }
     return g_mlp_tc;
 }

@@ -147,7 +147,9 @@ int i2p_project_seq(int b, int n, int H, int W, float fup_deg, float fdown_deg, 
  * below; the host consults this mask), 8 = the first-generation forward kernel inside i2p_pw_linear_fwd.
  * 16 = SWIZZLE_128B operand tiles + bulk-copied (TMA engine) weights in the forward / dX kernels.
  * 32 = the host also sends max-over-k gradient sources (dout + arg-max) to the tensor-core dX / dW kernels.
- * Default: environment variable I2P_MLP_TC, else 55 (= 7 | 16 | 32).  0 = f32 FMA kernels everywhere. */
+ * 64 = (with 16) two MMAs per k-step instead of three in the forward / dX kernels: A_hi x [B_hi | B_lo] as one MMA of
+ *      N = 2 BN, the correction terms in their own accumulator (one thread issues ~120 cycles per MMA whatever its N).
+ * Default: environment variable I2P_MLP_TC, else 119 (= 7 | 16 | 32 | 64).  0 = f32 FMA kernels everywhere. */
 void i2p_set_mlp_tensor_cores(int mask);
 int i2p_get_mlp_tensor_cores(void);
 /* Number of 128-row tiles (rows of the tile_stats buffer). */
