@@ -287,12 +287,12 @@ namespace i2p {
 //               is below ((rho - 0.01) * smallest cell width)^2: every point not yet visited is further than that.
 //               The k best are kept ordered by (distance, index), the order of the brute-force scans.
 // Distances are computed by the same expression as the brute-force kernels, so outputs are bit-identical.  The 0.1 % /
-// 1 % margins cover the rounding of the cell computation (relative 1e-5 of a cell at most).
+// 1 % margins cover the rounding of the cell computation (at most ~1e-4 of a cell: up to 1024 cells per axis in f32).
 constexpr int BG_MAXDIM = 1024, BG_MAXCELLS = 1 << 18;
 constexpr int BG_MAXNS = 64;    // ball query: nsample kept per thread
 constexpr int BG_MAXK = 32;
 
-struct GridBox { unsigned lo[3], hi[3]; };     // order-preserving unsigned images of the float bounds
+struct GridBox { unsigned lo[3], hi[3]; };     // order-preserving unsigned images of the float bounds (lo: its complement, see bg_bbox_kernel)
 
 __device__ __forceinline__ unsigned f2ord(float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
