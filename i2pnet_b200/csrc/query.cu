@@ -281,12 +281,12 @@ namespace i2p {
 // The reference kernels scan all N points per query.  For larger clouds the points are binned into the cells of a
 // uniform grid over the cloud's bounding box (counting sort: bounding box, count, scan, scatter -- four small kernels;
 // the sorted copy carries the original index in .w), and a query visits only nearby cells:
-//   ball query  cells no smaller than 1.001 r, the 27 cells around the query's own, keeping the nsample SMALLEST
+//   ball query  cells no smaller than 1.002 r, the 27 cells around the query's own, keeping the nsample SMALLEST
 //               indices inside the radius -- the reference's "first nsample in index order";
 //   k-NN, 3-NN  shells of cells of growing Chebyshev radius rho around the query's cell until the k-th best distance
 //               is below ((rho - 0.01) * smallest cell width)^2: every point not yet visited is further than that.
 //               The k best are kept ordered by (distance, index), the order of the brute-force scans.
-// Distances are computed by the same expression as the brute-force kernels, so outputs are bit-identical.  The 0.1 % /
+// Distances are computed by the same expression as the brute-force kernels, so outputs are bit-identical.  The 0.2 % /
 // 1 % margins cover the rounding of the cell computation (at most ~1e-4 of a cell: up to 1024 cells per axis in f32).
 constexpr int BG_MAXDIM = 1024, BG_MAXCELLS = 1 << 18;
 constexpr int BG_MAXNS = 64;    // ball query: nsample kept per thread
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(128) bg_ball_kernel(int n, int m, int max_cell
 static int ball_query_grid(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int32_t *idx,
                            cudaStream_t s) {
     CellList cl, ql;
-    int rc = cell_list_build(cl, b, n, xyz, radius * 1.001f, 0.f, nullptr, s, "ball_query");
+    int rc = cell_list_build(cl, b, n, xyz, radius * 1.002f, 0.f, nullptr, s, "ball_query");
     if (rc != I2P_OK) return rc;
     if (sort_queries(m, 0) && (rc = cell_list_build(ql, b, m, new_xyz, 0.f, 0.f, &cl, s, "ball_query")) != I2P_OK) { cudaFreeAsync(cl.ws, s); return rc; }
     bg_ball_kernel<<<dim3(ceil_div(m, 128), b), 128, 0, s>>>(n, m, cl.max_cells, radius, radius * radius, nsample, new_xyz, cl.dims, cl.starts,
