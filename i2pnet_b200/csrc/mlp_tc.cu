@@ -971,9 +971,9 @@ int i2p_pw_linear_bwd_dw_tc(int rows, int cin, int cout, const float *g_dense, c
     const int bn = cout <= 64 ? 64 : 128;
     const int mt = ceil_div(cin, tc::BM), ntl = ceil_div(cout, bn);
     // about two waves of CTAs (2 resident per SM), at least 8 chunks of rows per CTA
-    static int waves = -1;     // I2P_DW_WAVES: tuning override (shorter CTAs let the block scheduler interleave the step's chain kernels)
-    if (waves < 0) { const char *e = getenv("I2P_DW_WAVES"); waves = e ? atoi(e) : 2; if (waves < 1) waves = 1; }
-    int chunks = (waves * 2 * 148 + mt * ntl - 1) / (mt * ntl);
+    static int ctas = -1;      // I2P_DW_CTAS: tuning override of the CTA count aimed at (default: two waves at two CTAs per SM)
+    if (ctas < 0) { const char *e = getenv("I2P_DW_CTAS"); ctas = e ? atoi(e) : 2 * 2 * 148; if (ctas < 1) ctas = 1; }
+    int chunks = (ctas + mt * ntl - 1) / (mt * ntl);
     int rpb = (rows + chunks - 1) / chunks;
     rpb = ((rpb + tc::BK - 1) / tc::BK) * tc::BK;
     if (rpb < 8 * tc::BK) rpb = 8 * tc::BK;
